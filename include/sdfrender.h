@@ -1,0 +1,159 @@
+/*
+ * sdfrender.h -- C ABI of libsdfrender.so, the B200 (sm_100a) differentiable depth
+ * renderer for discretised signed distance fields.
+ *
+ * This is the drop-in boundary for the one hot path of roym899/sdfest: it replaces the
+ * pybind11 module `sdf_renderer_cpp` that the reference JIT-builds from
+ *   sdfest/differentiable_renderer/csrc/sdf_renderer.cpp      (forward :42-61, backward :63-86,
+ *                                                              module def :88-91)
+ *   sdfest/differentiable_renderer/csrc/sdf_renderer_cuda.cu  (launchers :472-556, kernels :241-468)
+ * and is bound from Python with ctypes (sdfest_b200/_lib.py; INTEGRATION.md shows the stub a
+ * reference maintainer would add to sdf_renderer.py:21-28, 311, 347).
+ *
+ * Conventions (identical to the reference unless stated)
+ *   - every pointer is a DEVICE pointer to contiguous float32 (int32 where stated) memory on
+ *     the CURRENT CUDA device; the library never allocates, frees, or synchronises; all work is
+ *     enqueued on `stream` (a cudaStream_t passed as void*, NULL = legacy default stream) and is
+ *     CUDA-graph capturable.  (The reference allocates its outputs with ATen and launches on the
+ *     legacy default stream: sdf_renderer_cuda.cu:484, 495, 525-528, 536.)
+ *   - sdf: `resolution`^3 grid(s), index order x,y,z with z contiguous (sdf_renderer_cuda.cu:13,
+ *     226-238).  Any resolution >= 2 (the reference kernels hard-code 64: :225-230, 327, 347).
+ *     Hypothesis b reads the grid at sdf + b*sdf_stride (elements); sdf_stride = 0 shares one grid.
+ *   - position [batch,3], orientation [batch,4] (x,y,z,w; must be unit length -- not normalised,
+ *     sdf_renderer_cuda.cu:95-98 is never instantiated), inv_scale [batch]: pose of the grid in the
+ *     OpenGL camera frame (camera looks down -z, y up; image row 0 is the top row).
+ *   - cx, cy, fx, fy: pinhole parameters in the pixel-centre-0.5 convention
+ *     (Camera.get_pinhole_camera_parameters(0.5), sdf_renderer.py:116-133, 310).
+ *     NOTE the argument order cx, cy, fx, fy of the reference binding (sdf_renderer.cpp:48-51).
+ *   - depth [batch,height,width]: 0 = no surface, else positive z-distance; the kernels write
+ *     every element (no pre-zeroing needed; the reference relies on torch::zeros, :484).
+ *   - gradients are ACCUMULATED (+=) into the output buffers; pass SDFR_ZERO_GRADS to have the
+ *     library clear the requested ones first (cudaMemsetAsync on `stream`).  Buffers whose flag is
+ *     not set may be NULL and are never touched (the reference always computes all four,
+ *     sdf_renderer.py:346-357).
+ *
+ * Return value: 0 on success; negative = argument error (SDFR_E_*); positive = cudaError_t
+ * reported by the launch.  sdfr_last_error() returns a thread-local description.
+ */
+#ifndef SDFRENDER_H_
+#define SDFRENDER_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFR_ABI_VERSION 1
+
+#define SDFR_E_NULL (-1)  /* a required pointer is NULL */
+#define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
+#define SDFR_E_FLAGS (-3) /* unknown flag bits */
+
+/* flags of the backward entry points */
+#define SDFR_GRAD_SDF 0x01u
+#define SDFR_GRAD_POSITION 0x02u
+#define SDFR_GRAD_ORIENTATION 0x04u
+#define SDFR_GRAD_INV_SCALE 0x08u
+#define SDFR_GRAD_ALL 0x0fu
+/* SDF-gradient corner weights: default = the list the reference CUDA kernel uses
+ * (sdf_renderer_cuda.cu:373-388, a permutation of the trilinear weights -- SURVEY.md Q2);
+ * with this flag = the true trilinear weights of the reference CPU renderer
+ * (simple_renderer.py:399-408). */
+#define SDFR_SDF_GRAD_EXACT 0x10u
+#define SDFR_ZERO_GRADS 0x20u /* clear the requested gradient buffers before accumulating */
+
+int sdfr_abi_version(void);
+const char* sdfr_last_error(void);
+/* "sm_100a;..." -- what the library was compiled for */
+const char* sdfr_build_info(void);
+/* upper bound on sphere-tracing steps per ray (the reference has none) */
+int sdfr_max_steps(void);
+
+/*
+ * Forward: replaces sdf_renderer_cpp.forward (sdf_renderer.cpp:42-61 ->
+ * sdf_renderer_cuda.cu:472-510 -> forward kernel :241-298), batched over `batch` hypotheses.
+ */
+int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, const float* position,
+                 const float* orientation, const float* inv_scale, int batch, int width,
+                 int height, float cx, float cy, float fx, float fy, float threshold,
+                 float* depth, void* stream);
+
+/*
+ * Same as sdfr_forward, additionally accumulating work counters into stats[4] (device,
+ * unsigned long long, caller-zeroed): [0] trilinear samples, [1] pixels whose ray enters the
+ * box, [2] hit pixels, [3] rays stopped by the step cap.  Used for the roofline's S and Hh.
+ */
+int sdfr_forward_stats(const float* sdf, int resolution, long long sdf_stride,
+                       const float* position, const float* orientation, const float* inv_scale,
+                       int batch, int width, int height, float cx, float cy, float fx, float fy,
+                       float threshold, float* depth, unsigned long long* stats, void* stream);
+
+/*
+ * Backward: replaces sdf_renderer_cpp.backward (sdf_renderer.cpp:63-86 ->
+ * sdf_renderer_cuda.cu:512-556 -> backward kernel :300-468), batched.
+ * grad_depth, depth: [batch,height,width].  grad_sdf: hypothesis b accumulates into
+ * grad_sdf + b*grad_sdf_stride (0 = all hypotheses into one grid).  grad_position [batch,3],
+ * grad_orientation [batch,4] (x,y,z,w), grad_inv_scale [batch].
+ */
+int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int resolution,
+                  long long sdf_stride, const float* position, const float* orientation,
+                  const float* inv_scale, int batch, int width, int height, float cx, float cy,
+                  float fx, float fy, float* grad_sdf, long long grad_sdf_stride,
+                  float* grad_position, float* grad_orientation, float* grad_inv_scale,
+                  unsigned flags, void* stream);
+
+/*
+ * Fused render-and-compare, forward: renders `batch` hypotheses and compares each with an
+ * observed depth map using the masked L1 of the reference pipeline
+ * (estimation/simple_setup.py:125-131):  overlap = (obs > 0) & (est > 0),
+ *   loss_sum[b] += sum_overlap |est - obs|,  n_overlap[b] += |overlap|   (both caller-zeroed
+ * unless SDFR_ZERO_GRADS is in `flags`), so that loss_depth[b] = loss_sum[b] / n_overlap[b].
+ * depth_obs: hypothesis b compares with depth_obs + b*obs_stride (0 = one shared map).
+ */
+int sdfr_compare_forward(const float* sdf, int resolution, long long sdf_stride,
+                         const float* position, const float* orientation,
+                         const float* inv_scale, int batch, int width, int height, float cx,
+                         float cy, float fx, float fy, float threshold, const float* depth_obs,
+                         long long obs_stride, float* depth, float* loss_sum, float* n_overlap,
+                         unsigned flags, void* stream);
+
+/*
+ * Fused render-and-compare, backward: gradient of  sum_b upstream[b] * loss_sum[b]/n_overlap[b]
+ * without materialising grad_depth:  g(pixel) = upstream[b] * sign(est - obs) / n_overlap[b] on
+ * overlap pixels (sign(0) = 0, as torch.abs), 0 elsewhere.  upstream may be NULL (= 1 for all b).
+ * Hypotheses with n_overlap[b] == 0 contribute nothing.
+ */
+int sdfr_compare_backward(const float* depth, const float* depth_obs, long long obs_stride,
+                          const float* n_overlap, const float* upstream, const float* sdf,
+                          int resolution, long long sdf_stride, const float* position,
+                          const float* orientation, const float* inv_scale, int batch,
+                          int width, int height, float cx, float cy, float fx, float fy,
+                          float* grad_sdf, long long grad_sdf_stride, float* grad_position,
+                          float* grad_orientation, float* grad_inv_scale, unsigned flags,
+                          void* stream);
+
+/*
+ * Multi-object frame: `n_objects` posed grids rendered into ONE depth map, per-pixel minimum
+ * positive depth; winner [height,width] int32 receives the index of the object that produced
+ * the pixel (-1 = none; ties go to the lowest index).  No counterpart in the reference (it
+ * renders one object per call); semantics are those of oracle.composite_min_depth.
+ */
+int sdfr_forward_composite(const float* sdf, int resolution, long long sdf_stride,
+                           const float* position, const float* orientation,
+                           const float* inv_scale, int n_objects, int width, int height,
+                           float cx, float cy, float fx, float fy, float threshold, float* depth,
+                           int* winner, void* stream);
+
+/* Backward of sdfr_forward_composite: every pixel back-propagates to its winner. */
+int sdfr_backward_composite(const float* grad_depth, const float* depth, const int* winner,
+                            const float* sdf, int resolution, long long sdf_stride,
+                            const float* position, const float* orientation,
+                            const float* inv_scale, int n_objects, int width, int height,
+                            float cx, float cy, float fx, float fy, float* grad_sdf,
+                            long long grad_sdf_stride, float* grad_position,
+                            float* grad_orientation, float* grad_inv_scale, unsigned flags,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFRENDER_H_ */
