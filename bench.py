@@ -1,0 +1,464 @@
+#!/usr/bin/env python
+"""Benchmark of the render-and-compare hot path (BASELINE.json metric / config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # this repo's sm_100a kernels
+    python bench.py --impl reference [...]                        # CPU reference arm (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...             # one rank per GPU, weak scaling
+
+A STEP is one pass of the hot path over one batch of synthetic input: `--hypotheses` (64) pose /
+shape hypotheses, each with its own 64^3 SDF grid, rendered at 640x480 (fx=fy=320, threshold
+0.005: estimation/configs/default.yaml:1-9), compared with one observed depth map through the
+masked L1 of the reference pipeline (estimation/simple_setup.py:125-131), and back-propagated to
+the SDF grids, positions, quaternions and inverse scales.  metric = pixels rendered forward+backward
+per second (all pixels of all hypotheses, misses included -- SURVEY.md section 8d).
+
+One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+W, H, FX, FY, CX, CY = 640, 480, 320.0, 320.0, 320.0, 240.0  # default.yaml:1-8 (pixel_center 0.5)
+R = 64
+THRESHOLD = 0.005
+METRIC = "depth-render fwd+bwd Mpix/s (640x480, 64^3)"
+UNIT = "Mpix/s"
+L2_FLUSH_BYTES = 256 << 20
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=50)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--hypotheses", type=int, default=64, help="hypotheses per GPU (weak scaling)")
+    p.add_argument("--cpu-sample", type=int, default=4,
+                   help="hypotheses per step rendered by the CPU reference arm / cpu_baseline")
+    p.add_argument("--no-ref-ext", action="store_true",
+                   help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+def workload_name(B):
+    return (f"C2: {B} pose/shape hypotheses x {W}x{H} depth, one {R}^3 fp32 SDF grid per hypothesis, "
+            "fused render + masked-L1 compare forward and backward (all four gradients)")
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks: sampled through NVML while the timed region runs
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference renderer on the host cores
+# ---------------------------------------------------------------------------------------------
+def cpu_step(oracle, grids, pos, quat, inv_s, obs, nthreads):
+    """Forward render + masked L1 + backward for every hypothesis in the sample."""
+    import numpy as np
+
+    total = 0.0
+    for b in range(grids.shape[0]):
+        d = oracle.render(grids[b], pos[b], quat[b], inv_s[b], W, H, CX, CY, FX, FY, THRESHOLD,
+                          nthreads=nthreads)
+        loss, g, n = oracle.l1_depth_loss(d, obs)
+        bw = oracle.render_backward(g.astype(np.float32), d, grids[b], pos[b], quat[b], inv_s[b],
+                                    W, H, CX, CY, FX, FY, sdf_grad_mode="reference",
+                                    nthreads=nthreads)
+        total += loss + float(bw["g_inv_scale"])
+    return total
+
+
+def cpu_inputs(sample):
+    from sdfest_b200 import synthetic as syn
+
+    hyp = syn.make_hypotheses(sample, seed=0)
+    grids = syn.hypothesis_grids(hyp["shape_param"], R, "cpu").numpy()
+    return grids, hyp["position"].numpy(), hyp["orientation"].numpy(), hyp["inv_scale"].numpy()
+
+
+def time_cpu(sample, steps, warmup):
+    import oracle
+
+    nthreads = os.cpu_count() or 1
+    grids, pos, quat, inv_s = cpu_inputs(sample)
+    obs = oracle.render(grids[0], pos[0], quat[0], inv_s[0], W, H, CX, CY, FX, FY, THRESHOLD,
+                        nthreads=nthreads)
+    for _ in range(warmup):
+        cpu_step(oracle, grids, pos, quat, inv_s, obs, nthreads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(oracle, grids, pos, quat, inv_s, obs, nthreads)
+    dt = time.perf_counter() - t0
+    mpix = sample * W * H * steps / dt / 1e6
+    return mpix, dt / steps * 1e3, nthreads
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20))
+    warmup = max(1, min(args.warmup, 3))
+    sample = args.cpu_sample
+    mpix, ms, cores = time_cpu(sample, steps, warmup)
+    desc = (f"{sample} of the {args.hypotheses} hypotheses of one step per timed step "
+            f"(forward + masked L1 + backward through oracle/liboracle.so, OpenMP over image rows)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.hypotheses), "sample": desc},
+        "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": ("the reference's CPU renderer is pure Python (simple_renderer.py, ~8 kpix/s) and "
+                 "cannot travel to the GPU box; this arm times its C restatement (oracle/) on all "
+                 "host cores"),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from sdfest_b200 import _lib, build
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, forward_stats, render_and_compare
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    distributed = world > 1
+    if distributed:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    build.build()
+    lib = _lib.lib()
+
+    B = args.hypotheses
+    cam = Camera(W, H, FX, FY, CX, CY, pixel_center=0.5)
+    hyp = syn.make_hypotheses(B, seed=rank, device=dev)
+    grids = syn.hypothesis_grids(hyp["shape_param"], R, dev)
+    pos, quat, inv_s = hyp["position"], hyp["orientation"], hyp["inv_scale"]
+    # observed depth = render of the unperturbed hypothesis of rank 0's seed
+    from sdfest_b200.differentiable_renderer import render_depth_batched
+
+    base = syn.make_hypotheses(1, seed=0, device=dev)
+    obs = render_depth_batched(syn.hypothesis_grids(base["shape_param"], R, dev), base["position"],
+                               base["orientation"], base["inv_scale"], THRESHOLD, cam)[0].contiguous()
+
+    stats = forward_stats(grids, pos, quat, inv_s, THRESHOLD, cam)
+    S, Hh_all = stats["samples"], stats["hit_pixels"]
+    P = W * H
+
+    depth = torch.empty(B, H, W, device=dev)
+    sums = torch.zeros(2, B, device=dev)
+    g_sdf = torch.empty_like(grids)
+    g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
+    gathered = torch.empty(world * B, device=dev) if distributed else None
+    loss = torch.empty(B, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    RRR = R * R * R
+    flags_b = _lib.GRAD_ALL | _lib.ZERO_GRADS
+
+    def fwd():
+        _lib.check(lib.sdfr_compare_forward(
+            grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
+            CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
+            sums[1].data_ptr(), _lib.ZERO_GRADS, stream), "sdfr_compare_forward")
+
+    def bwd():
+        _lib.check(lib.sdfr_compare_backward(
+            depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None, grids.data_ptr(), R,
+            RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, CX, CY, FX, FY,
+            g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
+            stream), "sdfr_compare_backward")
+
+    def step():
+        fwd()
+        bwd()
+        if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
+            torch.div(sums[0], sums[1], out=loss)
+            dist.all_gather_into_tensor(gathered, loss)
+
+    flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+
+    def flush_l2():
+        flush_buf.zero_()
+
+    def timed(fn, n, warm):
+        """Sum of per-call CUDA-event times (ms) over n calls, L2 flushed before every call."""
+        for _ in range(warm):
+            flush_l2()
+            fn()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+               for _ in range(n)]
+        for a, b in evs:
+            flush_l2()
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    with ClockSampler(local_rank) as clocks:
+        total_ms = timed(step, K, Wm)
+    if distributed:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * B * P * K / (total_ms * 1e-3) / 1e6
+    ms_per_step = total_ms / K
+
+    # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
+    fwd_ms = timed(fwd, K, 2) / K
+    bwd_ms = timed(bwd, K, 2) / K
+
+    # ---- end-to-end through the public API with host buffers --------------------------------
+    h_grids = grids.cpu().pin_memory()
+    h_pose = torch.cat([pos, quat, inv_s[:, None]], 1).cpu().pin_memory()
+    h_obs = obs.cpu().pin_memory()
+    h_out_small = torch.empty(B, 10, pin_memory=True)  # loss, n_overlap, 8 pose grads
+    h_out_gsdf = torch.empty(B, R, R, R, pin_memory=True)
+    d_grids = torch.empty_like(grids)
+    d_pose = torch.empty(B, 8, device=dev)
+    d_obs = torch.empty_like(obs)
+    h2d = h_grids.numel() * 4 + h_pose.numel() * 4 + h_obs.numel() * 4
+    d2h = h_out_small.numel() * 4 + h_out_gsdf.numel() * 4
+
+    def e2e_step():
+        d_grids.copy_(h_grids, non_blocking=True)
+        d_pose.copy_(h_pose, non_blocking=True)
+        d_obs.copy_(h_obs, non_blocking=True)
+        sdf = d_grids.requires_grad_(True)
+        p = d_pose[:, 0:3].contiguous().requires_grad_(True)
+        q = d_pose[:, 3:7].contiguous().requires_grad_(True)
+        s = d_pose[:, 7].contiguous().requires_grad_(True)
+        l, _, n = render_and_compare(sdf, p, q, s, d_obs, THRESHOLD, cam)
+        l.sum().backward()
+        small = torch.cat([l.detach()[:, None], n[:, None], p.grad, q.grad, s.grad[:, None]], 1)
+        h_out_small.copy_(small, non_blocking=True)
+        h_out_gsdf.copy_(sdf.grad, non_blocking=True)
+        d_grids.grad = None
+        d_grids.requires_grad_(False)
+        torch.cuda.current_stream().synchronize()  # the caller reads the host results
+
+    Ke = max(3, min(K, 20))
+    for _ in range(3):
+        e2e_step()
+    torch.cuda.synchronize()
+    if distributed:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if distributed:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * P * Ke / e2e_s / 1e6
+    e2e_check = float(h_out_small[:, 0].sum())
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    n_over = int(sums[1].sum().item())
+    fwd_bytes = 32 * S + 4 * P * B + 4 * RRR * B + 4 * Hh_all
+    bwd_bytes = 4 * P * B + 4 * Hh_all + 32 * n_over + 64 * n_over + 4 * RRR * B
+    peak, peak_src = measured_peaks()
+    dom = "forward" if fwd_ms >= bwd_ms else "backward"
+    dom_bytes, dom_ms = (fwd_bytes, fwd_ms) if dom == "forward" else (bwd_bytes, bwd_ms)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"sdfr_{dom}_kernel (compare)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+        "note": ("algorithmic bytes = SURVEY 8d formula (32 B per trilinear sample + compulsory "
+                 "image/grid traffic); the 32*S gather term is served by L1/L2, so frac is against "
+                 "the HBM copy peak, not a claim of HBM traffic"),
+        "kernels": {
+            "forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
+            "backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
+        },
+        "work": {"samples_S": S, "hit_pixels": Hh_all, "overlap_pixels_Hh": n_over,
+                 "box_pixels": stats["box_pixels"], "pixels": P * B},
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(B), "hypotheses_per_gpu": B, "width": W, "height": H,
+                   "resolution": R, "threshold": THRESHOLD, "sdf": "analytic mug grids, one per hypothesis",
+                   "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset, outside the event pair)",
+                   "collective": "all_gather of per-hypothesis losses" if distributed else "none"},
+        "hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
+        "roofline": roofline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": Ke, "api": "render_and_compare + autograd backward, pinned host buffers",
+                "checksum": e2e_check},
+        "gpu_launches": 2 * K,
+        "clocks": clocks.summary(),
+        "lib": lib.sdfr_build_info().decode(),
+    }
+
+    if not args.no_cpu_baseline:
+        try:
+            mpix, ms, cores = time_cpu(args.cpu_sample, 3, 1)
+            line["cpu_baseline"] = {
+                "value": mpix, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_sample} hypotheses x {W}x{H} fwd+L1+bwd per step, 3 steps (oracle/liboracle.so, OpenMP)"}
+        except Exception as e:  # the oracle is a checker, never required by the product path
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
+                                    "sample": f"unavailable: {e}"}
+
+    if not args.no_ref_ext:
+        try:
+            line["reference_cuda_ext"] = time_reference_extension(
+                torch, dev, grids, pos, quat, inv_s, obs, flush_l2, min(K, 10))
+        except Exception as e:
+            line["reference_cuda_ext"] = {"unavailable": str(e)[:200]}
+
+    print(json.dumps(line), flush=True)
+    if distributed:
+        dist.destroy_process_group()
+
+
+def time_reference_extension(torch, dev, grids, pos, quat, inv_s, obs, flush_l2, steps):
+    """The reference's own CUDA extension (compiled from /root/reference into oracle/_ref) on the
+    same GPU and the same step: per hypothesis forward, masked L1 in torch, backward -- the way
+    the reference pipeline drives it (simple_setup.py:432-456), one hypothesis at a time."""
+    from oracle import build_ref
+
+    ext = build_ref.load_module()
+    if ext is None:
+        raise RuntimeError("oracle/_ref/sdf_renderer_cpp.so not present")
+    B = grids.shape[0]
+
+    def ref_step():
+        for b in range(B):
+            sdf, p, q, s = grids[b], pos[b], quat[b], inv_s[b:b + 1]
+            (d,) = ext.forward(sdf, p, q, s, W, H, CX, CY, FX, FY, THRESHOLD)
+            mask = (obs > 0) & (d > 0)
+            g = torch.where(mask, torch.sign(d - obs), torch.zeros_like(d)) / mask.sum()
+            ext.backward(g, d, sdf, p, q, s, W, H, CX, CY, FX, FY)
+
+    for _ in range(2):
+        ref_step()
+    torch.cuda.synchronize()
+    ms = 0.0
+    for _ in range(steps):
+        flush_l2()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        ref_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms += a.elapsed_time(b)
+    ms /= steps
+    return {"value": B * W * H / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+            "what": "sdf_renderer_cpp.forward + torch masked-L1 + sdf_renderer_cpp.backward per hypothesis"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,78 @@
+"""ctypes binding of libsdfrender.so -- the only native entry point of the package.
+
+There is NO fallback: if the library is missing or a call fails, a RuntimeError is raised.
+Signatures mirror include/sdfrender.h one to one.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
+
+ABI_VERSION = 1
+
+GRAD_SDF = 0x01
+GRAD_POSITION = 0x02
+GRAD_ORIENTATION = 0x04
+GRAD_INV_SCALE = 0x08
+GRAD_ALL = 0x0F
+SDF_GRAD_EXACT = 0x10
+ZERO_GRADS = 0x20
+
+_P = c_void_p
+_CAM = [c_int, c_int, c_float, c_float, c_float, c_float]  # W, H, cx, cy, fx, fy
+_POSE = [_P, _P, _P]  # position, orientation, inv_scale
+_GRADS = [_P, c_longlong, _P, _P, _P]  # grad_sdf, grad_sdf_stride, g_pos, g_quat, g_inv_scale
+
+SIGNATURES = {
+    "sdfr_abi_version": (c_int, []),
+    "sdfr_last_error": (ctypes.c_char_p, []),
+    "sdfr_build_info": (ctypes.c_char_p, []),
+    "sdfr_max_steps": (c_int, []),
+    "sdfr_forward": (c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P]),
+    "sdfr_forward_stats": (
+        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+    "sdfr_backward": (
+        c_int, [_P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
+    "sdfr_compare_forward": (
+        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
+                c_uint, _P]),
+    "sdfr_compare_backward": (
+        c_int, [_P, _P, c_longlong, _P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS,
+                c_uint, _P]),
+    "sdfr_forward_composite": (
+        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+    "sdfr_backward_composite": (
+        c_int, [_P, _P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the native library; raises if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m sdfest_b200.build` "
+                "(needs nvcc; there is no CPU or PyTorch fallback for the renderer)")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = restype
+            fn.argtypes = argtypes
+        got = handle.sdfr_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError(f"libsdfrender ABI {got} != binding ABI {ABI_VERSION}; rebuild")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().sdfr_last_error().decode(errors="replace")
+        kind = "argument error" if rc < 0 else "CUDA error"
+        raise RuntimeError(f"{what} failed ({kind} {rc}): {msg}")

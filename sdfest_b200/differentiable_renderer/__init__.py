@@ -1,0 +1,17 @@
+"""Differentiable depth renderer for discretised SDFs, B200-native.
+
+Mirrors ``sdfest.differentiable_renderer`` (whose package exports ``Camera`` and
+``render_depth_gpu``, reference ``__init__.py:6-8``) and adds the batched entry points.
+"""
+from .sdf_renderer import (  # noqa: F401
+    Camera,
+    SDFRendererFunctionGPU,
+    forward_stats,
+    get_sdf_grad_mode,
+    render_and_compare,
+    render_depth,
+    render_depth_batched,
+    render_depth_composite,
+    render_depth_gpu,
+    set_sdf_grad_mode,
+)

@@ -1,0 +1,3 @@
+"""Batched render-and-compare loop driving the renderer (reference: estimation/simple_setup.py)."""
+from .hypotheses import HypothesisOptimizer, gather_losses, global_best, shard_range  # noqa: F401
+from .losses import depth_to_pointcloud, pc_loss  # noqa: F401

@@ -154,7 +154,32 @@ def run_scene(sr, name, sdf, position, orientation, inv_scale, width, height, fo
     assert hits > 0, "golden scene without a single hit is useless"
 
 
+def pc_loss_fixture():
+    """Golden vector for the caller-side point-cloud loss (estimation/losses.py:32-135)."""
+    import torch
+
+    sys.path.insert(0, REF)
+    from sdfest.estimation.losses import pc_loss
+
+    rng = np.random.default_rng(11)
+    sdf = torch.tensor(sdf_torus(16), dtype=torch.float64)
+    points = torch.tensor(rng.uniform(-0.33, 0.33, (200, 3)) + np.array([0.05, -0.03, -0.8]))
+    pos = torch.tensor([0.05, -0.03, -0.8], dtype=torch.float64, requires_grad=True)
+    quat = torch.tensor(shoemake(3) * 1.3, requires_grad=True)  # un-normalised on purpose
+    scale = torch.tensor(0.3, dtype=torch.float64, requires_grad=True)
+    sdf.requires_grad_(True)
+    val = pc_loss(points, pos, quat, scale, sdf)
+    val.abs().mean().backward()
+    np.savez_compressed(
+        os.path.join(HERE, "pcloss_torus16.npz"), sdf=sdf.detach().numpy(), points=points.numpy(),
+        position=pos.detach().numpy(), orientation=quat.detach().numpy(),
+        scale=scale.detach().numpy(), value=val.detach().numpy(), g_position=pos.grad.numpy(),
+        g_orientation=quat.grad.numpy(), g_scale=scale.grad.numpy(), g_sdf=sdf.grad.numpy())
+    print("pcloss_torus16: outside points", int((val == 0).sum().item()), "of", val.numel())
+
+
 def main():
+    pc_loss_fixture()
     sr = load_reference_renderer()
     # 1. sphere, identity pose, coarse grid
     run_scene(sr, "sphere_r16", sdf_sphere(16), [0.0, 0.0, -1.0], [0, 0, 0, 1], 1 / 0.4,

@@ -1,0 +1,83 @@
+"""The C-ABI library loads and exports every symbol include/sdfrender.h declares; argument
+validation works without a GPU (no kernel is launched by these calls)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from sdfest_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sdfrender.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.lib()
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdfr_[a-z_]+)\s*\(", text)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for s in ("sdfr_forward", "sdfr_backward", "sdfr_compare_forward", "sdfr_compare_backward",
+              "sdfr_forward_composite", "sdfr_backward_composite", "sdfr_forward_stats",
+              "sdfr_abi_version", "sdfr_last_error", "sdfr_build_info", "sdfr_max_steps"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for s in declared_symbols():
+        assert hasattr(raw, s), f"{s} declared in sdfrender.h but not exported"
+    assert set(declared_symbols()) == set(_lib.SIGNATURES), "ctypes binding out of sync with header"
+
+
+def test_version_and_build_info(lib):
+    assert lib.sdfr_abi_version() == _lib.ABI_VERSION
+    assert b"sm_100a" in lib.sdfr_build_info()
+    assert lib.sdfr_max_steps() >= 1024
+
+
+def test_flag_values_match_header():
+    text = open(HEADER).read()
+    for name, val in (("SDFR_GRAD_SDF", _lib.GRAD_SDF), ("SDFR_GRAD_POSITION", _lib.GRAD_POSITION),
+                      ("SDFR_GRAD_ORIENTATION", _lib.GRAD_ORIENTATION),
+                      ("SDFR_GRAD_INV_SCALE", _lib.GRAD_INV_SCALE),
+                      ("SDFR_SDF_GRAD_EXACT", _lib.SDF_GRAD_EXACT),
+                      ("SDFR_ZERO_GRADS", _lib.ZERO_GRADS)):
+        m = re.search(rf"#define {name} (0x[0-9a-f]+)u", text)
+        assert m and int(m.group(1), 16) == val
+
+
+def test_argument_errors_need_no_gpu(lib):
+    cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
+    # empty batch / empty image: success, nothing launched
+    assert lib.sdfr_forward(None, 4, 0, None, None, None, 0, *cam, 0.01, None, None) == 0
+    assert lib.sdfr_forward(None, 4, 0, None, None, None, 1, 0, 8, 4.0, 4.0, 4.0, 4.0, 0.01,
+                            None, None) == 0
+    # NULL inputs
+    assert lib.sdfr_forward(None, 4, 0, None, None, None, 1, *cam, 0.01, None, None) == -1
+    assert b"NULL" in lib.sdfr_last_error()
+    # bad resolution / negative sizes
+    assert lib.sdfr_forward(None, 1, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 4, 0, None, None, None, -1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 4, -5, None, None, None, 1, *cam, 0.01, None, None) == -2
+    # unknown flags in backward
+    assert lib.sdfr_backward(None, None, None, 4, 0, None, None, None, 0, *cam, None, 0, None,
+                             None, None, 0x8000, None) == -3
+    with pytest.raises(RuntimeError, match="argument error"):
+        _lib.check(-1, "sdfr_forward")
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libsdfrender.so"))
+    with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
+        _lib.lib()

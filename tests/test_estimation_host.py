@@ -1,0 +1,104 @@
+"""Host-side logic of the batched render-and-compare loop, on CPU: the batched pc_loss against
+a golden vector from the reference's own estimation/losses.py, observed-point lifting, and the
+hypothesis sharding / loss all-gather over a 2-rank gloo group."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sdfest_b200.differentiable_renderer import Camera
+from sdfest_b200.estimation import depth_to_pointcloud, gather_losses, global_best, pc_loss, shard_range
+from util import GOLDEN_DIR
+
+
+def test_pc_loss_matches_reference_golden():
+    z = np.load(os.path.join(GOLDEN_DIR, "pcloss_torus16.npz"))
+    t = lambda k, g=False: torch.tensor(z[k], dtype=torch.float64, requires_grad=g)
+    pos, quat, scale, sdf = t("position", True), t("orientation", True), t("scale", True), t("sdf", True)
+    val = pc_loss(t("points"), pos[None], quat[None], scale[None], sdf[None])
+    assert val.shape == (1, 200)
+    assert np.abs(val[0].detach().numpy() - z["value"]).max() < 1e-12
+    assert (val == 0).sum() == (z["value"] == 0).sum() > 0
+    val[0].abs().mean().backward()
+    for got, key in ((pos.grad, "g_position"), (quat.grad, "g_orientation"), (scale.grad, "g_scale"),
+                     (sdf.grad, "g_sdf")):
+        assert np.abs(got.numpy() - z[key]).max() <= 1e-10 * max(np.abs(z[key]).max(), 1e-30)
+
+
+def test_pc_loss_batches_are_independent():
+    z = np.load(os.path.join(GOLDEN_DIR, "pcloss_torus16.npz"))
+    t = lambda k: torch.tensor(z[k], dtype=torch.float32)
+    B = 3
+    pos = t("position")[None] + 0.01 * torch.arange(B)[:, None]
+    quat = t("orientation")[None].repeat(B, 1)
+    scale = t("scale").reshape(1).repeat(B) * torch.tensor([1.0, 1.1, 0.9])
+    shared = pc_loss(t("points"), pos, quat, scale, t("sdf")[None])
+    for b in range(B):
+        one = pc_loss(t("points"), pos[b:b + 1], quat[b:b + 1], scale[b:b + 1], t("sdf")[None])
+        assert torch.allclose(shared[b], one[0], atol=1e-6)
+
+
+def test_depth_to_pointcloud_opengl_convention():
+    cam = Camera(4, 3, 2.0, 2.0, 2.0, 1.5, pixel_center=0.5)  # -> cx=1.5, cy=1.0 at centre 0
+    depth = torch.zeros(3, 4)
+    depth[1, 3] = 2.0
+    depth[0, 0] = 1.0
+    pts = depth_to_pointcloud(depth, cam)
+    assert pts.shape == (2, 3)
+    # row-major order of nonzero(): (0,0) first
+    assert torch.allclose(pts[0], torch.tensor([(0 - 1.5) * 1.0 / 2, -(0 - 1.0) * 1.0 / 2, -1.0]))
+    assert torch.allclose(pts[1], torch.tensor([(3 - 1.5) * 2.0 / 2, -(1 - 1.0) * 2.0 / 2, -2.0]))
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 64, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, n_total, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = shard_range(n_total, rank, world)
+        losses = torch.arange(lo, hi, dtype=torch.float32) * 0.5 + 1.0
+        if rank == 1:
+            losses[0] = float("nan")  # a hypothesis without overlap must never win
+            losses[-1] = 0.25         # the global best lives on rank 1
+        full = gather_losses(losses)
+        idx, val = global_best(losses, lo)
+        q.put((rank, full.tolist(), idx, val))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n_total", [8, 7])
+def test_two_rank_gloo_gather_and_argmin(n_total):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + n_total
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [i * 0.5 + 1.0 for i in range(n_total)]
+    lo1 = shard_range(n_total, 1, 2)[0]
+    expect[-1] = 0.25
+    for rank, full, idx, val in out:
+        assert len(full) == n_total
+        for i, (a, b) in enumerate(zip(full, expect)):
+            assert (np.isnan(a) and i == lo1) or a == b
+        assert idx == n_total - 1 and val == 0.25

@@ -1,0 +1,122 @@
+"""The exact per-ray functions the sm_100a kernels inline (sdfest_b200/csrc/sdfr_core.cuh),
+compiled for the host with g++ and checked against the oracle -- no GPU needed.  Covers the
+arithmetic and the conservativeness of the projected-box rectangle culling; the warp/CTA glue
+(shuffles, atomics, barriers) is covered by the -m gpu tests."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from util import (default_camera, golden_names, load_golden, mug_sdf, sdf_box, sdf_sphere,
+                  sdf_torus, shoemake)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "host_emul", "emul.cpp")
+SO = os.path.join(HERE, "host_emul", "libemul.so")
+CORE = os.path.join(os.path.dirname(HERE), "sdfest_b200", "csrc", "sdfr_core.cuh")
+f32 = np.float32
+
+
+@pytest.fixture(scope="module")
+def emul():
+    if (not os.path.isfile(SO)
+            or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", SO])
+    return ctypes.CDLL(SO)
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_forward(lib, sdf, pos, quat, inv_scale, W, H, cam, thr, use_rect=1):
+    sdf = np.ascontiguousarray(sdf, f32)
+    pos, quat = np.asarray(pos, f32), np.asarray(quat, f32)
+    s = np.asarray([inv_scale], f32)
+    depth = np.empty((H, W), f32)
+    steps = np.empty((H, W), np.int32)
+    rect = np.zeros(4, np.int32)
+    cf = [ctypes.c_float(v) for v in (cam["cx"], cam["cy"], cam["fx"], cam["fy"], thr)]
+    lib.emul_forward(P(sdf), sdf.shape[0], P(pos), P(quat), P(s), W, H, *cf, P(depth), P(steps),
+                     P(rect), use_rect)
+    return depth, steps, rect
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_device_math_matches_oracle_on_golden(emul, name):
+    z = load_golden(name)
+    thr = float(z["threshold"])
+    depth, steps, _ = run_forward(emul, z["sdf"], z["position"], z["orientation"],
+                                  float(z["inv_scale"]), z["W"], z["H"], z["cam"], thr)
+    d_or, st_or, _ = oracle.render(z["sdf"], z["position"], z["orientation"], z["inv_scale"],
+                                   z["W"], z["H"], threshold=thr, extras=True, **z["cam"])
+    # same operation order, no FMA contraction on the host -> bit-identical
+    assert np.array_equal(depth, d_or)
+    assert np.array_equal(steps, st_or)
+    # and within fp32 rounding of the reference's float64 renderer
+    hit = z["depth"] > 0
+    assert ((depth > 0) == hit).all()
+    assert (np.abs(depth - z["depth"])[hit] / z["depth"][hit]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names())
+@pytest.mark.parametrize("mode", ["reference", "exact"])
+def test_device_backward_matches_oracle(emul, name, mode):
+    z = load_golden(name)
+    sdf = np.ascontiguousarray(z["sdf"], f32)
+    R = sdf.shape[0]
+    pos, quat = z["position"].astype(f32), z["orientation"].astype(f32)
+    s = np.asarray([z["inv_scale"]], f32)
+    depth = oracle.render(sdf, pos, quat, s, z["W"], z["H"], threshold=float(z["threshold"]),
+                          **z["cam"])
+    g = z["g"].astype(f32)
+    bw = oracle.render_backward(g, depth, sdf, pos, quat, s, z["W"], z["H"], sdf_grad_mode=mode,
+                                **z["cam"])
+    gs, gp = np.zeros((R, R, R)), np.zeros(8)
+    cf = [ctypes.c_float(z["cam"][k]) for k in ("cx", "cy", "fx", "fy")]
+    emul.emul_backward(P(g), P(depth), P(sdf), R, P(pos), P(quat), P(s), z["W"], z["H"], *cf,
+                       int(mode == "exact"), P(gs), P(gp))
+    gpo = np.concatenate([bw["g_position"], bw["g_orientation"], [bw["g_inv_scale"]]])
+    assert np.abs(gp - gpo).max() <= 1e-6 * np.abs(gpo).max()
+    assert np.abs(gs - bw["g_sdf"]).max() <= 1e-5 * np.abs(bw["g_sdf"]).max()
+    if mode == "exact":  # and against the reference's own derivatives
+        assert np.abs(gp - z["g_pose"]).max() <= 1e-4 * np.abs(z["g_pose"]).max()
+        assert np.abs(gs - z["g_sdf_exact"]).max() <= 1e-4 * np.abs(z["g_sdf_exact"]).max()
+
+
+def test_rectangle_culling_is_conservative(emul):
+    """Random poses incl. objects partly off-screen, partly behind the camera, camera inside the
+    box: rendering with and without the projected-box rectangle must give identical images."""
+    rng = np.random.default_rng(0)
+    grids = [sdf_sphere(16), sdf_box(20), sdf_torus(24)]
+    W, H = 96, 64
+    cam = default_camera(W, H)
+    n_culled = 0
+    for i in range(60):
+        sdf = grids[i % 3]
+        scale = rng.uniform(0.05, 0.6)
+        pos = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.6, 0.6), rng.uniform(-1.5, 0.3)])
+        q = shoemake(100 + i)
+        a, _, rect = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005, use_rect=1)
+        b, _, _ = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005, use_rect=0)
+        assert np.array_equal(a, b), (i, pos, scale, rect)
+        n_culled += (rect[2] - rect[0]) * (rect[3] - rect[1]) < W * H
+    assert n_culled > 10  # the culling is actually exercised
+
+
+def test_full_size_mug_frame_matches_oracle(emul):
+    """One 640x480 frame of the reference workload (mug SDF, default camera)."""
+    sdf = mug_sdf()
+    W, H = 640, 480
+    cam = default_camera(W, H)
+    pos, q, scale = [0.02, -0.01, -0.4], shoemake(1), 0.15
+    depth, steps, rect = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005)
+    d_or, st_or, _ = oracle.render(sdf, pos, q, 1 / scale, W, H, threshold=0.005, extras=True,
+                                   nthreads=8, **cam)
+    assert np.array_equal(depth, d_or)
+    assert (depth > 0).sum() > 20000
+    assert (rect[2] - rect[0]) * (rect[3] - rect[1]) < W * H

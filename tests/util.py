@@ -1,0 +1,124 @@
+"""Shared scene builders for the test-suite (analytic SDFs, cameras, golden loader)."""
+from __future__ import annotations
+
+import glob
+import math
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+POSE_KEYS = ("x", "y", "z", "qx", "qy", "qz", "qw", "s_inv")
+
+
+def golden_names():
+    return sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*_r*.npz")))
+
+
+def load_golden(name):
+    z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    if "sdf" not in z:
+        z["sdf"] = np.load(os.path.join(GOLDEN_DIR, str(z["sdf_file"])))["sdf"]
+    W, H = int(z["width"]), int(z["height"])
+    f = W / math.tan(float(z["fov_deg"]) * math.pi / 180.0 / 2.0) / 2  # sdf_renderer.py:419
+    z["cam"] = dict(cx=W / 2, cy=H / 2, fx=f, fy=f)
+    z["W"], z["H"] = W, H
+    return z
+
+
+def mug_sdf():
+    return np.load(os.path.join(GOLDEN_DIR, "mug_z0_sdf.npz"))["sdf"]
+
+
+def grid_coords(R):
+    a = np.linspace(-1.0, 1.0, R)
+    return np.meshgrid(a, a, a, indexing="ij")
+
+
+def sdf_sphere(R, r=0.6):
+    x, y, z = grid_coords(R)
+    return (np.sqrt(x * x + y * y + z * z) - r).astype(np.float32)
+
+
+def sdf_torus(R, major=0.55, minor=0.2):
+    x, y, z = grid_coords(R)
+    q = np.sqrt(x * x + z * z) - major
+    return (np.sqrt(q * q + y * y) - minor).astype(np.float32)
+
+
+def sdf_box(R, half=(0.5, 0.35, 0.6)):
+    x, y, z = grid_coords(R)
+    qx, qy, qz = np.abs(x) - half[0], np.abs(y) - half[1], np.abs(z) - half[2]
+    outside = np.sqrt(np.maximum(qx, 0) ** 2 + np.maximum(qy, 0) ** 2 + np.maximum(qz, 0) ** 2)
+    return (outside + np.minimum(np.maximum(qx, np.maximum(qy, qz)), 0)).astype(np.float32)
+
+
+def sdf_bottle(R):
+    """Capped cylinder body + thinner neck (the 'bottle' of BASELINE config 4)."""
+    x, y, z = grid_coords(R)
+    r = np.sqrt(x * x + z * z)
+
+    def capped(rad, y0, y1):
+        dy = np.maximum(y0 - y, y - y1)
+        dr = r - rad
+        return np.minimum(np.maximum(dr, dy), 0) + np.sqrt(np.maximum(dr, 0) ** 2 + np.maximum(dy, 0) ** 2)
+
+    return np.minimum(capped(0.35, -0.8, 0.3), capped(0.14, 0.25, 0.8)).astype(np.float32)
+
+
+def sdf_bowl(R):
+    """Hemispherical shell (the 'bowl' of BASELINE config 4)."""
+    x, y, z = grid_coords(R)
+    shell = np.abs(np.sqrt(x * x + y * y + z * z) - 0.65) - 0.06
+    return np.maximum(shell, y - 0.1).astype(np.float32)
+
+
+def shoemake(seed):
+    """Uniform random unit quaternion (x,y,z,w) -- recipe of estimation/simple_setup.py:856-868."""
+    u1, u2, u3 = np.random.default_rng(seed).random(3)
+    return np.array([
+        np.sqrt(1 - u1) * np.sin(2 * np.pi * u2),
+        np.sqrt(1 - u1) * np.cos(2 * np.pi * u2),
+        np.sqrt(u1) * np.sin(2 * np.pi * u3),
+        np.sqrt(u1) * np.cos(2 * np.pi * u3),
+    ], dtype=np.float32)
+
+
+def default_camera(W=640, H=480):
+    """estimation/configs/default.yaml:1-8 scaled to (W,H): f = W/2, principal point centred."""
+    return dict(cx=W / 2, cy=H / 2, fx=W / 2, fy=W / 2)
+
+
+def depth_parity(depth, ref, threshold, rtol=1e-5, frac=0.999):
+    """The depth gate of BASELINE.md: >= `frac` of the pixels hit by either renderer agree to
+    `rtol` relative (with identical hit/miss state); the remainder -- sphere-trace termination
+    flipped by one step under rounding -- must stay within `threshold` relative, or be a hit/miss
+    flip.  Returns a dict of diagnostics and asserts the gate."""
+    depth = np.asarray(depth, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    either = (depth != 0) | (ref != 0)
+    both = (depth != 0) & (ref != 0)
+    n = int(either.sum())
+    rel = np.zeros_like(ref)
+    rel[both] = np.abs(depth[both] - ref[both]) / np.abs(ref[both])
+    good = both & (rel <= rtol)
+    n_good = int(good.sum())
+    mask_flips = int((either & ~both).sum())
+    loose = both & (rel > rtol)
+    info = dict(n=n, good=n_good, mask_flips=mask_flips, step_flips=int(loose.sum()),
+                max_rel_good=float(rel[good].max()) if n_good else 0.0,
+                bit_equal=float((depth[either] == ref[either]).mean()) if n else 1.0)
+    assert n == 0 or n_good >= frac * n, info
+    if loose.any():
+        assert rel[loose].max() <= 4 * threshold + 1e-3, info
+    return info
+
+
+def grad_close(a, b, rtol=1e-3, what=""):
+    """Gradient gate: |a-b| <= rtol * max|b| elementwise (fp32 atomics reorder the sums)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b).max() / scale
+    assert err <= rtol, f"{what}: max err {err:.3e} relative to max|ref|={scale:.3e}"
+    return err
