@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/sdfrender.h"
@@ -73,7 +74,8 @@ struct FwdParams {
   Camera cam;
   float threshold;
   float* __restrict__ depth;  // [B,H,W]
-  int z_offset;               // first hypothesis of this launch (gridDim.z chunking)
+  int z_offset;               // first hypothesis of this launch (gridDim.y chunking)
+  int use_tables;             // ray tables fit in shared memory
   // compare
   const float* __restrict__ depth_obs;
   long long obs_stride;
@@ -98,6 +100,7 @@ struct BwdParams {
   float* __restrict__ grad_inv_scale;
   unsigned flags;
   int z_offset;
+  int use_tables;
   // compare
   const float* __restrict__ depth_obs;
   long long obs_stride;
@@ -130,73 +133,137 @@ __device__ __forceinline__ void build_frame(Frame& smemF, const Pose& pose, int 
   }
 }
 
-/* CTA prologue shared by all kernels: Frame (warp 0) and the ray tables (warps 1, 2). */
-__device__ __forceinline__ void cta_prologue(Frame& F, float* colx, float* rowy, const Pose& pose,
-                                             int b, const Camera& cam, int bx0, int by0) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) {
-    build_frame(F, pose, b, cam, lane);
-  } else if (warp == 1) {
-    colx[lane] = pixel_dx(bx0 + lane, cam.cx, cam.fx);
-  } else if (warp == 2 && lane < kTileH) {
-    rowy[lane] = pixel_dy(by0 + lane, cam.cy, cam.fy);
-  }
-}
-
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
   return v;
 }
 
+/*
+ * Work decomposition of the batched kernels.
+ *
+ * grid = (G, hypotheses): G persistent CTAs per hypothesis.  A CTA builds the hypothesis' Frame
+ * and the ray tables ONCE (one barrier), then walks the 32x8-pixel tiles g, g+G, g+2G, ... of
+ * that hypothesis without any further barrier: tiles outside the projected box are only
+ * zero-filled, tiles inside are traced.  Per-pixel results that need a reduction (loss sums,
+ * pose gradients, counters) accumulate in registers across the CTA's tiles and are reduced once
+ * at the end.  (Round 1 first shipped one CTA per tile: 76 800 CTAs with a prologue + barrier
+ * each -- ncu showed 37 % of the stall samples on those barriers and 60 % of the executed
+ * instructions outside the march loop; profiles/r01_notes.md.)
+ */
+struct Tiling {
+  int tiles_x, tiles_y;          /* tile grid of the whole image */
+  int rtx0, rty0, rtw, rth;      /* tile range covering the projected box */
+};
+
+__device__ __forceinline__ Tiling make_tiling(const Frame& F, const Camera& cam) {
+  Tiling T;
+  T.tiles_x = (cam.W + kTileW - 1) / kTileW;
+  T.tiles_y = (cam.H + kTileH - 1) / kTileH;
+  if (F.x1 <= F.x0 || F.y1 <= F.y0) {
+    T.rtx0 = T.rty0 = T.rtw = T.rth = 0;
+  } else {
+    T.rtx0 = F.x0 / kTileW;
+    T.rty0 = F.y0 / kTileH;
+    T.rtw = (F.x1 + kTileW - 1) / kTileW - T.rtx0;
+    T.rth = (F.y1 + kTileH - 1) / kTileH - T.rty0;
+  }
+  return T;
+}
+
+/* CTA prologue: Frame by warp 0, then the ray tables for the columns / rows of the box's tile
+ * range (double-precision divisions as in cu:146-147, amortised over all tiles of the CTA). */
+__device__ __forceinline__ Tiling cta_prologue(Frame& Fs, float* tables, bool use_tables,
+                                               const Pose& pose, int b, const Camera& cam,
+                                               float*& colx, float*& rowy) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) build_frame(Fs, pose, b, cam, lane);
+  __syncthreads();
+  const Tiling T = make_tiling(Fs, cam);
+  colx = tables;
+  rowy = tables + T.tiles_x * kTileW;
+  if (use_tables) {
+    const int ncol = T.rtw * kTileW, nrow = T.rth * kTileH;
+    for (int i = threadIdx.x; i < ncol; i += kThreads)
+      colx[i] = pixel_dx(T.rtx0 * kTileW + i, cam.cx, cam.fx);
+    for (int i = threadIdx.x; i < nrow; i += kThreads)
+      rowy[i] = pixel_dy(T.rty0 * kTileH + i, cam.cy, cam.fy);
+    __syncthreads();
+  }
+  return T;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Forward (replaces sdf_renderer_cuda_forward_kernel, cu:241-298).
  * ---------------------------------------------------------------------------------------- */
-template <bool COMPARE, bool STATS>
-__global__ void __launch_bounds__(kThreads)
+template <int RT, bool COMPARE, bool STATS>
+__global__ void __launch_bounds__(kThreads, 5)
 sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
-  __shared__ Frame F;
-  __shared__ float colx[kTileW];
-  __shared__ float rowy[kTileH];
+  extern __shared__ float tables[];
+  __shared__ Frame Fs;
   __shared__ float red[2][kWarps];
 
-  const int b = blockIdx.z + P.z_offset;
-  const int bx0 = blockIdx.x * kTileW, by0 = blockIdx.y * kTileH;
+  const int b = blockIdx.y + P.z_offset;
+  const int g = blockIdx.x, G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = ((warp & 3) << 3) + (lane & 7);
   const int ly = ((warp >> 2) << 2) + (lane >> 3);
-  const int px = bx0 + lx, py = by0 + ly;
-  const bool inside = px < P.cam.W && py < P.cam.H;
-  float* __restrict__ out = P.depth + ((size_t)b * P.cam.H + py) * P.cam.W + px;
+  const int W = P.cam.W, H = P.cam.H;
+  float *colx, *rowy;
+  const Tiling T = cta_prologue(Fs, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
+  const Frame& F = Fs; /* read-only from here on; the march hoists what it needs */
+  float* __restrict__ out = P.depth + (size_t)b * H * W;
+  const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
 
-  cta_prologue(F, colx, rowy, P.pose, b, P.cam, bx0, by0);
-  __syncthreads();
-
-  /* CTA outside the projected box: nothing can be hit (cu:294-296 writes 0 for these) */
-  if (bx0 >= F.x1 || bx0 + kTileW <= F.x0 || by0 >= F.y1 || by0 + kTileH <= F.y0) {
-    if (inside) *out = 0.0f;
-    return;
+  /* pass 1: tiles that cannot see the box are zero (cu:294-296 writes 0 for these rays) */
+  const int n_tiles = T.tiles_x * T.tiles_y;
+  for (int t = g; t < n_tiles; t += G) {
+    const int ty = t / T.tiles_x, tx = t - ty * T.tiles_x;
+    if (tx >= T.rtx0 && tx < T.rtx0 + T.rtw && ty >= T.rty0 && ty < T.rty0 + T.rth) continue;
+    const int px = tx * kTileW + lx, py = ty * kTileH + ly;
+    if (px < W && py < H) out[(size_t)py * W + px] = 0.0f;
   }
 
-  float z = 0.0f;
-  int steps = 0;
-  bool entered = false, capped = false;
-  if (inside && px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
-    const Ray r = make_ray(F, colx[lx], rowy[ly]);
-    float t_min, t_max;
-    if (ray_box(F, r, t_min, t_max)) {
-      entered = true;
-      const float* __restrict__ g = P.sdf + (size_t)b * P.sdf_stride;
-      z = march(g, P.grid, F, r, t_min, t_max, P.threshold, steps, capped);
+  /* pass 2: tiles inside the box's rectangle are traced */
+  float err_acc = 0.0f, cnt_acc = 0.0f;
+  unsigned st_steps = 0, st_entered = 0, st_hit = 0, st_capped = 0;
+  const int n_rect = T.rtw * T.rth;
+  for (int r = g; r < n_rect; r += G) {
+    const int rty = r / T.rtw, rtx = r - rty * T.rtw;
+    const int px = (T.rtx0 + rtx) * kTileW + lx, py = (T.rty0 + rty) * kTileH + ly;
+    if (px >= W || py >= H) continue;
+    float z = 0.0f;
+    if (px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
+      const float ux = P.use_tables ? colx[rtx * kTileW + lx] : pixel_dx(px, P.cam.cx, P.cam.fx);
+      const float uy = P.use_tables ? rowy[rty * kTileH + ly] : pixel_dy(py, P.cam.cy, P.cam.fy);
+      const Ray ray = make_ray(F, ux, uy);
+      float t_min, t_max;
+      if (ray_box(F, ray, t_min, t_max)) {
+        int steps;
+        bool capped;
+        z = march<RT>(grid, P.grid, F, ray, t_min, t_max, P.threshold, steps, capped);
+        if (STATS) {
+          st_steps += steps;
+          st_entered += 1;
+          st_hit += z != 0.0f;
+          st_capped += capped;
+        }
+      }
+    }
+    out[(size_t)py * W + px] = z;
+    if (COMPARE && z > 0.0f) {
+      /* masked L1 against the observation (estimation/simple_setup.py:125-131) */
+      const float obs = __ldg(P.depth_obs + (size_t)b * P.obs_stride + (size_t)py * W + px);
+      if (obs > 0.0f) {
+        err_acc += fabsf(z - obs);
+        cnt_acc += 1.0f;
+      }
     }
   }
-  if (inside) *out = z;
 
   if (STATS) {
-    const unsigned s = __reduce_add_sync(kFull, (unsigned)steps);
-    const unsigned e = __popc(__ballot_sync(kFull, entered));
-    const unsigned h = __popc(__ballot_sync(kFull, z != 0.0f));
-    const unsigned c = __popc(__ballot_sync(kFull, capped));
+    const unsigned s = __reduce_add_sync(kFull, st_steps), e = __reduce_add_sync(kFull, st_entered);
+    const unsigned h = __reduce_add_sync(kFull, st_hit), c = __reduce_add_sync(kFull, st_capped);
     if (lane == 0) {
       if (s) atomicAdd(P.stats + 0, (unsigned long long)s);
       if (e) atomicAdd(P.stats + 1, (unsigned long long)e);
@@ -204,23 +271,12 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
       if (c) atomicAdd(P.stats + 3, (unsigned long long)c);
     }
   }
-
   if (COMPARE) {
-    /* masked L1 against the observation (estimation/simple_setup.py:125-131) */
-    float err = 0.0f, cnt = 0.0f;
-    if (z > 0.0f) {
-      const float obs =
-          __ldg(P.depth_obs + (size_t)b * P.obs_stride + (size_t)py * P.cam.W + px);
-      if (obs > 0.0f) {
-        err = fabsf(z - obs);
-        cnt = 1.0f;
-      }
-    }
-    err = warp_sum(err);
-    cnt = warp_sum(cnt);
+    err_acc = warp_sum(err_acc);
+    cnt_acc = warp_sum(cnt_acc);
     if (lane == 0) {
-      red[0][warp] = err;
-      red[1][warp] = cnt;
+      red[0][warp] = err_acc;
+      red[1][warp] = cnt_acc;
     }
     __syncthreads();
     if (threadIdx.x < 2) {
@@ -235,62 +291,67 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
 /* ------------------------------------------------------------------------------------------
  * Backward (replaces sdf_renderer_cuda_backward_kernel, cu:300-468).
  * MODE 0: explicit grad_depth.  MODE 1: fused compare (gradient of the masked L1 rebuilt here).
+ * Only tiles inside the projected box are visited: `depth` must be the image the forward
+ * produced for the same pose (it is zero everywhere else).
  * ---------------------------------------------------------------------------------------- */
-template <int MODE, bool WANT_SDF, bool WANT_POSE>
-__global__ void __launch_bounds__(kThreads)
+template <int RT, int MODE, bool WANT_SDF, bool WANT_POSE>
+__global__ void __launch_bounds__(kThreads, 4)
 sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
-  __shared__ Frame F;
-  __shared__ float colx[kTileW];
-  __shared__ float rowy[kTileH];
+  extern __shared__ float tables[];
+  __shared__ Frame Fs;
   __shared__ float red[kWarps][8];
-  __shared__ float coef_s;
 
-  const int b = blockIdx.z + P.z_offset;
-  const int bx0 = blockIdx.x * kTileW, by0 = blockIdx.y * kTileH;
+  const int b = blockIdx.y + P.z_offset;
+  const int g = blockIdx.x, G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lx = ((warp & 3) << 3) + (lane & 7);
   const int ly = ((warp >> 2) << 2) + (lane >> 3);
-  const int px = bx0 + lx, py = by0 + ly;
-  const bool inside = px < P.cam.W && py < P.cam.H;
-  const size_t pix = ((size_t)b * P.cam.H + py) * P.cam.W + px;
+  const int W = P.cam.W, H = P.cam.H;
 
-  /* upstream gradient of this pixel */
-  float z = 0.0f, gup = 0.0f;
-  if (MODE == 1 && threadIdx.x == 0) {
+  float coef = 1.0f;
+  if (MODE == 1) { /* d loss_b / d pixel = upstream_b * sign / n_overlap_b */
     const float n = __ldg(P.n_overlap + b);
     const float u = P.upstream ? __ldg(P.upstream + b) : 1.0f;
-    coef_s = n > 0.0f ? u / n : 0.0f;
+    coef = n > 0.0f ? u / n : 0.0f;
+    if (coef == 0.0f) return; /* uniform over the CTA */
   }
-  if (inside) z = __ldg(P.depth + pix);
-  if (MODE == 0) {
-    if (z != 0.0f) gup = __ldg(P.grad_depth + pix);
-  } else {
-    if (z > 0.0f) {
-      const float obs =
-          __ldg(P.depth_obs + (size_t)b * P.obs_stride + (size_t)py * P.cam.W + px);
-      if (obs > 0.0f) gup = (z > obs) ? 1.0f : ((z < obs) ? -1.0f : 0.0f);
-    }
-  }
-  const bool active = (z != 0.0f) && (gup != 0.0f);
-  if (!__syncthreads_or(active)) return; /* also orders coef_s */
-  if (MODE == 1) gup *= coef_s;
 
-  cta_prologue(F, colx, rowy, P.pose, b, P.cam, bx0, by0);
-  __syncthreads();
+  float *colx, *rowy;
+  const Tiling T = cta_prologue(Fs, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
+  const Frame& F = Fs;
+  const float* __restrict__ depth = P.depth + (size_t)b * H * W;
+  const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
+  float* __restrict__ gsdf = WANT_SDF ? P.grad_sdf + (size_t)b * P.grad_sdf_stride : nullptr;
+  const bool exact = (P.flags & SDFR_SDF_GRAD_EXACT) != 0;
+  const int R = RT > 0 ? RT : P.grid.R, R2 = R * R;
 
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
 
-  if (active && gup != 0.0f) {
-    const Ray r = make_ray(F, colx[lx], rowy[ly]);
-    const float* __restrict__ g = P.sdf + (size_t)b * P.sdf_stride;
+  const int n_rect = T.rtw * T.rth;
+  for (int r = g; r < n_rect; r += G) {
+    const int rty = r / T.rtw, rtx = r - rty * T.rtw;
+    const int px = (T.rtx0 + rtx) * kTileW + lx, py = (T.rty0 + rty) * kTileH + ly;
+    if (px >= W || py >= H) continue;
+    const size_t pix = (size_t)py * W + px;
+    const float z = __ldg(depth + pix);
+    float gup;
+    if (MODE == 0) {
+      gup = __ldg(P.grad_depth + (size_t)b * H * W + pix);
+    } else {
+      const float obs = __ldg(P.depth_obs + (size_t)b * P.obs_stride + pix);
+      gup = (z > 0.0f && obs > 0.0f) ? ((z > obs) ? coef : ((z < obs) ? -coef : 0.0f)) : 0.0f;
+    }
+    if (z == 0.0f || gup == 0.0f) continue;
+
+    const float ux = P.use_tables ? colx[rtx * kTileW + lx] : pixel_dx(px, P.cam.cx, P.cam.fx);
+    const float uy = P.use_tables ? rowy[rty * kTileH + ly] : pixel_dy(py, P.cam.cy, P.cam.fy);
+    const Ray ray = make_ray(F, ux, uy);
     PixelGrad pg;
-    pixel_backward<WANT_SDF, WANT_POSE>(g, P.grid, F, r, z, gup,
-                                        (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+    pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, z, gup, exact, pg);
     if (WANT_SDF) {
-      float* __restrict__ gs = P.grad_sdf + (size_t)b * P.grad_sdf_stride + pg.base;
-      const int R = P.grid.R, R2 = P.grid.R2;
+      float* __restrict__ gs = gsdf + pg.base;
       atomicAdd(gs, pg.w[0]);
       atomicAdd(gs + 1, pg.w[1]);
       atomicAdd(gs + R, pg.w[2]);
@@ -302,12 +363,13 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
     }
     if (WANT_POSE) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = pg.pose[i] * gup;
+      for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * gup;
     }
   }
 
   if (WANT_POSE) {
-    /* warp shuffle -> shared -> 8 atomics per CTA (the reference: 8 per hit pixel, cu:459-466) */
+    /* registers -> warp shuffle -> shared -> 8 atomics per CTA (the reference issues 8
+     * same-address atomics per hit pixel, cu:459-466) */
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
     if (lane == 0) {
@@ -373,8 +435,8 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
       if (!ray_box(F, r, t_min, t_max)) continue;
       int steps;
       bool capped;
-      const float z = march(P.sdf + (size_t)(k0 + k) * P.sdf_stride, P.grid, F, r, t_min,
-                            t_max, P.threshold, steps, capped);
+      const float z = march<0>(P.sdf + (size_t)(k0 + k) * P.sdf_stride, P.grid, F, r, t_min,
+                               t_max, P.threshold, steps, capped);
       if (z > 0.0f && (win < 0 || z < best)) {
         best = z;
         win = k0 + k;
@@ -434,8 +496,8 @@ sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
       const Ray r = make_ray(F, colx[lx], rowy[ly]);
       const float* __restrict__ g = P.sdf + (size_t)k * P.sdf_stride;
       PixelGrad pg;
-      pixel_backward<WANT_SDF, WANT_POSE>(g, P.grid, F, r, z, gup,
-                                          (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+      pixel_backward<0, WANT_SDF, WANT_POSE>(g, P.grid, F, r, z, gup,
+                                             (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
       if (WANT_SDF) {
         float* __restrict__ gs = P.grad_sdf + (size_t)k * P.grad_sdf_stride + pg.base;
         const int R = P.grid.R, R2 = P.grid.R2;
@@ -503,14 +565,74 @@ int zero_async(void* p, size_t bytes, cudaStream_t s) {
   return 0;
 }
 
+/* CTAs per hypothesis: enough CTAs to fill the device several times over (tail effect), never
+ * more than there are tiles.  148 SMs x 32 on a B200. */
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int ctas_per_hypothesis(int batch, int W, int H) {
+  const long long n_tiles = (long long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
+  long long target = (long long)sm_count() * 32;
+  if (const char* env = getenv("SDFR_TARGET_CTAS")) { /* tuning knob, see scripts/gpu_micro.py */
+    const long long v = atoll(env);
+    if (v > 0) target = v;
+  }
+  long long g = (target + batch - 1) / batch;
+  if (g > n_tiles) g = n_tiles;
+  if (g > 65535) g = 65535;
+  return g < 1 ? 1 : (int)g;
+}
+
+/* dynamic shared memory for the ray tables; 0 = image too wide, compute per thread instead */
+size_t table_bytes(int W, int H) {
+  const size_t n = (size_t)((W + kTileW - 1) / kTileW) * kTileW +
+                   (size_t)((H + kTileH - 1) / kTileH) * kTileH;
+  return n * sizeof(float) <= 40 * 1024 ? n * sizeof(float) : 0;
+}
+
+template <int RT, bool COMPARE, bool STATS>
+void launch_forward_rt(FwdParams& P, dim3 grid, size_t smem, cudaStream_t s) {
+  sdfr_forward_kernel<RT, COMPARE, STATS><<<grid, kThreads, smem, s>>>(P);
+}
+
 template <bool COMPARE, bool STATS>
 int launch_forward(FwdParams P, int batch, cudaStream_t s) {
+  const size_t smem = table_bytes(P.cam.W, P.cam.H);
+  P.use_tables = smem != 0;
+  const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
-    const int nz = batch - z0 < 65535 ? batch - z0 : 65535;
-    sdfr_forward_kernel<COMPARE, STATS><<<tile_grid(P.cam.W, P.cam.H, nz), kThreads, 0, s>>>(P);
+    const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
+    switch (P.grid.R) { /* common resolutions get immediate-offset gathers */
+      case 64: launch_forward_rt<64, COMPARE, STATS>(P, grid, smem, s); break;
+      case 128: launch_forward_rt<128, COMPARE, STATS>(P, grid, smem, s); break;
+      case 32: launch_forward_rt<32, COMPARE, STATS>(P, grid, smem, s); break;
+      default: launch_forward_rt<0, COMPARE, STATS>(P, grid, smem, s); break;
+    }
   }
   return check_launch("sdfr_forward_kernel");
+}
+
+template <int RT, int MODE>
+void launch_backward_rt(BwdParams& P, dim3 grid, size_t smem, bool want_sdf, bool want_pose,
+                        cudaStream_t s) {
+  if (want_sdf && want_pose)
+    sdfr_backward_kernel<RT, MODE, true, true><<<grid, kThreads, smem, s>>>(P);
+  else if (want_sdf)
+    sdfr_backward_kernel<RT, MODE, true, false><<<grid, kThreads, smem, s>>>(P);
+  else
+    sdfr_backward_kernel<RT, MODE, false, true><<<grid, kThreads, smem, s>>>(P);
 }
 
 template <int MODE>
@@ -519,16 +641,18 @@ int launch_backward(BwdParams P, int batch, cudaStream_t s) {
   const bool want_pose =
       (P.flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
   if (!want_sdf && !want_pose) return 0;
+  const size_t smem = table_bytes(P.cam.W, P.cam.H);
+  P.use_tables = smem != 0;
+  const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
-    const int nz = batch - z0 < 65535 ? batch - z0 : 65535;
-    const dim3 grid = tile_grid(P.cam.W, P.cam.H, nz);
-    if (want_sdf && want_pose)
-      sdfr_backward_kernel<MODE, true, true><<<grid, kThreads, 0, s>>>(P);
-    else if (want_sdf)
-      sdfr_backward_kernel<MODE, true, false><<<grid, kThreads, 0, s>>>(P);
-    else
-      sdfr_backward_kernel<MODE, false, true><<<grid, kThreads, 0, s>>>(P);
+    const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
+    switch (P.grid.R) {
+      case 64: launch_backward_rt<64, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
+      case 128: launch_backward_rt<128, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
+      case 32: launch_backward_rt<32, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
+      default: launch_backward_rt<0, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
+    }
   }
   return check_launch("sdfr_backward_kernel");
 }
@@ -607,7 +731,7 @@ extern "C" {
 int sdfr_abi_version(void) { return SDFR_ABI_VERSION; }
 const char* sdfr_last_error(void) { return g_err; }
 const char* sdfr_build_info(void) {
-  return "libsdfrender sm_100a; tile 32x8, 8 warps of 8x4 px; fp32; nvcc " __DATE__;
+  return "libsdfrender sm_100a; persistent CTAs per hypothesis, tile 32x8 (8 warps of 8x4 px); fp32; nvcc " __DATE__;
 }
 int sdfr_max_steps(void) { return sdfr::kMaxSteps; }
 

@@ -127,5 +127,7 @@ def make_hypotheses(n: int, seed: int = 0, device="cpu", base_position=(0.02, -0
 def hypothesis_grids(shape_params, R: int, device, categories=("mug",)) -> torch.Tensor:
     """(n,R,R,R) grids: hypothesis i has category ``categories[i % len]`` and its own shape."""
     params = [float(v) for v in shape_params.tolist()]
-    return torch.stack([category_grid(categories[i % len(categories)], R, device, p)
-                        for i, p in enumerate(params)]).contiguous()
+    out = torch.empty(len(params), R, R, R, dtype=torch.float32, device=device)
+    for i, p in enumerate(params):
+        out[i] = category_grid(categories[i % len(categories)], R, "cpu", p)
+    return out

@@ -48,7 +48,7 @@ extern "C" int emul_forward(const float* sdf, int R, const float* pos, const flo
         const Ray r = make_ray(F, pixel_dx(px, cx, fx), pixel_dy(py, cy, fy));
         float t_min, t_max;
         if (ray_box(F, r, t_min, t_max))
-          z = march(sdf, G, F, r, t_min, t_max, threshold, steps, capped);
+          z = march<0>(sdf, G, F, r, t_min, t_max, threshold, steps, capped);
       }
       depth[(size_t)py * W + px] = z;
       if (steps_out) steps_out[(size_t)py * W + px] = steps;
@@ -73,7 +73,7 @@ extern "C" int emul_backward(const float* grad_depth, const float* depth, const 
       if (gup == 0.f) continue;
       const Ray r = make_ray(F, pixel_dx(px, cx, fx), pixel_dy(py, cy, fy));
       PixelGrad pg;
-      pixel_backward<true, true>(sdf, G, F, r, z, gup, exact != 0, pg);
+      pixel_backward<0, true, true>(sdf, G, F, r, z, gup, exact != 0, pg);
       const int offs[8] = {0, 1, G.R, G.R + 1, G.R2, G.R2 + 1, G.R2 + G.R, G.R2 + G.R + 1};
       for (int k = 0; k < 8; ++k) g_sdf[pg.base + offs[k]] += (double)pg.w[k];
       for (int k = 0; k < 8; ++k) g_pose[k] += (double)(pg.pose[k] * gup);

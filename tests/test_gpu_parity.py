@@ -28,7 +28,8 @@ def cam_obj(W, H, cam):
 
 
 def T(a, dev, grad=False):
-    t = torch.as_tensor(np.ascontiguousarray(a, dtype=np.float32), device=dev)
+    a = np.asarray(a, dtype=np.float32)
+    t = torch.as_tensor(np.ascontiguousarray(a).reshape(a.shape), device=dev)  # keeps 0-dim
     return t.requires_grad_(grad)
 
 
