@@ -261,9 +261,23 @@ def main():
             g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
             stream), "sdfr_compare_backward")
 
+    def fused():
+        _lib.check(lib.sdfr_compare_fused(
+            grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
+            CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
+            sums[1].data_ptr(), g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
+            g_is.data_ptr(), flags_b, stream), "sdfr_compare_fused")
+
+    def scale():
+        _lib.check(lib.sdfr_scale_grads(
+            sums[1].data_ptr(), None, R, B, g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
+            g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, stream), "sdfr_scale_grads")
+
     def step():
-        fwd()
-        bwd()
+        # forward render + masked-L1 compare + backward in ONE traversal, then the deferred
+        # per-hypothesis normalisation of the gradients
+        fused()
+        scale()
         if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
             torch.div(sums[0], sums[1], out=loss)
             dist.all_gather_into_tensor(gathered, loss)
@@ -306,6 +320,8 @@ def main():
     ms_per_step = total_ms / K
 
     # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
+    fused_ms = timed(fused, K, 2) / K
+    scale_ms = timed(scale, K, 2) / K
     fwd_ms = timed(fwd, K, 2) / K
     bwd_ms = timed(bwd, K, 2) / K
 
@@ -363,22 +379,27 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     n_over = int(sums[1].sum().item())
+    # 32 B per trilinear sample, depth store, observation read at hits, grid read once;
+    # fused backward: 32 B corner re-read + 64 B RMW per overlap pixel, grad grid written once
     fwd_bytes = 32 * S + 4 * P * B + 4 * RRR * B + 4 * Hh_all
     bwd_bytes = 4 * P * B + 4 * Hh_all + 32 * n_over + 64 * n_over + 4 * RRR * B
+    fused_bytes = fwd_bytes + 32 * n_over + 64 * n_over + 4 * RRR * B
     peak, peak_src = measured_peaks()
-    dom = "forward" if fwd_ms >= bwd_ms else "backward"
-    dom_bytes, dom_ms = (fwd_bytes, fwd_ms) if dom == "forward" else (bwd_bytes, bwd_ms)
+    dom_bytes, dom_ms = fused_bytes, fused_ms
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"sdfr_{dom}_kernel (compare)", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "sdfr_forward_kernel<64, MODE=2> (fused render+compare+backward, incl. its memsets)",
+        "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
         "note": ("algorithmic bytes = SURVEY 8d formula (32 B per trilinear sample + compulsory "
                  "image/grid traffic); the 32*S gather term is served by L1/L2, so frac is against "
                  "the HBM copy peak, not a claim of HBM traffic"),
         "kernels": {
-            "forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
-            "backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
+            "fused_incl_memsets": {"ms": fused_ms, "bytes": fused_bytes, "GBps": fused_bytes / fused_ms / 1e6},
+            "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
+            "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
+            "unfused_backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
         },
         "work": {"samples_S": S, "hit_pixels": Hh_all, "overlap_pixels_Hh": n_over,
                  "box_pixels": stats["box_pixels"], "pixels": P * B},
@@ -397,7 +418,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "render_and_compare + autograd backward, pinned host buffers",
                 "checksum": e2e_check},
-        "gpu_launches": 2 * K,
+        "gpu_launches": 3 * K,  # fused kernel + pose-zero kernel + scale kernel per step
         "clocks": clocks.summary(),
         "lib": lib.sdfr_build_info().decode(),
     }

@@ -132,6 +132,30 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
                           void* stream);
 
 /*
+ * Fused render-and-compare with the backward folded into the SAME traversal (one kernel): as
+ * sdfr_compare_forward, plus UNNORMALISED gradients of  sum_overlap |est - obs|  accumulated into
+ * the requested buffers while each ray is still live in registers.  The per-hypothesis factor
+ * upstream[b] / n_overlap[b] is only known once every pixel is done; all gradients are linear in
+ * it, so it is applied afterwards by sdfr_scale_grads (or by the caller, e.g. folded into an
+ * optimizer step).  With SDFR_GRAD_SDF each hypothesis needs its own grad grid
+ * (grad_sdf_stride != 0 unless batch == 1).  SDFR_ZERO_GRADS also clears loss_sum / n_overlap.
+ */
+int sdfr_compare_fused(const float* sdf, int resolution, long long sdf_stride,
+                       const float* position, const float* orientation, const float* inv_scale,
+                       int batch, int width, int height, float cx, float cy, float fx, float fy,
+                       float threshold, const float* depth_obs, long long obs_stride,
+                       float* depth, float* loss_sum, float* n_overlap, float* grad_sdf,
+                       long long grad_sdf_stride, float* grad_position, float* grad_orientation,
+                       float* grad_inv_scale, unsigned flags, void* stream);
+
+/* In place:  grad[b] *= (upstream ? upstream[b] : 1) / n_overlap[b]  (0 where n_overlap == 0)
+ * for the buffers selected by `flags`. */
+int sdfr_scale_grads(const float* n_overlap, const float* upstream, int resolution, int batch,
+                     float* grad_sdf, long long grad_sdf_stride, float* grad_position,
+                     float* grad_orientation, float* grad_inv_scale, unsigned flags,
+                     void* stream);
+
+/*
  * Multi-object frame: `n_objects` posed grids rendered into ONE depth map, per-pixel minimum
  * positive depth; winner [height,width] int32 receives the index of the object that produced
  * the pixel (-1 = none; ties go to the lowest index).  No counterpart in the reference (it

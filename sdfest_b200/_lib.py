@@ -42,6 +42,10 @@ SIGNATURES = {
     "sdfr_compare_backward": (
         c_int, [_P, _P, c_longlong, _P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS,
                 c_uint, _P]),
+    "sdfr_compare_fused": (
+        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
+                *_GRADS, c_uint, _P]),
+    "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P]),
     "sdfr_forward_composite": (
         c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
     "sdfr_backward_composite": (

@@ -83,6 +83,13 @@ struct FwdParams {
   float* __restrict__ n_overlap;
   // stats
   unsigned long long* __restrict__ stats;
+  // fused compare + backward (unnormalised gradients)
+  float* __restrict__ grad_sdf;
+  long long grad_sdf_stride;
+  float* __restrict__ grad_position;
+  float* __restrict__ grad_orientation;
+  float* __restrict__ grad_inv_scale;
+  unsigned flags;
 };
 
 struct BwdParams {
@@ -143,17 +150,39 @@ __device__ __forceinline__ float warp_sum(float v) {
  * Work decomposition of the batched kernels.
  *
  * grid = (G, hypotheses): G persistent CTAs per hypothesis.  A CTA builds the hypothesis' Frame
- * and the ray tables ONCE (one barrier), then walks the 32x8-pixel tiles g, g+G, g+2G, ... of
- * that hypothesis without any further barrier: tiles outside the projected box are only
- * zero-filled, tiles inside are traced.  Per-pixel results that need a reduction (loss sums,
- * pose gradients, counters) accumulate in registers across the CTA's tiles and are reduced once
- * at the end.  (Round 1 first shipped one CTA per tile: 76 800 CTAs with a prologue + barrier
- * each -- ncu showed 37 % of the stall samples on those barriers and 60 % of the executed
- * instructions outside the march loop; profiles/r01_notes.md.)
+ * and the ray tables ONCE, then walks the 32x8-pixel tiles g, g+G, g+2G, ... of that hypothesis
+ * without any further barrier: tiles outside the projected box are only zero-filled, tiles
+ * inside are traced.  Per-pixel results that need a reduction (loss sums, pose gradients,
+ * counters) accumulate in registers across the CTA's tiles and are reduced once at the end.
+ * (Round 1 first shipped one CTA per tile: 76 800 CTAs with a prologue + barrier each -- ncu
+ * showed 37 % of the stall samples on those barriers and 60 % of the executed instructions
+ * outside the march loop; profiles/r01_notes.md.)
  */
 struct Tiling {
-  int tiles_x, tiles_y;          /* tile grid of the whole image */
-  int rtx0, rty0, rtw, rth;      /* tile range covering the projected box */
+  int tiles_x, tiles_y;      /* tile grid of the whole image */
+  int rtx0, rty0, rtw, rth;  /* tile range covering the projected box */
+  int tab_x0, tab_y0;        /* first tile column / row held by the ray tables */
+};
+
+/* (row, col) walk over a w-wide tile range in steps of G tiles without integer division in
+ * the loop: one division at start, then add-and-carry. */
+struct TileWalk {
+  int ty, tx, dy, dx, w;
+  __device__ __forceinline__ TileWalk(int first, int G, int w_) : w(w_) {
+    const int ww = w_ > 0 ? w_ : 1;
+    ty = first / ww;
+    tx = first - ty * ww;
+    dy = G / ww;
+    dx = G - dy * ww;
+  }
+  __device__ __forceinline__ void next() {
+    tx += dx;
+    ty += dy;
+    if (tx >= w) {
+      tx -= w;
+      ty += 1;
+    }
+  }
 };
 
 __device__ __forceinline__ Tiling make_tiling(const Frame& F, const Camera& cam) {
@@ -168,40 +197,103 @@ __device__ __forceinline__ Tiling make_tiling(const Frame& F, const Camera& cam)
     T.rtw = (F.x1 + kTileW - 1) / kTileW - T.rtx0;
     T.rth = (F.y1 + kTileH - 1) / kTileH - T.rty0;
   }
+  T.tab_x0 = T.rtx0;
+  T.tab_y0 = T.rty0;
   return T;
 }
 
-/* CTA prologue: Frame by warp 0, then the ray tables for the columns / rows of the box's tile
- * range (double-precision divisions as in cu:146-147, amortised over all tiles of the CTA). */
+/* CTA prologue: Frame by warp 0, then the ray tables (double-precision divisions as in
+ * cu:146-147, amortised over all tiles of the CTA).  When the CTA owns at most one tile of the
+ * box (small batches: G >= number of box tiles) only that tile's 32 + 8 entries are built. */
 __device__ __forceinline__ Tiling cta_prologue(Frame& Fs, float* tables, bool use_tables,
                                                const Pose& pose, int b, const Camera& cam,
                                                float*& colx, float*& rowy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0) build_frame(Fs, pose, b, cam, lane);
   __syncthreads();
-  const Tiling T = make_tiling(Fs, cam);
+  Tiling T = make_tiling(Fs, cam);
   colx = tables;
   rowy = tables + T.tiles_x * kTileW;
   if (use_tables) {
-    const int ncol = T.rtw * kTileW, nrow = T.rth * kTileH;
+    const int n_rect = T.rtw * T.rth;
+    int ncol = T.rtw * kTileW, nrow = T.rth * kTileH;
+    if (n_rect <= (int)gridDim.x) { /* this CTA traces tile blockIdx.x of the box, or nothing */
+      if ((int)blockIdx.x < n_rect) {
+        const int ty = (int)blockIdx.x / T.rtw;
+        T.tab_x0 = T.rtx0 + ((int)blockIdx.x - ty * T.rtw);
+        T.tab_y0 = T.rty0 + ty;
+        ncol = kTileW;
+        nrow = kTileH;
+      } else {
+        ncol = nrow = 0;
+      }
+    }
     for (int i = threadIdx.x; i < ncol; i += kThreads)
-      colx[i] = pixel_dx(T.rtx0 * kTileW + i, cam.cx, cam.fx);
+      colx[i] = pixel_dx(T.tab_x0 * kTileW + i, cam.cx, cam.fx);
     for (int i = threadIdx.x; i < nrow; i += kThreads)
-      rowy[i] = pixel_dy(T.rty0 * kTileH + i, cam.cy, cam.fy);
+      rowy[i] = pixel_dy(T.tab_y0 * kTileH + i, cam.cy, cam.fy);
     __syncthreads();
   }
   return T;
 }
 
+template <int RT>
+__device__ __forceinline__ void scatter_sdf(float* __restrict__ gs, const Grid& G,
+                                            const PixelGrad& pg) {
+  const int R = RT > 0 ? RT : G.R, R2 = R * R;
+  gs += pg.base;
+  atomicAdd(gs, pg.w[0]);
+  atomicAdd(gs + 1, pg.w[1]);
+  atomicAdd(gs + R, pg.w[2]);
+  atomicAdd(gs + R + 1, pg.w[3]);
+  atomicAdd(gs + R2, pg.w[4]);
+  atomicAdd(gs + R2 + 1, pg.w[5]);
+  atomicAdd(gs + R2 + R, pg.w[6]);
+  atomicAdd(gs + R2 + R + 1, pg.w[7]);
+}
+
+/* registers -> warp shuffle -> shared -> 8 atomics per CTA (the reference issues 8 same-address
+ * atomics per hit pixel, cu:459-466).  Contains one barrier: call from uniform control flow. */
+__device__ __forceinline__ void reduce_pose(float (&acc)[8], float (*red)[8], int b,
+                                            float* gp, float* gq, float* gi, unsigned flags) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+    const int i = threadIdx.x;
+    if (s != 0.0f) {
+      if (i < 3) {
+        if (flags & SDFR_GRAD_POSITION) atomicAdd(gp + 3 * b + i, s);
+      } else if (i < 7) {
+        if (flags & SDFR_GRAD_ORIENTATION) atomicAdd(gq + 4 * b + (i - 3), s);
+      } else {
+        if (flags & SDFR_GRAD_INV_SCALE) atomicAdd(gi + b, s);
+      }
+    }
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Forward (replaces sdf_renderer_cuda_forward_kernel, cu:241-298).
+ * MODE 0: depth only.  MODE 1: + masked-L1 compare sums.  MODE 2: + the backward of that loss
+ * fused into the same traversal (unnormalised: d/d theta of sum |est - obs|; the per-hypothesis
+ * factor upstream/n_overlap is only known once all pixels are done and is applied afterwards by
+ * sdfr_scale_grads -- every gradient is linear in it).
  * ---------------------------------------------------------------------------------------- */
-template <int RT, bool COMPARE, bool STATS>
+template <int RT, int MODE, bool STATS, bool WANT_SDF, bool WANT_POSE>
 __global__ void __launch_bounds__(kThreads, 5)
 sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
-  __shared__ float red[2][kWarps];
+  __shared__ float red[kWarps][8];
 
   const int b = blockIdx.y + P.z_offset;
   const int g = blockIdx.x, G = gridDim.x;
@@ -214,29 +306,40 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   const Frame& F = Fs; /* read-only from here on; the march hoists what it needs */
   float* __restrict__ out = P.depth + (size_t)b * H * W;
   const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
+  const float* __restrict__ obs_img = MODE >= 1 ? P.depth_obs + (size_t)b * P.obs_stride : nullptr;
 
   /* pass 1: tiles that cannot see the box are zero (cu:294-296 writes 0 for these rays) */
-  const int n_tiles = T.tiles_x * T.tiles_y;
-  for (int t = g; t < n_tiles; t += G) {
-    const int ty = t / T.tiles_x, tx = t - ty * T.tiles_x;
-    if (tx >= T.rtx0 && tx < T.rtx0 + T.rtw && ty >= T.rty0 && ty < T.rty0 + T.rth) continue;
-    const int px = tx * kTileW + lx, py = ty * kTileH + ly;
-    if (px < W && py < H) out[(size_t)py * W + px] = 0.0f;
+  {
+    const int n_tiles = T.tiles_x * T.tiles_y;
+    TileWalk w(g, G, T.tiles_x);
+    for (int t = g; t < n_tiles; t += G, w.next()) {
+      if (w.tx >= T.rtx0 && w.tx < T.rtx0 + T.rtw && w.ty >= T.rty0 && w.ty < T.rty0 + T.rth)
+        continue;
+      const int px = w.tx * kTileW + lx, py = w.ty * kTileH + ly;
+      if (px < W && py < H) out[(size_t)py * W + px] = 0.0f;
+    }
   }
 
   /* pass 2: tiles inside the box's rectangle are traced */
+  float acc[8]; /* MODE 1: [0] = sum |err|, [1] = count.  MODE 2: pose gradients + the two */
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
   float err_acc = 0.0f, cnt_acc = 0.0f;
   unsigned st_steps = 0, st_entered = 0, st_hit = 0, st_capped = 0;
   const int n_rect = T.rtw * T.rth;
-  for (int r = g; r < n_rect; r += G) {
-    const int rty = r / T.rtw, rtx = r - rty * T.rtw;
-    const int px = (T.rtx0 + rtx) * kTileW + lx, py = (T.rty0 + rty) * kTileH + ly;
+  TileWalk w(g, G, T.rtw);
+  for (int r = g; r < n_rect; r += G, w.next()) {
+    const int tx = T.rtx0 + w.tx, ty = T.rty0 + w.ty;
+    const int px = tx * kTileW + lx, py = ty * kTileH + ly;
     if (px >= W || py >= H) continue;
     float z = 0.0f;
+    Ray ray;
     if (px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
-      const float ux = P.use_tables ? colx[rtx * kTileW + lx] : pixel_dx(px, P.cam.cx, P.cam.fx);
-      const float uy = P.use_tables ? rowy[rty * kTileH + ly] : pixel_dy(py, P.cam.cy, P.cam.fy);
-      const Ray ray = make_ray(F, ux, uy);
+      const float ux = P.use_tables ? colx[(tx - T.tab_x0) * kTileW + lx]
+                                    : pixel_dx(px, P.cam.cx, P.cam.fx);
+      const float uy = P.use_tables ? rowy[(ty - T.tab_y0) * kTileH + ly]
+                                    : pixel_dy(py, P.cam.cy, P.cam.fy);
+      ray = make_ray(F, ux, uy);
       float t_min, t_max;
       if (ray_box(F, ray, t_min, t_max)) {
         int steps;
@@ -250,13 +353,26 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
         }
       }
     }
-    out[(size_t)py * W + px] = z;
-    if (COMPARE && z > 0.0f) {
+    const size_t pix = (size_t)py * W + px;
+    out[pix] = z;
+    if (MODE >= 1 && z > 0.0f) {
       /* masked L1 against the observation (estimation/simple_setup.py:125-131) */
-      const float obs = __ldg(P.depth_obs + (size_t)b * P.obs_stride + (size_t)py * W + px);
+      const float obs = __ldg(obs_img + pix);
       if (obs > 0.0f) {
         err_acc += fabsf(z - obs);
         cnt_acc += 1.0f;
+        if (MODE == 2 && z != obs) {
+          const float sgn = z > obs ? 1.0f : -1.0f;
+          PixelGrad pg;
+          pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, z, sgn,
+                                                  (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+          if (WANT_SDF)
+            scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, P.grid, pg);
+          if (WANT_POSE) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
+          }
+        }
       }
     }
   }
@@ -271,26 +387,21 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
       if (c) atomicAdd(P.stats + 3, (unsigned long long)c);
     }
   }
-  if (COMPARE) {
+  if (MODE >= 1) {
     err_acc = warp_sum(err_acc);
     cnt_acc = warp_sum(cnt_acc);
     if (lane == 0) {
-      red[0][warp] = err_acc;
-      red[1][warp] = cnt_acc;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-      float s = 0.0f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += red[threadIdx.x][w];
-      if (s != 0.0f) atomicAdd((threadIdx.x == 0 ? P.loss_sum : P.n_overlap) + b, s);
+      if (err_acc != 0.0f) atomicAdd(P.loss_sum + b, err_acc);
+      if (cnt_acc != 0.0f) atomicAdd(P.n_overlap + b, cnt_acc);
     }
   }
+  if (MODE == 2 && WANT_POSE)
+    reduce_pose(acc, red, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
 }
 
 /* ------------------------------------------------------------------------------------------
  * Backward (replaces sdf_renderer_cuda_backward_kernel, cu:300-468).
- * MODE 0: explicit grad_depth.  MODE 1: fused compare (gradient of the masked L1 rebuilt here).
+ * MODE 0: explicit grad_depth.  MODE 1: compare (gradient of the masked L1 rebuilt here).
  * Only tiles inside the projected box are visited: `depth` must be the image the forward
  * produced for the same pose (it is zero everywhere else).
  * ---------------------------------------------------------------------------------------- */
@@ -320,78 +431,113 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   const Tiling T = cta_prologue(Fs, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
   const Frame& F = Fs;
   const float* __restrict__ depth = P.depth + (size_t)b * H * W;
+  const float* __restrict__ upimg =
+      MODE == 0 ? P.grad_depth + (size_t)b * H * W : P.depth_obs + (size_t)b * P.obs_stride;
   const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
   float* __restrict__ gsdf = WANT_SDF ? P.grad_sdf + (size_t)b * P.grad_sdf_stride : nullptr;
   const bool exact = (P.flags & SDFR_SDF_GRAD_EXACT) != 0;
-  const int R = RT > 0 ? RT : P.grid.R, R2 = R * R;
 
   float acc[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
 
+  /* the scan is latency bound (two dependent-free loads per pixel, ~7 % of the warp tiles hold
+   * work): the loads of the NEXT tile are issued before the current one is processed */
   const int n_rect = T.rtw * T.rth;
+  TileWalk w(g, G, T.rtw);
+  int px = 0, py = 0, tx = 0, ty = 0;
+  float z = 0.0f, u = 0.0f;
+  bool valid = false;
+  auto fetch = [&](int r) {
+    valid = false;
+    z = 0.0f;
+    if (r < n_rect) {
+      tx = T.rtx0 + w.tx;
+      ty = T.rty0 + w.ty;
+      px = tx * kTileW + lx;
+      py = ty * kTileH + ly;
+      if (px < W && py < H) {
+        valid = true;
+        z = __ldg(depth + (size_t)py * W + px);
+        u = __ldg(upimg + (size_t)py * W + px);
+      }
+    }
+  };
+  fetch(g);
   for (int r = g; r < n_rect; r += G) {
-    const int rty = r / T.rtw, rtx = r - rty * T.rtw;
-    const int px = (T.rtx0 + rtx) * kTileW + lx, py = (T.rty0 + rty) * kTileH + ly;
-    if (px >= W || py >= H) continue;
-    const size_t pix = (size_t)py * W + px;
-    const float z = __ldg(depth + pix);
+    const float zc = z, uc = u;
+    const int cpx = px, cpy = py, ctx = tx, cty = ty;
+    const bool cvalid = valid;
+    w.next();
+    fetch(r + G);
+    if (!cvalid || zc == 0.0f) continue;
     float gup;
     if (MODE == 0) {
-      gup = __ldg(P.grad_depth + (size_t)b * H * W + pix);
+      gup = uc;
     } else {
-      const float obs = __ldg(P.depth_obs + (size_t)b * P.obs_stride + pix);
-      gup = (z > 0.0f && obs > 0.0f) ? ((z > obs) ? coef : ((z < obs) ? -coef : 0.0f)) : 0.0f;
+      gup = (zc > 0.0f && uc > 0.0f) ? ((zc > uc) ? coef : ((zc < uc) ? -coef : 0.0f)) : 0.0f;
     }
-    if (z == 0.0f || gup == 0.0f) continue;
-
-    const float ux = P.use_tables ? colx[rtx * kTileW + lx] : pixel_dx(px, P.cam.cx, P.cam.fx);
-    const float uy = P.use_tables ? rowy[rty * kTileH + ly] : pixel_dy(py, P.cam.cy, P.cam.fy);
+    if (gup == 0.0f) continue;
+    const float ux = P.use_tables ? colx[(ctx - T.tab_x0) * kTileW + lx]
+                                  : pixel_dx(cpx, P.cam.cx, P.cam.fx);
+    const float uy = P.use_tables ? rowy[(cty - T.tab_y0) * kTileH + ly]
+                                  : pixel_dy(cpy, P.cam.cy, P.cam.fy);
     const Ray ray = make_ray(F, ux, uy);
     PixelGrad pg;
-    pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, z, gup, exact, pg);
-    if (WANT_SDF) {
-      float* __restrict__ gs = gsdf + pg.base;
-      atomicAdd(gs, pg.w[0]);
-      atomicAdd(gs + 1, pg.w[1]);
-      atomicAdd(gs + R, pg.w[2]);
-      atomicAdd(gs + R + 1, pg.w[3]);
-      atomicAdd(gs + R2, pg.w[4]);
-      atomicAdd(gs + R2 + 1, pg.w[5]);
-      atomicAdd(gs + R2 + R, pg.w[6]);
-      atomicAdd(gs + R2 + R + 1, pg.w[7]);
-    }
+    pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, zc, gup, exact, pg);
+    if (WANT_SDF) scatter_sdf<RT>(gsdf, P.grid, pg);
     if (WANT_POSE) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * gup;
     }
   }
 
-  if (WANT_POSE) {
-    /* registers -> warp shuffle -> shared -> 8 atomics per CTA (the reference issues 8
-     * same-address atomics per hit pixel, cu:459-466) */
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-    if (lane == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) red[warp][i] = acc[i];
+  if (WANT_POSE)
+    reduce_pose(acc, red, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
+}
+
+/* grad *= upstream[b] / n_overlap[b]: the normalisation the fused compare kernel defers. */
+__global__ void __launch_bounds__(256)
+sdfr_scale_grads_kernel(const float* __restrict__ n_overlap, const float* __restrict__ upstream,
+                        long long grid_elems, float* __restrict__ grad_sdf, long long gs_stride,
+                        float* __restrict__ gp, float* __restrict__ gq, float* __restrict__ gi,
+                        unsigned flags) {
+  const int b = blockIdx.y;
+  const float n = __ldg(n_overlap + b);
+  const float u = upstream ? __ldg(upstream + b) : 1.0f;
+  const float coef = n > 0.0f ? u / n : 0.0f;
+  if (blockIdx.x == 0 && threadIdx.x < 8) {
+    const int i = threadIdx.x;
+    if (i < 3) {
+      if (flags & SDFR_GRAD_POSITION) gp[3 * b + i] *= coef;
+    } else if (i < 7) {
+      if (flags & SDFR_GRAD_ORIENTATION) gq[4 * b + (i - 3)] *= coef;
+    } else {
+      if (flags & SDFR_GRAD_INV_SCALE) gi[b] *= coef;
     }
-    __syncthreads();
-    if (threadIdx.x < 8) {
-      float s = 0.0f;
-#pragma unroll
-      for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
-      const int i = threadIdx.x;
-      if (s != 0.0f) {
-        if (i < 3) {
-          if (P.flags & SDFR_GRAD_POSITION) atomicAdd(P.grad_position + 3 * b + i, s);
-        } else if (i < 7) {
-          if (P.flags & SDFR_GRAD_ORIENTATION) atomicAdd(P.grad_orientation + 4 * b + (i - 3), s);
-        } else {
-          if (P.flags & SDFR_GRAD_INV_SCALE) atomicAdd(P.grad_inv_scale + b, s);
-        }
-      }
+  }
+  if (flags & SDFR_GRAD_SDF) {
+    float* __restrict__ gs = grad_sdf + (size_t)b * gs_stride;
+    const long long n4 = ((reinterpret_cast<uintptr_t>(gs) & 15) == 0) ? grid_elems / 4 : 0;
+    float4* __restrict__ gs4 = reinterpret_cast<float4*>(gs);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
+         i += (long long)gridDim.x * blockDim.x) {
+      float4 v = gs4[i];
+      v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
+      gs4[i] = v;
     }
+    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < grid_elems;
+         i += (long long)gridDim.x * blockDim.x)
+      gs[i] *= coef;
+  }
+}
+
+/* zero up to three small buffers in one launch (pose-gradient outputs) */
+__global__ void sdfr_zero_small_kernel(float* a, int na, float* b, int nb, float* c, int nc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na + nb + nc; i += gridDim.x * blockDim.x) {
+    if (i < na) a[i] = 0.0f;
+    else if (i < na + nb) b[i - na] = 0.0f;
+    else c[i - na - nb] = 0.0f;
   }
 }
 
@@ -601,12 +747,26 @@ size_t table_bytes(int W, int H) {
   return n * sizeof(float) <= 40 * 1024 ? n * sizeof(float) : 0;
 }
 
-template <int RT, bool COMPARE, bool STATS>
+template <int RT, int MODE, bool STATS>
 void launch_forward_rt(FwdParams& P, dim3 grid, size_t smem, cudaStream_t s) {
-  sdfr_forward_kernel<RT, COMPARE, STATS><<<grid, kThreads, smem, s>>>(P);
+  if (MODE != 2) {
+    sdfr_forward_kernel<RT, MODE, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
+    return;
+  }
+  const bool want_sdf = (P.flags & SDFR_GRAD_SDF) != 0;
+  const bool want_pose =
+      (P.flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
+  if (want_sdf && want_pose)
+    sdfr_forward_kernel<RT, MODE, STATS, true, true><<<grid, kThreads, smem, s>>>(P);
+  else if (want_sdf)
+    sdfr_forward_kernel<RT, MODE, STATS, true, false><<<grid, kThreads, smem, s>>>(P);
+  else if (want_pose)
+    sdfr_forward_kernel<RT, MODE, STATS, false, true><<<grid, kThreads, smem, s>>>(P);
+  else
+    sdfr_forward_kernel<RT, 1, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
 }
 
-template <bool COMPARE, bool STATS>
+template <int MODE, bool STATS>
 int launch_forward(FwdParams P, int batch, cudaStream_t s) {
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
@@ -615,10 +775,10 @@ int launch_forward(FwdParams P, int batch, cudaStream_t s) {
     P.z_offset = z0;
     const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
     switch (P.grid.R) { /* common resolutions get immediate-offset gathers */
-      case 64: launch_forward_rt<64, COMPARE, STATS>(P, grid, smem, s); break;
-      case 128: launch_forward_rt<128, COMPARE, STATS>(P, grid, smem, s); break;
-      case 32: launch_forward_rt<32, COMPARE, STATS>(P, grid, smem, s); break;
-      default: launch_forward_rt<0, COMPARE, STATS>(P, grid, smem, s); break;
+      case 64: launch_forward_rt<64, MODE, STATS>(P, grid, smem, s); break;
+      case 128: launch_forward_rt<128, MODE, STATS>(P, grid, smem, s); break;
+      case 32: launch_forward_rt<32, MODE, STATS>(P, grid, smem, s); break;
+      default: launch_forward_rt<0, MODE, STATS>(P, grid, smem, s); break;
     }
   }
   return check_launch("sdfr_forward_kernel");
@@ -682,9 +842,15 @@ int zero_grads(unsigned flags, int R, int batch, float* gs, long long gs_stride,
         rc = zero_async(gs + (size_t)b * gs_stride, grid_elems * sizeof(float), s);
     }
   }
-  if (rc == 0 && (flags & SDFR_GRAD_POSITION)) rc = zero_async(gp, sizeof(float) * 3 * batch, s);
-  if (rc == 0 && (flags & SDFR_GRAD_ORIENTATION)) rc = zero_async(gq, sizeof(float) * 4 * batch, s);
-  if (rc == 0 && (flags & SDFR_GRAD_INV_SCALE)) rc = zero_async(gi, sizeof(float) * batch, s);
+  if (rc == 0 && (flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE))) {
+    /* the three small outputs in ONE launch instead of three memset nodes */
+    const int na = (flags & SDFR_GRAD_POSITION) ? 3 * batch : 0;
+    const int nb = (flags & SDFR_GRAD_ORIENTATION) ? 4 * batch : 0;
+    const int nc = (flags & SDFR_GRAD_INV_SCALE) ? batch : 0;
+    const int n = na + nb + nc;
+    sdfr_zero_small_kernel<<<n > 4096 ? 16 : 1, 256, 0, s>>>(gp, na, gq, nb, gi, nc);
+    rc = check_launch("sdfr_zero_small_kernel");
+  }
   return rc;
 }
 
@@ -743,7 +909,7 @@ int sdfr_forward(const float* sdf, int R, long long sdf_stride, const float* pos
   if (!depth) return fail(SDFR_E_NULL, "depth is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
-  return launch_forward<false, false>(P, batch, (cudaStream_t)stream);
+  return launch_forward<0, false>(P, batch, (cudaStream_t)stream);
 }
 
 int sdfr_forward_stats(const float* sdf, int R, long long sdf_stride, const float* pos,
@@ -756,7 +922,7 @@ int sdfr_forward_stats(const float* sdf, int R, long long sdf_stride, const floa
   FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   P.stats = stats;
-  return launch_forward<false, true>(P, batch, (cudaStream_t)stream);
+  return launch_forward<0, true>(P, batch, (cudaStream_t)stream);
 }
 
 int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int R,
@@ -800,7 +966,7 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, const fl
   P.obs_stride = obs_stride;
   P.loss_sum = loss_sum;
   P.n_overlap = n_overlap;
-  return launch_forward<true, false>(P, batch, s);
+  return launch_forward<1, false>(P, batch, s);
 }
 
 int sdfr_compare_backward(const float* depth, const float* depth_obs, long long obs_stride,
@@ -825,6 +991,66 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   P.n_overlap = n_overlap;
   P.upstream = upstream;
   return launch_backward<1>(P, batch, s);
+}
+
+int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, const float* pos,
+                       const float* quat, const float* inv_scale, int batch, int W, int H,
+                       float cx, float cy, float fx, float fy, float threshold,
+                       const float* depth_obs, long long obs_stride, float* depth,
+                       float* loss_sum, float* n_overlap, float* gs, long long gs_stride,
+                       float* gp, float* gq, float* gi, unsigned flags, void* stream) {
+  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
+  if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
+  if ((flags & SDFR_GRAD_SDF) && gs_stride == 0 && batch > 1)
+    return fail(SDFR_E_SHAPE,
+                "fused compare needs one grad_sdf grid per hypothesis (the deferred 1/n_overlap "
+                "differs per hypothesis); use sdfr_compare_forward + sdfr_compare_backward");
+  if (batch == 0) return 0;
+  if (!loss_sum || !n_overlap) return fail(SDFR_E_NULL, "loss_sum or n_overlap is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & SDFR_ZERO_GRADS) {
+    if (int rc = zero_async(loss_sum, sizeof(float) * batch, s)) return rc;
+    if (int rc = zero_async(n_overlap, sizeof(float) * batch, s)) return rc;
+  }
+  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
+  if (W == 0 || H == 0) return 0;
+  if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
+  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+                           threshold, depth);
+  P.depth_obs = depth_obs;
+  P.obs_stride = obs_stride;
+  P.loss_sum = loss_sum;
+  P.n_overlap = n_overlap;
+  P.grad_sdf = gs;
+  P.grad_sdf_stride = gs_stride;
+  P.grad_position = gp;
+  P.grad_orientation = gq;
+  P.grad_inv_scale = gi;
+  P.flags = flags;
+  return launch_forward<2, false>(P, batch, s);
+}
+
+int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int batch, float* gs,
+                     long long gs_stride, float* gp, float* gq, float* gi, unsigned flags,
+                     void* stream) {
+  if (batch < 0) return fail(SDFR_E_SHAPE, "negative batch");
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (int rc = check_backward_outputs(flags & ~SDFR_ZERO_GRADS, gs, gs_stride, gp, gq, gi)) return rc;
+  if (batch == 0 || !(flags & SDFR_GRAD_ALL)) return 0;
+  if (!n_overlap) return fail(SDFR_E_NULL, "n_overlap is NULL");
+  if ((flags & SDFR_GRAD_SDF) && gs_stride == 0 && batch > 1)
+    return fail(SDFR_E_SHAPE, "a shared grad_sdf grid cannot be scaled per hypothesis");
+  const long long elems = (long long)R * R * R;
+  const int gx = (flags & SDFR_GRAD_SDF) ? (int)((elems / 4 + 2047) / 2048 < 1 ? 1 : (elems / 4 + 2047) / 2048) : 1;
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    const int nz = batch - z0 < 65535 ? batch - z0 : 65535;
+    sdfr_scale_grads_kernel<<<dim3(gx, nz), 256, 0, (cudaStream_t)stream>>>(
+        n_overlap + z0, upstream ? upstream + z0 : nullptr, elems,
+        gs ? gs + (size_t)z0 * gs_stride : nullptr, gs_stride, gp ? gp + 3 * (size_t)z0 : nullptr,
+        gq ? gq + 4 * (size_t)z0 : nullptr, gi ? gi + z0 : nullptr, flags);
+  }
+  return check_launch("sdfr_scale_grads_kernel");
 }
 
 int sdfr_forward_composite(const float* sdf, int R, long long sdf_stride, const float* pos,

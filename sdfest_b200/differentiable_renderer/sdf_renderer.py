@@ -174,10 +174,15 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
         W, H, cx, cy, fx, fy = ctx.cam
         needs = ctx.needs_input_grad[:4]
         flags = _grad_flags(needs, ctx.sdf_grad_mode)
-        g_sdf = torch.zeros_like(sdf) if needs[0] else None
-        g_p = torch.zeros_like(position) if needs[1] else None
-        g_q = torch.zeros_like(orientation) if needs[2] else None
-        g_is = torch.zeros_like(inv_scale) if needs[3] else None
+        if position.numel() == 3 and orientation.numel() == 4 and inv_scale.numel() == 1:
+            alloc = torch.empty_like  # the library clears exactly these elements itself
+            flags |= _lib.ZERO_GRADS
+        else:  # over-long pose tensors: the tail must read as zero
+            alloc = torch.zeros_like
+        g_sdf = alloc(sdf) if needs[0] else None
+        g_p = alloc(position) if needs[1] else None
+        g_q = alloc(orientation) if needs[2] else None
+        g_is = alloc(inv_scale) if needs[3] else None
         if any(needs):
             grad_depth_image = grad_depth_image.contiguous()
             _check_input(grad_depth_image, "grad_depth_image")
@@ -273,10 +278,11 @@ class _BatchedRender(torch.autograd.Function):
         B, R, stride, W, H, cx, cy, fx, fy, mode = ctx.meta
         needs = ctx.needs_input_grad[:4]
         flags = _grad_flags(needs, mode)
-        g_sdf = torch.zeros_like(sdf) if needs[0] else None
-        g_p = torch.zeros_like(position) if needs[1] else None
-        g_q = torch.zeros_like(orientation) if needs[2] else None
-        g_is = torch.zeros_like(inv_scale) if needs[3] else None
+        g_sdf = torch.empty_like(sdf) if needs[0] else None
+        g_p = torch.empty_like(position) if needs[1] else None
+        g_q = torch.empty_like(orientation) if needs[2] else None
+        g_is = torch.empty_like(inv_scale) if needs[3] else None
+        flags |= _lib.ZERO_GRADS
         if any(needs):
             grad_depth = grad_depth.contiguous()
             _check_input(grad_depth, "grad_depth")
@@ -303,6 +309,10 @@ def render_depth_batched(sdf: torch.Tensor, position: torch.Tensor, orientation:
 
 
 class _RenderAndCompare(torch.autograd.Function):
+    """Masked-L1 render-and-compare.  When a gradient will be needed, the backward is folded into
+    the forward traversal (sdfr_compare_fused: one kernel, unnormalised gradients) and backward()
+    only applies the per-hypothesis factor upstream/n_overlap (sdfr_scale_grads)."""
+
     @staticmethod
     def forward(ctx, sdf, position, orientation, inv_scale, depth_obs, threshold, camera,
                 sdf_grad_mode):
@@ -316,18 +326,35 @@ class _RenderAndCompare(torch.autograd.Function):
         else:
             raise RuntimeError(
                 f"depth_obs must have shape ({H},{W}) or ({B},{H},{W}), got {tuple(depth_obs.shape)}")
+        needs = tuple(ctx.needs_input_grad[:4])
+        # a grid shared by several hypotheses cannot take the deferred per-hypothesis scaling
+        fused = any(needs) and not (needs[0] and stride == 0 and B > 1)
+        grads = [None, None, None, None]
         with torch.cuda.device_of(sdf):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
-            sums = torch.zeros((2, B), dtype=torch.float32, device=sdf.device)
-            _lib.check(_lib.lib().sdfr_compare_forward(
-                sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
-                inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
-                depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
-                sums[1].data_ptr(), 0, _stream()), "sdfr_compare_forward")
+            sums = torch.empty((2, B), dtype=torch.float32, device=sdf.device)
+            lib = _lib.lib()
+            if fused:
+                flags = _grad_flags(needs, sdf_grad_mode) | _lib.ZERO_GRADS
+                grads = [torch.empty_like(t) if n else None
+                         for t, n in zip((sdf, position, orientation, inv_scale), needs)]
+                _lib.check(lib.sdfr_compare_fused(
+                    sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
+                    inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
+                    depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
+                    sums[1].data_ptr(), _ptr(grads[0]), stride, _ptr(grads[1]), _ptr(grads[2]),
+                    _ptr(grads[3]), flags, _stream()), "sdfr_compare_fused")
+            else:
+                _lib.check(lib.sdfr_compare_forward(
+                    sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
+                    inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
+                    depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
+                    sums[1].data_ptr(), _lib.ZERO_GRADS, _stream()), "sdfr_compare_forward")
             loss = sums[0] / sums[1]  # NaN where nothing overlaps, as torch.mean of an empty set
             n_overlap = sums[1].clone()
         ctx.save_for_backward(depth, depth_obs, sums, sdf, position, orientation, inv_scale)
         ctx.meta = (B, R, stride, obs_stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
+        ctx.fused_grads = grads if fused else None
         ctx.mark_non_differentiable(depth, n_overlap)
         return loss, depth, n_overlap
 
@@ -336,20 +363,30 @@ class _RenderAndCompare(torch.autograd.Function):
         depth, depth_obs, sums, sdf, position, orientation, inv_scale = ctx.saved_tensors
         B, R, stride, obs_stride, W, H, cx, cy, fx, fy, mode = ctx.meta
         needs = ctx.needs_input_grad[:4]
+        if not any(needs):
+            return (None,) * 8
         flags = _grad_flags(needs, mode)
-        g_sdf = torch.zeros_like(sdf) if needs[0] else None
-        g_p = torch.zeros_like(position) if needs[1] else None
-        g_q = torch.zeros_like(orientation) if needs[2] else None
-        g_is = torch.zeros_like(inv_scale) if needs[3] else None
-        if any(needs):
-            upstream = grad_loss.to(torch.float32).contiguous()
-            with torch.cuda.device_of(sdf):
-                _lib.check(_lib.lib().sdfr_compare_backward(
+        upstream = grad_loss.to(torch.float32).contiguous()
+        lib = _lib.lib()
+        with torch.cuda.device_of(sdf):
+            if ctx.fused_grads is not None:
+                # the traversal already happened: only the deferred upstream/n_overlap factor is left
+                g_sdf, g_p, g_q, g_is = ctx.fused_grads
+                ctx.fused_grads = None  # scaled in place: a second backward re-traverses below
+                _lib.check(lib.sdfr_scale_grads(
+                    sums[1].data_ptr(), upstream.data_ptr(), R, B, _ptr(g_sdf), stride, _ptr(g_p),
+                    _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_scale_grads")
+            else:
+                g_sdf = torch.empty_like(sdf) if needs[0] else None
+                g_p = torch.empty_like(position) if needs[1] else None
+                g_q = torch.empty_like(orientation) if needs[2] else None
+                g_is = torch.empty_like(inv_scale) if needs[3] else None
+                _lib.check(lib.sdfr_compare_backward(
                     depth.data_ptr(), depth_obs.data_ptr(), obs_stride, sums[1].data_ptr(),
                     upstream.data_ptr(), sdf.data_ptr(), R, stride, position.data_ptr(),
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
-                    _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is), flags, _stream()),
-                    "sdfr_compare_backward")
+                    _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is),
+                    flags | _lib.ZERO_GRADS, _stream()), "sdfr_compare_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None, None
 
 
@@ -390,10 +427,11 @@ class _CompositeRender(torch.autograd.Function):
         K, R, stride, W, H, cx, cy, fx, fy, mode = ctx.meta
         needs = ctx.needs_input_grad[:4]
         flags = _grad_flags(needs, mode)
-        g_sdf = torch.zeros_like(sdf) if needs[0] else None
-        g_p = torch.zeros_like(position) if needs[1] else None
-        g_q = torch.zeros_like(orientation) if needs[2] else None
-        g_is = torch.zeros_like(inv_scale) if needs[3] else None
+        g_sdf = torch.empty_like(sdf) if needs[0] else None
+        g_p = torch.empty_like(position) if needs[1] else None
+        g_q = torch.empty_like(orientation) if needs[2] else None
+        g_is = torch.empty_like(inv_scale) if needs[3] else None
+        flags |= _lib.ZERO_GRADS
         if any(needs):
             grad_depth = grad_depth.contiguous()
             _check_input(grad_depth, "grad_depth")

@@ -501,3 +501,120 @@ def test_rejects_bad_inputs_on_gpu(cuda_device):
     assert render_depth_batched(good[0], torch.zeros(0, 3, device=cuda_device),
                                 torch.zeros(0, 4, device=cuda_device),
                                 torch.zeros(0, device=cuda_device), 0.01, cam).shape == (0, 24, 32)
+
+
+# ------------------------------------------------------------------------------------------
+# fused compare+backward traversal, deferred normalisation, and the batched loop
+# ------------------------------------------------------------------------------------------
+def _compare_setup(cuda_device, B=3, W=320, H=240, shared=False, seed=6):
+    thr = 0.005
+    cam_d = default_camera(W, H)
+    cam = cam_obj(W, H, cam_d)
+    grid = mug_sdf()
+    grids = grid if shared else np.stack([grid + np.float32(0.001 * i) for i in range(B)])
+    pos, quat, inv_s = hypotheses(B, seed=seed)
+    obs = oracle.render(grid, [0.02, -0.01, -0.45], shoemake(seed * 1000), 1 / 0.15, W, H,
+                        threshold=thr, nthreads=8, **cam_d)
+    mk = lambda: [T(grids, cuda_device, True), T(pos, cuda_device, True),
+                  T(quat, cuda_device, True), T(inv_s, cuda_device, True)]
+    return mk, T(obs, cuda_device), thr, cam
+
+
+def test_fused_traversal_equals_two_kernel_path(cuda_device):
+    """sdfr_compare_fused + sdfr_scale_grads == sdfr_compare_forward + sdfr_compare_backward."""
+    mk, obs, thr, cam = _compare_setup(cuda_device)
+    w = torch.tensor([1.0, 0.3, 2.5], device=cuda_device)
+    a = mk()
+    loss, depth, n = render_and_compare(*a, obs, thr, cam)
+    (loss * w).sum().backward(retain_graph=True)
+    first = [x.grad.clone() for x in a]
+    for x in a:
+        x.grad = None
+    # the second backward cannot reuse the (already scaled) fused buffers: it re-traverses with
+    # the two-kernel path and must give the same gradients
+    (loss * w).sum().backward()
+    for nm, f, x in zip(["sdf", "position", "orientation", "inv_scale"], first, a):
+        grad_close(x.grad.cpu().numpy(), f.cpu().numpy(), 2e-4, "fused vs two-kernel " + nm)
+    assert all(float(f.abs().max()) > 0 for f in first)
+
+
+def test_shared_grid_compare_falls_back_and_accumulates(cuda_device):
+    mk, obs, thr, cam = _compare_setup(cuda_device, shared=True)
+    a = mk()
+    loss, depth, n = render_and_compare(*a, obs, thr, cam)
+    loss.sum().backward()
+    per = mk()
+    per[0] = torch.stack([a[0].detach()] * 3).requires_grad_(True)
+    loss2, _, _ = render_and_compare(*per, obs, thr, cam)
+    loss2.sum().backward()
+    assert torch.equal(loss, loss2)
+    grad_close(a[0].grad.cpu().numpy(), per[0].grad.sum(0).cpu().numpy(), 2e-4, "shared compare sdf")
+    grad_close(a[1].grad.cpu().numpy(), per[1].grad.cpu().numpy(), 2e-4, "shared compare pos")
+
+
+def test_compare_only_pose_or_only_sdf_gradients(cuda_device):
+    mk, obs, thr, cam = _compare_setup(cuda_device)
+    full = mk()
+    render_and_compare(*full, obs, thr, cam)[0].sum().backward()
+    only_sdf = mk()
+    for x in only_sdf[1:]:
+        x.requires_grad_(False)
+    render_and_compare(*only_sdf, obs, thr, cam)[0].sum().backward()
+    grad_close(only_sdf[0].grad.cpu().numpy(), full[0].grad.cpu().numpy(), 1e-4, "sdf only")
+    only_pose = mk()
+    only_pose[0].requires_grad_(False)
+    render_and_compare(*only_pose, obs, thr, cam)[0].sum().backward()
+    for i in (1, 2, 3):
+        grad_close(only_pose[i].grad.cpu().numpy(), full[i].grad.cpu().numpy(), 1e-4, "pose only")
+    with torch.no_grad():
+        l, d, n = render_and_compare(*mk(), obs, thr, cam)
+    assert torch.isfinite(l).all() and (n > 0).all()
+
+
+def test_single_frame_small_batch_paths(cuda_device):
+    """B=1 uses one CTA per box tile with tile-local ray tables; must equal the oracle too."""
+    for W, H in ((640, 480), (100, 37)):
+        cam_d = default_camera(W, H)
+        sdf, pos, q, inv_s = mug_sdf(), np.float32([0.02, -0.01, -0.4]), shoemake(1), np.float32(1 / 0.15)
+        d = render_depth_gpu(T(sdf, cuda_device), T(pos, cuda_device), T(q, cuda_device),
+                             T([inv_s], cuda_device), threshold=0.005, camera=cam_obj(W, H, cam_d))
+        ref = oracle.render(sdf, pos, q, inv_s, W, H, threshold=0.005, nthreads=8, **cam_d)
+        depth_parity(d.cpu().numpy(), ref, 0.005, rtol=DEPTH_RTOL)
+
+
+def test_large_batch_few_ctas_per_hypothesis(cuda_device):
+    """B large enough that every CTA walks many tiles (G small): same images as one by one."""
+    B, W, H, thr = 300, 96, 64, 0.005
+    cam = cam_obj(W, H, default_camera(W, H))
+    pos, quat, inv_s = hypotheses(B, seed=9)
+    a = [T(mug_sdf(), cuda_device), T(pos, cuda_device), T(quat, cuda_device), T(inv_s, cuda_device)]
+    d = render_depth_batched(*a, thr, cam)
+    for b in (0, 17, 299):
+        one = render_depth_gpu(a[0], a[1][b], a[2][b], a[3][b:b + 1], threshold=thr, camera=cam)
+        assert torch.equal(one, d[b])
+
+
+def test_hypothesis_optimizer_recovers_pose(cuda_device):
+    """The batched render-and-compare loop (simple_setup.py:400-470 for B hypotheses): losses
+    fall and the best hypothesis approaches the pose that generated the observation."""
+    from sdfest_b200.estimation import HypothesisOptimizer
+    from sdfest_b200 import synthetic as syn
+
+    W, H, thr, B = 320, 240, 0.005, 8
+    cam = cam_obj(W, H, default_camera(W, H))
+    grid = syn.sdf_mug(64, cuda_device)
+    hyp = syn.make_hypotheses(B, seed=3, device=cuda_device, pos_sigma=0.01, rot_deg=5.0,
+                              scale_rel=0.05)
+    true_p, true_q = hyp["position"][0:1].clone(), hyp["orientation"][0:1].clone()
+    true_s = 1.0 / hyp["inv_scale"][0:1]
+    obs = render_depth_batched(grid, true_p, true_q, 1.0 / true_s, thr, cam)[0].contiguous()
+    opt = HypothesisOptimizer(cam, thr, obs, hyp["position"][1:], hyp["orientation"][1:],
+                              1.0 / hyp["inv_scale"][1:], sdf=grid[None], max_points=2000)
+    first = opt.step().clone()
+    last = opt.run(60)
+    assert torch.isfinite(last).all()
+    assert (last < first).float().mean() > 0.8
+    best = int(torch.argmin(last))
+    err0 = torch.linalg.norm(hyp["position"][1:][best] - true_p[0]).item()
+    err1 = torch.linalg.norm(opt.position[best].detach() - true_p[0]).item()
+    assert err1 < max(0.5 * err0, 2e-3), (err0, err1)
