@@ -547,7 +547,9 @@ def test_shared_grid_compare_falls_back_and_accumulates(cuda_device):
     per[0] = torch.stack([a[0].detach()] * 3).requires_grad_(True)
     loss2, _, _ = render_and_compare(*per, obs, thr, cam)
     loss2.sum().backward()
-    assert torch.equal(loss, loss2)
+    # same pixels, but the per-warp partial sums reach the loss accumulator through float atomics
+    # in launch-dependent order: equal to rounding, not bit for bit
+    assert torch.allclose(loss, loss2, rtol=1e-5, atol=0)
     grad_close(a[0].grad.cpu().numpy(), per[0].grad.sum(0).cpu().numpy(), 2e-4, "shared compare sdf")
     grad_close(a[1].grad.cpu().numpy(), per[1].grad.cpu().numpy(), 2e-4, "shared compare pos")
 
