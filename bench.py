@@ -248,25 +248,41 @@ def main():
     RRR = R * R * R
     flags_b = _lib.GRAD_ALL | _lib.ZERO_GRADS
 
+    import ctypes
+
+    n_sk = ctypes.c_longlong(0)
+    _lib.check(lib.sdfr_skewed_pitches(R, None, None, ctypes.byref(n_sk)), "sdfr_skewed_pitches")
+    SK = int(n_sk.value)
+    skewed = torch.empty(B, SK, device=dev)
+
+    def skew():
+        # dense decoder-layout grids -> bank-conflict-free pitched copy (one streaming pass); part
+        # of every step because the grids change every iteration when the latent is optimised
+        _lib.check(lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, stream),
+                   "sdfr_skew_grids")
+
     def fwd():
         _lib.check(lib.sdfr_compare_forward(
-            grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
-            CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
-            sums[1].data_ptr(), _lib.ZERO_GRADS, stream), "sdfr_compare_forward")
+            skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
+            inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
+            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, stream),
+            "sdfr_compare_forward")
 
     def bwd():
         _lib.check(lib.sdfr_compare_backward(
-            depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None, grids.data_ptr(), R,
-            RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, CX, CY, FX, FY,
-            g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
-            stream), "sdfr_compare_backward")
+            depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None, skewed.data_ptr(), R,
+            SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
+            CX, CY, FX, FY, g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
+            g_is.data_ptr(), flags_b, stream), "sdfr_compare_backward")
 
-    def fused():
+    def fused(dense=False):
         _lib.check(lib.sdfr_compare_fused(
-            grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
-            CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
-            sums[1].data_ptr(), g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
-            g_is.data_ptr(), flags_b, stream), "sdfr_compare_fused")
+            (grids if dense else skewed).data_ptr(), R, RRR if dense else SK,
+            _lib.LAYOUT_DENSE if dense else _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
+            inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
+            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), RRR,
+            g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b, stream),
+            "sdfr_compare_fused")
 
     def scale():
         _lib.check(lib.sdfr_scale_grads(
@@ -274,8 +290,9 @@ def main():
             g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, stream), "sdfr_scale_grads")
 
     def step():
-        # forward render + masked-L1 compare + backward in ONE traversal, then the deferred
-        # per-hypothesis normalisation of the gradients
+        # layout pass, then forward render + masked-L1 compare + backward in ONE traversal, then
+        # the deferred per-hypothesis normalisation of the gradients
+        skew()
         fused()
         scale()
         if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
@@ -320,7 +337,10 @@ def main():
     ms_per_step = total_ms / K
 
     # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
+    skew()
     fused_ms = timed(fused, K, 2) / K
+    fused_dense_ms = timed(lambda: fused(True), K, 2) / K
+    skew_ms = timed(skew, K, 2) / K
     scale_ms = timed(scale, K, 2) / K
     fwd_ms = timed(fwd, K, 2) / K
     bwd_ms = timed(bwd, K, 2) / K
@@ -388,7 +408,7 @@ def main():
     dom_bytes, dom_ms = fused_bytes, fused_ms
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "sdfr_forward_kernel<64, MODE=2> (fused render+compare+backward, incl. its memsets)",
+        "bound": "hbm", "kernel": "sdfr_forward_kernel<64, skewed, MODE=2> (fused render+compare+backward, incl. its memsets)",
         "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
@@ -397,6 +417,9 @@ def main():
                  "the HBM copy peak, not a claim of HBM traffic"),
         "kernels": {
             "fused_incl_memsets": {"ms": fused_ms, "bytes": fused_bytes, "GBps": fused_bytes / fused_ms / 1e6},
+            "fused_dense_layout_incl_memsets": {"ms": fused_dense_ms, "bytes": fused_bytes,
+                                                "GBps": fused_bytes / fused_dense_ms / 1e6},
+            "skew_grids": {"ms": skew_ms, "bytes": 4 * (RRR + SK) * B, "GBps": 4 * (RRR + SK) * B / skew_ms / 1e6},
             "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
             "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
             "unfused_backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
@@ -418,7 +441,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "api": "render_and_compare + autograd backward, pinned host buffers",
                 "checksum": e2e_check},
-        "gpu_launches": 3 * K,  # fused kernel + pose-zero kernel + scale kernel per step
+        "gpu_launches": 4 * K,  # skew + pose-zero + fused + scale kernels per step
         "clocks": clocks.summary(),
         "lib": lib.sdfr_build_info().decode(),
     }

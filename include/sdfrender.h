@@ -19,6 +19,10 @@
  *   - sdf: `resolution`^3 grid(s), index order x,y,z with z contiguous (sdf_renderer_cuda.cu:13,
  *     226-238).  Any resolution >= 2 (the reference kernels hard-code 64: :225-230, 327, 347).
  *     Hypothesis b reads the grid at sdf + b*sdf_stride (elements); sdf_stride = 0 shares one grid.
+ *     sdf_layout = SDFR_LAYOUT_DENSE is that layout; SDFR_LAYOUT_SKEWED is the pitched copy made by
+ *     sdfr_skew_grids (same fp32 values, element (x,y,z) at x*pitch_x + y*pitch_y + z), which
+ *     removes the L1 bank conflicts of the 8-corner gathers.  Gradient
+ *     grids are always dense.
  *   - position [batch,3], orientation [batch,4] (x,y,z,w; must be unit length -- not normalised,
  *     sdf_renderer_cuda.cu:95-98 is never instantiated), inv_scale [batch]: pose of the grid in the
  *     OpenGL camera frame (camera looks down -z, y up; image row 0 is the top row).
@@ -42,11 +46,15 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 1
+#define SDFR_ABI_VERSION 2
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
 #define SDFR_E_FLAGS (-3) /* unknown flag bits */
+
+/* sdf_layout */
+#define SDFR_LAYOUT_DENSE 0
+#define SDFR_LAYOUT_SKEWED 1
 
 /* flags of the backward entry points */
 #define SDFR_GRAD_SDF 0x01u
@@ -69,10 +77,23 @@ const char* sdfr_build_info(void);
 int sdfr_max_steps(void);
 
 /*
+ * Skewed layout: pitches (elements) and the number of elements one skewed grid occupies.
+ * Any of the output pointers may be NULL.
+ */
+int sdfr_skewed_pitches(int resolution, int* pitch_y, int* pitch_x, long long* elems);
+
+/*
+ * Copy `batch` dense grids (sdf + b*sdf_stride) into skewed grids (skewed + b*skewed_stride,
+ * skewed_stride >= elems of sdfr_skewed_pitches).  One streaming pass, ~2*4*R^3 bytes per grid.
+ */
+int sdfr_skew_grids(const float* sdf, int resolution, long long sdf_stride, int batch,
+                    float* skewed, long long skewed_stride, void* stream);
+
+/*
  * Forward: replaces sdf_renderer_cpp.forward (sdf_renderer.cpp:42-61 ->
  * sdf_renderer_cuda.cu:472-510 -> forward kernel :241-298), batched over `batch` hypotheses.
  */
-int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, const float* position,
+int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, int sdf_layout, const float* position,
                  const float* orientation, const float* inv_scale, int batch, int width,
                  int height, float cx, float cy, float fx, float fy, float threshold,
                  float* depth, void* stream);
@@ -82,7 +103,7 @@ int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, const f
  * unsigned long long, caller-zeroed): [0] trilinear samples, [1] pixels whose ray enters the
  * box, [2] hit pixels, [3] rays stopped by the step cap.  Used for the roofline's S and Hh.
  */
-int sdfr_forward_stats(const float* sdf, int resolution, long long sdf_stride,
+int sdfr_forward_stats(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                        const float* position, const float* orientation, const float* inv_scale,
                        int batch, int width, int height, float cx, float cy, float fx, float fy,
                        float threshold, float* depth, unsigned long long* stats, void* stream);
@@ -95,7 +116,7 @@ int sdfr_forward_stats(const float* sdf, int resolution, long long sdf_stride,
  * grad_orientation [batch,4] (x,y,z,w), grad_inv_scale [batch].
  */
 int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int resolution,
-                  long long sdf_stride, const float* position, const float* orientation,
+                  long long sdf_stride, int sdf_layout, const float* position, const float* orientation,
                   const float* inv_scale, int batch, int width, int height, float cx, float cy,
                   float fx, float fy, float* grad_sdf, long long grad_sdf_stride,
                   float* grad_position, float* grad_orientation, float* grad_inv_scale,
@@ -109,7 +130,7 @@ int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf,
  * unless SDFR_ZERO_GRADS is in `flags`), so that loss_depth[b] = loss_sum[b] / n_overlap[b].
  * depth_obs: hypothesis b compares with depth_obs + b*obs_stride (0 = one shared map).
  */
-int sdfr_compare_forward(const float* sdf, int resolution, long long sdf_stride,
+int sdfr_compare_forward(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                          const float* position, const float* orientation,
                          const float* inv_scale, int batch, int width, int height, float cx,
                          float cy, float fx, float fy, float threshold, const float* depth_obs,
@@ -124,7 +145,7 @@ int sdfr_compare_forward(const float* sdf, int resolution, long long sdf_stride,
  */
 int sdfr_compare_backward(const float* depth, const float* depth_obs, long long obs_stride,
                           const float* n_overlap, const float* upstream, const float* sdf,
-                          int resolution, long long sdf_stride, const float* position,
+                          int resolution, long long sdf_stride, int sdf_layout, const float* position,
                           const float* orientation, const float* inv_scale, int batch,
                           int width, int height, float cx, float cy, float fx, float fy,
                           float* grad_sdf, long long grad_sdf_stride, float* grad_position,
@@ -140,7 +161,7 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
  * optimizer step).  With SDFR_GRAD_SDF each hypothesis needs its own grad grid
  * (grad_sdf_stride != 0 unless batch == 1).  SDFR_ZERO_GRADS also clears loss_sum / n_overlap.
  */
-int sdfr_compare_fused(const float* sdf, int resolution, long long sdf_stride,
+int sdfr_compare_fused(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                        const float* position, const float* orientation, const float* inv_scale,
                        int batch, int width, int height, float cx, float cy, float fx, float fy,
                        float threshold, const float* depth_obs, long long obs_stride,
@@ -161,7 +182,7 @@ int sdfr_scale_grads(const float* n_overlap, const float* upstream, int resoluti
  * the pixel (-1 = none; ties go to the lowest index).  No counterpart in the reference (it
  * renders one object per call); semantics are those of oracle.composite_min_depth.
  */
-int sdfr_forward_composite(const float* sdf, int resolution, long long sdf_stride,
+int sdfr_forward_composite(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                            const float* position, const float* orientation,
                            const float* inv_scale, int n_objects, int width, int height,
                            float cx, float cy, float fx, float fy, float threshold, float* depth,
@@ -169,7 +190,7 @@ int sdfr_forward_composite(const float* sdf, int resolution, long long sdf_strid
 
 /* Backward of sdfr_forward_composite: every pixel back-propagates to its winner. */
 int sdfr_backward_composite(const float* grad_depth, const float* depth, const int* winner,
-                            const float* sdf, int resolution, long long sdf_stride,
+                            const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                             const float* position, const float* orientation,
                             const float* inv_scale, int n_objects, int width, int height,
                             float cx, float cy, float fx, float fy, float* grad_sdf,

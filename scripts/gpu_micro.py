@@ -59,9 +59,9 @@ st = torch.cuda.current_stream().cuda_stream
 
 
 def ours_single_cabi():
-    lib.sdfr_forward(grid.data_ptr(), R, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1, W, H,
+    lib.sdfr_forward(grid.data_ptr(), R, 0, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1, W, H,
                      320.0, 240.0, 320.0, 320.0, THR, depth1.data_ptr(), st)
-    lib.sdfr_backward(g.data_ptr(), depth1.data_ptr(), grid.data_ptr(), R, 0, p.data_ptr(),
+    lib.sdfr_backward(g.data_ptr(), depth1.data_ptr(), grid.data_ptr(), R, 0, 0, p.data_ptr(),
                       q.data_ptr(), s.data_ptr(), 1, W, H, 320.0, 240.0, 320.0, 320.0,
                       gs.data_ptr(), 0, gp.data_ptr(), gq.data_ptr(), gi.data_ptr(),
                       _lib.GRAD_ALL | _lib.ZERO_GRADS, st)
@@ -92,35 +92,69 @@ pos, quat, inv_s = hyp["position"], hyp["orientation"], hyp["inv_scale"]
 depth = torch.empty(B, H, W, device=dev)
 sums = torch.zeros(2, B, device=dev)
 obs = torch.empty(H, W, device=dev)
-lib.sdfr_forward(grids.data_ptr(), R, 0, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), 1, W, H,
+lib.sdfr_forward(grids.data_ptr(), R, 0, 0, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), 1, W, H,
                  320.0, 240.0, 320.0, 320.0, THR, obs.data_ptr(), st)
 g_sdf = torch.empty_like(grids)
 g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
 RRR = R ** 3
 
 
-def fwd():
-    lib.sdfr_compare_forward(grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(),
+import ctypes
+
+n_sk = ctypes.c_longlong(0)
+lib.sdfr_skewed_pitches(R, None, None, ctypes.byref(n_sk))
+SK = int(n_sk.value)
+skewed = torch.empty(B, SK, device=dev)
+lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, st)
+
+
+def src(layout):
+    return (skewed.data_ptr(), SK, 1) if layout else (grids.data_ptr(), RRR, 0)
+
+
+def fwd(layout=1):
+    ptr, stride, lt = src(layout)
+    lib.sdfr_compare_forward(ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                              inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
                              obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
                              sums[1].data_ptr(), _lib.ZERO_GRADS, st)
 
 
-def bwd(flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
+def fused(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
+    ptr, stride, lt = src(layout)
+    lib.sdfr_compare_fused(ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
+                           inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
+                           obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
+                           sums[1].data_ptr(), g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
+                           g_quat.data_ptr(), g_is.data_ptr(), flags, st)
+
+
+def bwd(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
+    ptr, stride, lt = src(layout)
     lib.sdfr_compare_backward(depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None,
-                              grids.data_ptr(), R, RRR, pos.data_ptr(), quat.data_ptr(),
+                              ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                               inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0,
                               g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
                               g_is.data_ptr(), flags, st)
 
 
+fwd()
+out["c2_layouts"] = {
+    "skew_pass": timed(lambda: lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, st)),
+    "fwd_dense": timed(lambda: fwd(0)), "fwd_skewed": timed(lambda: fwd(1)),
+    "fused_dense": timed(lambda: fused(0)), "fused_skewed": timed(lambda: fused(1)),
+    "fused_skewed_pose_only": timed(lambda: fused(1, 0x0E | _lib.ZERO_GRADS)),
+    "fused_skewed_sdf_only": timed(lambda: fused(1, 0x01 | _lib.ZERO_GRADS)),
+    "bwd_dense": timed(lambda: bwd(0)), "bwd_skewed": timed(lambda: bwd(1)),
+    "bwd_skewed_pose_only": timed(lambda: bwd(1, 0x0E | _lib.ZERO_GRADS)),
+    "bwd_skewed_sdf_only": timed(lambda: bwd(1, 0x01 | _lib.ZERO_GRADS)),
+    "bwd_skewed_no_memset": timed(lambda: bwd(1, _lib.GRAD_ALL)),
+}
 sweep = {}
-for target in (592, 1184, 2368, 4736, 9472, 18944, 76800):
+for target in (1184, 2368, 4736, 9472):
     os.environ["SDFR_TARGET_CTAS"] = str(target)
     fwd()
-    sweep[target] = {"fwd": timed(fwd), "bwd": timed(bwd),
-                     "bwd_pose_only": timed(lambda: bwd(0x0E | _lib.ZERO_GRADS)),
-                     "bwd_no_memset": timed(lambda: bwd(_lib.GRAD_ALL))}
+    sweep[target] = {"fwd": timed(fwd), "fused": timed(fused), "bwd": timed(bwd)}
 os.environ.pop("SDFR_TARGET_CTAS")
 out["c2_cta_sweep"] = sweep
 tag = sys.argv[1] if len(sys.argv) > 1 else "micro"

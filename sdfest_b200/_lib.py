@@ -9,9 +9,11 @@ import ctypes
 import os
 from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
+# SDFR_LIB_PATH: tuning experiments load an alternative build of the SAME library (scripts/)
+LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -20,6 +22,8 @@ GRAD_INV_SCALE = 0x08
 GRAD_ALL = 0x0F
 SDF_GRAD_EXACT = 0x10
 ZERO_GRADS = 0x20
+LAYOUT_DENSE = 0
+LAYOUT_SKEWED = 1
 
 _P = c_void_p
 _CAM = [c_int, c_int, c_float, c_float, c_float, c_float]  # W, H, cx, cy, fx, fy
@@ -31,25 +35,27 @@ SIGNATURES = {
     "sdfr_last_error": (ctypes.c_char_p, []),
     "sdfr_build_info": (ctypes.c_char_p, []),
     "sdfr_max_steps": (c_int, []),
-    "sdfr_forward": (c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P]),
+    "sdfr_forward": (c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P]),
     "sdfr_forward_stats": (
-        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
     "sdfr_backward": (
-        c_int, [_P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
+        c_int, [_P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
     "sdfr_compare_forward": (
-        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
                 c_uint, _P]),
     "sdfr_compare_backward": (
-        c_int, [_P, _P, c_longlong, _P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS,
+        c_int, [_P, _P, c_longlong, _P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS,
                 c_uint, _P]),
     "sdfr_compare_fused": (
-        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
                 *_GRADS, c_uint, _P]),
+    "sdfr_skewed_pitches": (c_int, [c_int, _P, _P, _P]),
+    "sdfr_skew_grids": (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P]),
     "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P]),
     "sdfr_forward_composite": (
-        c_int, [_P, c_int, c_longlong, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
     "sdfr_backward_composite": (
-        c_int, [_P, _P, _P, _P, c_int, c_longlong, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
+        c_int, [_P, _P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
 }
 
 _lib = None

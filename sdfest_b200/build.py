@@ -47,7 +47,8 @@ def up_to_date() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB_PATH
-    cmd = [find_nvcc(), *NVCC_FLAGS, *SOURCES, "-o", LIB_PATH]
+    extra = os.environ.get("SDFR_NVCC_EXTRA", "").split()  # tuning experiments (-DSDFR_FWD_BLOCKS=4)
+    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, *SOURCES, "-o", LIB_PATH]
     if verbose:
         cmd[1:1] = ["-Xptxas", "-v"]
         print(" ".join(cmd))

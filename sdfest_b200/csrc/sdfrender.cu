@@ -118,8 +118,9 @@ struct BwdParams {
   int n_objects;
 };
 
-/* Built by warp 0: pose part by every lane (registers), the 8 box corners by lanes 0-7. */
-__device__ __forceinline__ void build_frame(Frame& smemF, const Pose& pose, int b,
+/* Built by warp 0: pose part by every lane (registers), the 8 box corners by lanes 0-7, the 28
+ * corner pairs that may carry a silhouette edge by lanes 0-27 (edges == nullptr: no hull). */
+__device__ __forceinline__ void build_frame(Frame& smemF, HullEdge* edges, const Pose& pose, int b,
                                             const Camera& cam, int lane) {
   Frame F;
   frame_pose(F, pose.position + 3 * b, pose.orientation + 4 * b, pose.inv_scale + b);
@@ -137,6 +138,35 @@ __device__ __forceinline__ void build_frame(Frame& smemF, const Pose& pose, int 
   if (lane == 0) {
     frame_rect(F, cam, all_ok, cmin, cmax, rmin, rmax);
     smemF = F;
+  }
+  if (edges != nullptr) { /* same selection as build_hull_serial: first 8 accepted pairs */
+    const bool sane =
+        all_ok && __all_sync(kFull, fabsf(col) <= kHullCoordMax && fabsf(row) <= kHullCoordMax);
+    int i = 0, j = 1;
+    if (lane < 28) hull_pair(lane, i, j);
+    const float xi = __shfl_sync(kFull, col, i), yi = __shfl_sync(kFull, row, i);
+    const float xj = __shfl_sync(kFull, col, j), yj = __shfl_sync(kFull, row, j);
+    float a = 0.f, bb = 0.f, c = 0.f;
+    const bool line = sane && lane < 28 && hull_line(xi, yi, xj, yj, a, bb, c);
+    float smin = 1e30f, smax = -1e30f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float sd = a * __shfl_sync(kFull, col, k) + bb * __shfl_sync(kFull, row, k) + c;
+      smin = fminf(smin, sd);
+      smax = fmaxf(smax, sd);
+    }
+    HullEdge e;
+    e.a = 0.f; e.b = 0.f; e.c = 1.f; e.pad = 0.f;
+    const bool valid = line && hull_accept(a, bb, c, smin, smax, e);
+    const unsigned m = __ballot_sync(kFull, valid);
+    const int slot = __popc(m & ((1u << lane) - 1u));
+    if (valid && slot < kMaxHullEdges) edges[slot] = e;
+    const int n = min(__popc(m), kMaxHullEdges);
+    if (lane < kMaxHullEdges && lane >= n) { /* always-true padding */
+      HullEdge t;
+      t.a = 0.f; t.b = 0.f; t.c = 1.f; t.pad = 0.f;
+      edges[lane] = t;
+    }
   }
 }
 
@@ -205,11 +235,11 @@ __device__ __forceinline__ Tiling make_tiling(const Frame& F, const Camera& cam)
 /* CTA prologue: Frame by warp 0, then the ray tables (double-precision divisions as in
  * cu:146-147, amortised over all tiles of the CTA).  When the CTA owns at most one tile of the
  * box (small batches: G >= number of box tiles) only that tile's 32 + 8 entries are built. */
-__device__ __forceinline__ Tiling cta_prologue(Frame& Fs, float* tables, bool use_tables,
-                                               const Pose& pose, int b, const Camera& cam,
-                                               float*& colx, float*& rowy) {
+__device__ __forceinline__ Tiling cta_prologue(Frame& Fs, HullEdge* edges, float* tables,
+                                               bool use_tables, const Pose& pose, int b,
+                                               const Camera& cam, float*& colx, float*& rowy) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0) build_frame(Fs, pose, b, cam, lane);
+  if (warp == 0) build_frame(Fs, edges, pose, b, cam, lane);
   __syncthreads();
   Tiling T = make_tiling(Fs, cam);
   colx = tables;
@@ -288,63 +318,95 @@ __device__ __forceinline__ void reduce_pose(float (&acc)[8], float (*red)[8], in
  * factor upstream/n_overlap is only known once all pixels are done and is applied afterwards by
  * sdfr_scale_grads -- every gradient is linear in it).
  * ---------------------------------------------------------------------------------------- */
-template <int RT, int MODE, bool STATS, bool WANT_SDF, bool WANT_POSE>
-__global__ void __launch_bounds__(kThreads, 5)
+#ifndef SDFR_FWD_BLOCKS
+#define SDFR_FWD_BLOCKS 5 /* resident CTAs per SM the forward kernels are register-budgeted for */
+#endif
+template <int RT, int LT, int MODE, bool STATS, bool WANT_SDF, bool WANT_POSE>
+__global__ void __launch_bounds__(kThreads, SDFR_FWD_BLOCKS)
 sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
+  __shared__ HullEdge edges[kMaxHullEdges];
   __shared__ float red[kWarps][8];
+  __shared__ int next_q;
 
   const int b = blockIdx.y + P.z_offset;
   const int g = blockIdx.x, G = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int lx = ((warp & 3) << 3) + (lane & 7);
-  const int ly = ((warp >> 2) << 2) + (lane >> 3);
+  const int lane_x = lane & 7, lane_y = lane >> 3;
   const int W = P.cam.W, H = P.cam.H;
+  if (threadIdx.x == 0) next_q = kWarps;
   float *colx, *rowy;
-  const Tiling T = cta_prologue(Fs, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
+  const Tiling T = cta_prologue(Fs, edges, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
   const Frame& F = Fs; /* read-only from here on; the march hoists what it needs */
   float* __restrict__ out = P.depth + (size_t)b * H * W;
   const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
   const float* __restrict__ obs_img = MODE >= 1 ? P.depth_obs + (size_t)b * P.obs_stride : nullptr;
+  /* keep the per-hypothesis bases in registers: ptxas otherwise re-derives b*stride inside the
+   * march loop to save two registers (profiles/r01a: 8 of 68 loop instructions) */
+  asm volatile("" : "+l"(out));
+  asm volatile("" : "+l"(grid));
 
-  /* pass 1: tiles that cannot see the box are zero (cu:294-296 writes 0 for these rays) */
+  /* pass 1: tiles that cannot see the box are zero (cu:294-296 writes 0 for these rays); one
+   * whole 32x8 tile per warp, two 16-byte stores per lane */
   {
     const int n_tiles = T.tiles_x * T.tiles_y;
-    TileWalk w(g, G, T.tiles_x);
-    for (int t = g; t < n_tiles; t += G, w.next()) {
-      if (w.tx >= T.rtx0 && w.tx < T.rtx0 + T.rtw && w.ty >= T.rty0 && w.ty < T.rty0 + T.rth)
-        continue;
-      const int px = w.tx * kTileW + lx, py = w.ty * kTileH + ly;
-      if (px < W && py < H) out[(size_t)py * W + px] = 0.0f;
+    const bool vec = ((W & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    for (int t = g + warp * G; t < n_tiles; t += kWarps * G) {
+      const int ty = t / T.tiles_x, tx = t - ty * T.tiles_x;
+      if (tx >= T.rtx0 && tx < T.rtx0 + T.rtw && ty >= T.rty0 && ty < T.rty0 + T.rth) continue;
+      const int x0 = tx * kTileW, y0 = ty * kTileH;
+      if (vec && x0 + kTileW <= W && y0 + kTileH <= H) {
+        float4* p = reinterpret_cast<float4*>(out + (size_t)(y0 + lane_y) * W + x0) + lane_x;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        p[0] = z4;
+        p[W] = z4; /* 4 rows further down: 4*W floats = W float4 */
+      } else {
+        for (int i = lane; i < kThreads; i += 32) {
+          const int px = x0 + (i & (kTileW - 1)), py = y0 + (i / kTileW);
+          if (px < W && py < H) out[(size_t)py * W + px] = 0.0f;
+        }
+      }
     }
   }
 
-  /* pass 2: tiles inside the box's rectangle are traced */
-  float acc[8]; /* MODE 1: [0] = sum |err|, [1] = count.  MODE 2: pose gradients + the two */
+  /* pass 2: tiles inside the box's rectangle.  The CTA owns rectangle tiles g, g+G, ...; their
+   * 8x4-pixel warp tiles are handed to the warps dynamically (shared counter), so a warp whose
+   * rays finish early -- or whose warp tile lies outside the box silhouette -- takes the next. */
+  float acc[8]; /* MODE 2: pose gradients */
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
   float err_acc = 0.0f, cnt_acc = 0.0f;
   unsigned st_steps = 0, st_entered = 0, st_hit = 0, st_capped = 0;
   const int n_rect = T.rtw * T.rth;
-  TileWalk w(g, G, T.rtw);
-  for (int r = g; r < n_rect; r += G, w.next()) {
-    const int tx = T.rtx0 + w.tx, ty = T.rty0 + w.ty;
-    const int px = tx * kTileW + lx, py = ty * kTileH + ly;
-    if (px >= W || py >= H) continue;
+  const int n_q = n_rect > g ? ((n_rect - g + G - 1) / G) * kWarps : 0;
+  const HullEdge edge = edges[lane & (kMaxHullEdges - 1)];
+  /* rectangle tile number -> (row, column) without an integer division: exact for < 2^22 tiles
+   * (check_common bounds the image accordingly) */
+  const float inv_rtw = 1.0f / (float)(T.rtw > 0 ? T.rtw : 1);
+  /* compile-time grid constants (immediates) for the common resolutions */
+  const Grid Gc = RT > 0 ? make_grid(RT, LT) : P.grid;
+  for (int q = warp; q < n_q;) {
+    const int r = g + (q >> 3) * G, sub = q & 7;
+    const int wty = (int)(((float)r + 0.5f) * inv_rtw);
+    const int tx = T.rtx0 + (r - wty * T.rtw), ty = T.rty0 + wty;
+    const int wx0 = tx * kTileW + ((sub & 3) << 3), wy0 = ty * kTileH + ((sub >> 2) << 2);
+    const int px = wx0 + lane_x, py = wy0 + lane_y;
+    const bool inimg = px < W && py < H;
+    /* silhouette test for the whole warp tile: lane e evaluates hull edge e */
+    const bool culled =
+        __any_sync(kFull, hull_block_outside(edge, (float)wx0, (float)wy0, 8.0f, 4.0f));
     float z = 0.0f;
     Ray ray;
-    if (px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
-      const float ux = P.use_tables ? colx[(tx - T.tab_x0) * kTileW + lx]
-                                    : pixel_dx(px, P.cam.cx, P.cam.fx);
-      const float uy = P.use_tables ? rowy[(ty - T.tab_y0) * kTileH + ly]
-                                    : pixel_dy(py, P.cam.cy, P.cam.fy);
+    if (!culled && inimg && px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
+      const float ux = P.use_tables ? colx[px - T.tab_x0 * kTileW] : pixel_dx(px, P.cam.cx, P.cam.fx);
+      const float uy = P.use_tables ? rowy[py - T.tab_y0 * kTileH] : pixel_dy(py, P.cam.cy, P.cam.fy);
       ray = make_ray(F, ux, uy);
       float t_min, t_max;
       if (ray_box(F, ray, t_min, t_max)) {
         int steps;
         bool capped;
-        z = march<RT>(grid, P.grid, F, ray, t_min, t_max, P.threshold, steps, capped);
+        z = march<RT, LT>(grid, Gc, F, ray, t_min, t_max, P.threshold, steps, capped);
         if (STATS) {
           st_steps += steps;
           st_entered += 1;
@@ -353,28 +415,32 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
         }
       }
     }
-    const size_t pix = (size_t)py * W + px;
-    out[pix] = z;
-    if (MODE >= 1 && z > 0.0f) {
-      /* masked L1 against the observation (estimation/simple_setup.py:125-131) */
-      const float obs = __ldg(obs_img + pix);
-      if (obs > 0.0f) {
-        err_acc += fabsf(z - obs);
-        cnt_acc += 1.0f;
-        if (MODE == 2 && z != obs) {
-          const float sgn = z > obs ? 1.0f : -1.0f;
-          PixelGrad pg;
-          pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, z, sgn,
-                                                  (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
-          if (WANT_SDF)
-            scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, P.grid, pg);
-          if (WANT_POSE) {
+    if (inimg) {
+      const unsigned pix = (unsigned)py * (unsigned)W + (unsigned)px;
+      out[pix] = z;
+      if (MODE >= 1 && z > 0.0f) {
+        /* masked L1 against the observation (estimation/simple_setup.py:125-131) */
+        const float obs = __ldg(obs_img + pix);
+        if (obs > 0.0f) {
+          err_acc += fabsf(z - obs);
+          cnt_acc += 1.0f;
+          if (MODE == 2 && z != obs) {
+            const float sgn = z > obs ? 1.0f : -1.0f;
+            PixelGrad pg;
+            pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, z, sgn,
+                                                        (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+            if (WANT_SDF)
+              scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg);
+            if (WANT_POSE) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
+              for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
+            }
           }
         }
       }
     }
+    if (lane == 0) q = atomicAdd(&next_q, 1);
+    q = __shfl_sync(kFull, q, 0);
   }
 
   if (STATS) {
@@ -405,7 +471,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
  * Only tiles inside the projected box are visited: `depth` must be the image the forward
  * produced for the same pose (it is zero everywhere else).
  * ---------------------------------------------------------------------------------------- */
-template <int RT, int MODE, bool WANT_SDF, bool WANT_POSE>
+template <int RT, int LT, int MODE, bool WANT_SDF, bool WANT_POSE>
 __global__ void __launch_bounds__(kThreads, 4)
 sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ float tables[];
@@ -428,7 +494,7 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   }
 
   float *colx, *rowy;
-  const Tiling T = cta_prologue(Fs, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
+  const Tiling T = cta_prologue(Fs, nullptr, tables, P.use_tables, P.pose, b, P.cam, colx, rowy);
   const Frame& F = Fs;
   const float* __restrict__ depth = P.depth + (size_t)b * H * W;
   const float* __restrict__ upimg =
@@ -484,7 +550,7 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
                                   : pixel_dy(cpy, P.cam.cy, P.cam.fy);
     const Ray ray = make_ray(F, ux, uy);
     PixelGrad pg;
-    pixel_backward<RT, WANT_SDF, WANT_POSE>(grid, P.grid, F, ray, zc, gup, exact, pg);
+    pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, P.grid, F, ray, zc, gup, exact, pg);
     if (WANT_SDF) scatter_sdf<RT>(gsdf, P.grid, pg);
     if (WANT_POSE) {
 #pragma unroll
@@ -570,7 +636,7 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
   for (int k0 = 0; k0 < n_objects; k0 += kMaxObjPerPass) {
     const int nk = min(kMaxObjPerPass, n_objects - k0);
     __syncthreads(); /* previous pass done with Fs; also publishes the tables */
-    for (int k = warp; k < nk; k += kWarps) build_frame(Fs[k], P.pose, k0 + k, P.cam, lane);
+    for (int k = warp; k < nk; k += kWarps) build_frame(Fs[k], nullptr, P.pose, k0 + k, P.cam, lane);
     __syncthreads();
     if (!inside) continue;
     for (int k = 0; k < nk; ++k) {
@@ -683,15 +749,48 @@ sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
   }
 }
 
+/* Dense [R][R][R] -> skewed pitched copy (sdfr_core.cuh: kLayoutSkewed).  One warp per (x,y)
+ * row: coalesced reads, coalesced (unaligned) writes; the padding is never read. */
+__global__ void __launch_bounds__(256)
+sdfr_skew_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst,
+                 long long dst_stride, int R, int py, int px) {
+  const int b = blockIdx.y;
+  const float* __restrict__ s = src + (size_t)b * src_stride;
+  float* __restrict__ d = dst + (size_t)b * dst_stride;
+  if ((R & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+    /* one thread per 4 consecutive z: a 16-byte read, four 4-byte writes (rows of the skewed
+     * array start at odd element offsets) */
+    const int q4 = R >> 2, n4 = R * R * q4;
+    const float4* __restrict__ s4 = reinterpret_cast<const float4*>(s);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+      const int row = i / q4, z = (i - row * q4) << 2;
+      const int ix = row / R, iy = row - ix * R;
+      const float4 v = __ldg(s4 + i);
+      float* __restrict__ o = d + (size_t)ix * px + iy * py + z;
+      o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+    }
+    return;
+  }
+  const int n = R * R * R;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = i / R, z = i - row * R;
+    const int ix = row / R, iy = row - ix * R;
+    d[(size_t)ix * px + iy * py + z] = __ldg(s + i);
+  }
+}
+
 /* ------------------------------------------------------------------------------------------
  * Host side
  * ---------------------------------------------------------------------------------------- */
-int check_common(const float* sdf, int R, long long sdf_stride, const float* pos,
+int check_common(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                  const float* quat, const float* inv_scale, int batch, int W, int H) {
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED)
+    return fail(SDFR_E_FLAGS, "unknown sdf_layout");
   if (batch < 0 || W < 0 || H < 0) return fail(SDFR_E_SHAPE, "negative batch/width/height");
   if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
   if (sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative sdf_stride");
-  if (W > (1 << 20) || H > (1 << 19)) return fail(SDFR_E_SHAPE, "image too large");
+  if (W > (1 << 20) || H > (1 << 19) || (long long)W * H >= (1ll << 30))
+    return fail(SDFR_E_SHAPE, "image too large (width*height must be < 2^30)");
   if (batch == 0 || W == 0 || H == 0) return 0;
   if (!sdf || !pos || !quat || !inv_scale) return fail(SDFR_E_NULL, "NULL input pointer");
   return 0;
@@ -747,52 +846,63 @@ size_t table_bytes(int W, int H) {
   return n * sizeof(float) <= 40 * 1024 ? n * sizeof(float) : 0;
 }
 
-template <int RT, int MODE, bool STATS>
+template <int RT, int LT, int MODE, bool STATS>
 void launch_forward_rt(FwdParams& P, dim3 grid, size_t smem, cudaStream_t s) {
   if (MODE != 2) {
-    sdfr_forward_kernel<RT, MODE, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
+    sdfr_forward_kernel<RT, LT, MODE, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
     return;
   }
   const bool want_sdf = (P.flags & SDFR_GRAD_SDF) != 0;
   const bool want_pose =
       (P.flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
   if (want_sdf && want_pose)
-    sdfr_forward_kernel<RT, MODE, STATS, true, true><<<grid, kThreads, smem, s>>>(P);
+    sdfr_forward_kernel<RT, LT, MODE, STATS, true, true><<<grid, kThreads, smem, s>>>(P);
   else if (want_sdf)
-    sdfr_forward_kernel<RT, MODE, STATS, true, false><<<grid, kThreads, smem, s>>>(P);
+    sdfr_forward_kernel<RT, LT, MODE, STATS, true, false><<<grid, kThreads, smem, s>>>(P);
   else if (want_pose)
-    sdfr_forward_kernel<RT, MODE, STATS, false, true><<<grid, kThreads, smem, s>>>(P);
+    sdfr_forward_kernel<RT, LT, MODE, STATS, false, true><<<grid, kThreads, smem, s>>>(P);
   else
-    sdfr_forward_kernel<RT, 1, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
+    sdfr_forward_kernel<RT, LT, 1, STATS, false, false><<<grid, kThreads, smem, s>>>(P);
 }
+
+/* common resolutions get compile-time pitches (immediate-offset gathers) in both layouts; every
+ * other resolution runs the generic kernel with the run-time pitches of P.grid */
+#define SDFR_DISPATCH_RT_LT(R, skewed, CALL)                                       \
+  do {                                                                             \
+    if ((R) == 64 && !(skewed)) { CALL(64, kLayoutDense); }                        \
+    else if ((R) == 64) { CALL(64, kLayoutSkewed); }                               \
+    else if ((R) == 128 && !(skewed)) { CALL(128, kLayoutDense); }                 \
+    else if ((R) == 128) { CALL(128, kLayoutSkewed); }                             \
+    else if ((R) == 32 && !(skewed)) { CALL(32, kLayoutDense); }                   \
+    else if ((R) == 32) { CALL(32, kLayoutSkewed); }                               \
+    else { CALL(0, kLayoutDense); }                                                \
+  } while (0)
 
 template <int MODE, bool STATS>
 int launch_forward(FwdParams P, int batch, cudaStream_t s) {
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
   const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
+  const bool skewed = P.grid.py != P.grid.R;
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
-    switch (P.grid.R) { /* common resolutions get immediate-offset gathers */
-      case 64: launch_forward_rt<64, MODE, STATS>(P, grid, smem, s); break;
-      case 128: launch_forward_rt<128, MODE, STATS>(P, grid, smem, s); break;
-      case 32: launch_forward_rt<32, MODE, STATS>(P, grid, smem, s); break;
-      default: launch_forward_rt<0, MODE, STATS>(P, grid, smem, s); break;
-    }
+#define SDFR_CALL(RT, LT) launch_forward_rt<RT, LT, MODE, STATS>(P, grid, smem, s)
+    SDFR_DISPATCH_RT_LT(P.grid.R, skewed, SDFR_CALL);
+#undef SDFR_CALL
   }
   return check_launch("sdfr_forward_kernel");
 }
 
-template <int RT, int MODE>
+template <int RT, int LT, int MODE>
 void launch_backward_rt(BwdParams& P, dim3 grid, size_t smem, bool want_sdf, bool want_pose,
                         cudaStream_t s) {
   if (want_sdf && want_pose)
-    sdfr_backward_kernel<RT, MODE, true, true><<<grid, kThreads, smem, s>>>(P);
+    sdfr_backward_kernel<RT, LT, MODE, true, true><<<grid, kThreads, smem, s>>>(P);
   else if (want_sdf)
-    sdfr_backward_kernel<RT, MODE, true, false><<<grid, kThreads, smem, s>>>(P);
+    sdfr_backward_kernel<RT, LT, MODE, true, false><<<grid, kThreads, smem, s>>>(P);
   else
-    sdfr_backward_kernel<RT, MODE, false, true><<<grid, kThreads, smem, s>>>(P);
+    sdfr_backward_kernel<RT, LT, MODE, false, true><<<grid, kThreads, smem, s>>>(P);
 }
 
 template <int MODE>
@@ -804,15 +914,13 @@ int launch_backward(BwdParams P, int batch, cudaStream_t s) {
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
   const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
+  const bool skewed = P.grid.py != P.grid.R;
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
-    switch (P.grid.R) {
-      case 64: launch_backward_rt<64, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
-      case 128: launch_backward_rt<128, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
-      case 32: launch_backward_rt<32, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
-      default: launch_backward_rt<0, MODE>(P, grid, smem, want_sdf, want_pose, s); break;
-    }
+#define SDFR_CALL(RT, LT) launch_backward_rt<RT, LT, MODE>(P, grid, smem, want_sdf, want_pose, s)
+    SDFR_DISPATCH_RT_LT(P.grid.R, skewed, SDFR_CALL);
+#undef SDFR_CALL
   }
   return check_launch("sdfr_backward_kernel");
 }
@@ -854,7 +962,7 @@ int zero_grads(unsigned flags, int R, int batch, float* gs, long long gs_stride,
   return rc;
 }
 
-FwdParams fwd_params(const float* sdf, int R, long long sdf_stride, const float* pos,
+FwdParams fwd_params(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                      const float* quat, const float* inv_scale, int W, int H, float cx, float cy,
                      float fx, float fy, float threshold, float* depth) {
   FwdParams P;
@@ -862,14 +970,14 @@ FwdParams fwd_params(const float* sdf, int R, long long sdf_stride, const float*
   P.sdf = sdf;
   P.sdf_stride = sdf_stride;
   P.pose = Pose{pos, quat, inv_scale};
-  P.grid = make_grid(R);
+  P.grid = make_grid(R, layout);
   P.cam = Camera{W, H, cx, cy, fx, fy};
   P.threshold = threshold;
   P.depth = depth;
   return P;
 }
 
-BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_stride,
+BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_stride, int layout,
                      const float* pos, const float* quat, const float* inv_scale, int W, int H,
                      float cx, float cy, float fx, float fy, float* gs, long long gs_stride,
                      float* gp, float* gq, float* gi, unsigned flags) {
@@ -879,7 +987,7 @@ BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_
   P.sdf = sdf;
   P.sdf_stride = sdf_stride;
   P.pose = Pose{pos, quat, inv_scale};
-  P.grid = make_grid(R);
+  P.grid = make_grid(R, layout);
   P.cam = Camera{W, H, cx, cy, fx, fy};
   P.grad_sdf = gs;
   P.grad_sdf_stride = gs_stride;
@@ -901,54 +1009,54 @@ const char* sdfr_build_info(void) {
 }
 int sdfr_max_steps(void) { return sdfr::kMaxSteps; }
 
-int sdfr_forward(const float* sdf, int R, long long sdf_stride, const float* pos,
+int sdfr_forward(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                  const float* quat, const float* inv_scale, int batch, int W, int H, float cx,
                  float cy, float fx, float fy, float threshold, float* depth, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (batch == 0 || W == 0 || H == 0) return 0;
   if (!depth) return fail(SDFR_E_NULL, "depth is NULL");
-  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   return launch_forward<0, false>(P, batch, (cudaStream_t)stream);
 }
 
-int sdfr_forward_stats(const float* sdf, int R, long long sdf_stride, const float* pos,
+int sdfr_forward_stats(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                        const float* quat, const float* inv_scale, int batch, int W, int H,
                        float cx, float cy, float fx, float fy, float threshold, float* depth,
                        unsigned long long* stats, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (batch == 0 || W == 0 || H == 0) return 0;
   if (!depth || !stats) return fail(SDFR_E_NULL, "depth or stats is NULL");
-  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   P.stats = stats;
   return launch_forward<0, true>(P, batch, (cudaStream_t)stream);
 }
 
 int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int R,
-                  long long sdf_stride, const float* pos, const float* quat,
+                  long long sdf_stride, int layout, const float* pos, const float* quat,
                   const float* inv_scale, int batch, int W, int H, float cx, float cy, float fx,
                   float fy, float* gs, long long gs_stride, float* gp, float* gq, float* gi,
                   unsigned flags, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (batch == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
   if (W == 0 || H == 0) return 0;
   if (!grad_depth || !depth) return fail(SDFR_E_NULL, "grad_depth or depth is NULL");
-  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            gs, gs_stride, gp, gq, gi, flags);
   P.grad_depth = grad_depth;
   return launch_backward<0>(P, batch, s);
 }
 
-int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, const float* pos,
+int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                          const float* quat, const float* inv_scale, int batch, int W, int H,
                          float cx, float cy, float fx, float fy, float threshold,
                          const float* depth_obs, long long obs_stride, float* depth,
                          float* loss_sum, float* n_overlap, unsigned flags, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (flags & ~SDFR_ZERO_GRADS) return fail(SDFR_E_FLAGS, "unknown flag bits");
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if (batch == 0) return 0;
@@ -960,7 +1068,7 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, const fl
   }
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
-  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
@@ -971,11 +1079,11 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, const fl
 
 int sdfr_compare_backward(const float* depth, const float* depth_obs, long long obs_stride,
                           const float* n_overlap, const float* upstream, const float* sdf, int R,
-                          long long sdf_stride, const float* pos, const float* quat,
+                          long long sdf_stride, int layout, const float* pos, const float* quat,
                           const float* inv_scale, int batch, int W, int H, float cx, float cy,
                           float fx, float fy, float* gs, long long gs_stride, float* gp,
                           float* gq, float* gi, unsigned flags, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if (batch == 0) return 0;
@@ -984,7 +1092,7 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs || !n_overlap)
     return fail(SDFR_E_NULL, "depth, depth_obs or n_overlap is NULL");
-  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            gs, gs_stride, gp, gq, gi, flags);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
@@ -993,13 +1101,13 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   return launch_backward<1>(P, batch, s);
 }
 
-int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, const float* pos,
+int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                        const float* quat, const float* inv_scale, int batch, int W, int H,
                        float cx, float cy, float fx, float fy, float threshold,
                        const float* depth_obs, long long obs_stride, float* depth,
                        float* loss_sum, float* n_overlap, float* gs, long long gs_stride,
                        float* gp, float* gq, float* gi, unsigned flags, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if ((flags & SDFR_GRAD_SDF) && gs_stride == 0 && batch > 1)
@@ -1016,7 +1124,7 @@ int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, const floa
   if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
-  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
@@ -1053,14 +1161,14 @@ int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int b
   return check_launch("sdfr_scale_grads_kernel");
 }
 
-int sdfr_forward_composite(const float* sdf, int R, long long sdf_stride, const float* pos,
+int sdfr_forward_composite(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                            const float* quat, const float* inv_scale, int n_objects, int W,
                            int H, float cx, float cy, float fx, float fy, float threshold,
                            float* depth, int* winner, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, n_objects, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, n_objects, W, H)) return rc;
   if (W == 0 || H == 0) return 0;
   if (!depth || !winner) return fail(SDFR_E_NULL, "depth or winner is NULL");
-  FwdParams P = fwd_params(sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            threshold, depth);
   sdfr_forward_composite_kernel<<<tile_grid(W, H, 1), kThreads, 0, (cudaStream_t)stream>>>(
       P, n_objects, winner);
@@ -1068,12 +1176,12 @@ int sdfr_forward_composite(const float* sdf, int R, long long sdf_stride, const 
 }
 
 int sdfr_backward_composite(const float* grad_depth, const float* depth, const int* winner,
-                            const float* sdf, int R, long long sdf_stride, const float* pos,
+                            const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                             const float* quat, const float* inv_scale, int n_objects, int W,
                             int H, float cx, float cy, float fx, float fy, float* gs,
                             long long gs_stride, float* gp, float* gq, float* gi, unsigned flags,
                             void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, pos, quat, inv_scale, n_objects, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, n_objects, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (n_objects == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1081,7 +1189,7 @@ int sdfr_backward_composite(const float* grad_depth, const float* depth, const i
   if (W == 0 || H == 0) return 0;
   if (!grad_depth || !depth || !winner)
     return fail(SDFR_E_NULL, "grad_depth, depth or winner is NULL");
-  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
+  BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            gs, gs_stride, gp, gq, gi, flags);
   P.grad_depth = grad_depth;
   P.winner = winner;
@@ -1098,6 +1206,35 @@ int sdfr_backward_composite(const float* grad_depth, const float* depth, const i
   else
     sdfr_backward_composite_kernel<false, true><<<grid, kThreads, 0, s>>>(P);
   return check_launch("sdfr_backward_composite_kernel");
+}
+
+int sdfr_skewed_pitches(int R, int* pitch_y, int* pitch_x, long long* elems) {
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  const Grid G = make_grid(R, kLayoutSkewed);
+  if (pitch_y) *pitch_y = G.py;
+  if (pitch_x) *pitch_x = G.px;
+  if (elems) *elems = (long long)R * G.px;
+  return 0;
+}
+
+int sdfr_skew_grids(const float* sdf, int R, long long sdf_stride, int batch, float* skewed,
+                    long long skewed_stride, void* stream) {
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (batch < 0 || sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative batch or sdf_stride");
+  if (batch == 0) return 0;
+  if (!sdf || !skewed) return fail(SDFR_E_NULL, "NULL grid pointer");
+  const Grid G = make_grid(R, kLayoutSkewed);
+  if (skewed_stride < (long long)R * G.px)
+    return fail(SDFR_E_SHAPE, "skewed_stride smaller than sdfr_skewed_pitches' elems");
+  const long long work = ((long long)R * R * R + 3) / 4;
+  int gx = (int)((work + 255) / 256 < 1024 ? (work + 255) / 256 : 1024);
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    const int nz = batch - z0 < 65535 ? batch - z0 : 65535;
+    sdfr_skew_kernel<<<dim3(gx, nz), 256, 0, (cudaStream_t)stream>>>(
+        sdf + (size_t)z0 * sdf_stride, sdf_stride, skewed + (size_t)z0 * skewed_stride,
+        skewed_stride, R, G.py, G.px);
+  }
+  return check_launch("sdfr_skew_kernel");
 }
 
 }  // extern "C"

@@ -8,10 +8,12 @@ from .sdf_renderer import (  # noqa: F401
     SDFRendererFunctionGPU,
     forward_stats,
     get_sdf_grad_mode,
+    get_sdf_layout_policy,
     render_and_compare,
     render_depth,
     render_depth_batched,
     render_depth_composite,
     render_depth_gpu,
     set_sdf_grad_mode,
+    set_sdf_layout_policy,
 )

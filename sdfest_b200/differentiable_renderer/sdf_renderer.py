@@ -41,6 +41,57 @@ def get_sdf_grad_mode() -> str:
     return _default_sdf_grad_mode
 
 
+_SDF_LAYOUT_POLICIES = ("auto", "dense", "skewed")
+_sdf_layout_policy = "auto"
+
+
+def set_sdf_layout_policy(policy: str) -> None:
+    """How the kernels read the SDF grids.
+
+    ``"dense"``: straight from the caller's ``(R,R,R)`` tensor (the reference layout).
+    ``"skewed"``: from a pitched scratch copy made by one streaming pass (``sdfr_skew_grids``) in
+    which voxels a few cells apart fall into different L1 banks -- the 8-corner gathers of a warp
+    then cost ~2 L1 cycles instead of ~6; same fp32 values, identical
+    results.  ``"auto"`` (default): skewed when the rendering work outweighs the copy.
+    """
+    global _sdf_layout_policy
+    if policy not in _SDF_LAYOUT_POLICIES:
+        raise ValueError(f"sdf layout policy must be one of {_SDF_LAYOUT_POLICIES}")
+    _sdf_layout_policy = policy
+
+
+def get_sdf_layout_policy() -> str:
+    return _sdf_layout_policy
+
+
+_skew_geometry = {}
+
+
+def _skewed_elems(R: int) -> int:
+    if R not in _skew_geometry:
+        import ctypes
+
+        n = ctypes.c_longlong(0)
+        _lib.check(_lib.lib().sdfr_skewed_pitches(R, None, None, ctypes.byref(n)),
+                   "sdfr_skewed_pitches")
+        _skew_geometry[R] = int(n.value)
+    return _skew_geometry[R]
+
+
+def _grid_operand(sdf: torch.Tensor, R: int, stride: int, n_render: int, pixels: int):
+    """(tensor to read, its per-hypothesis stride, layout id) for a render of ``n_render`` images
+    of ``pixels`` pixels from ``sdf``; makes the skewed copy when the policy says so."""
+    n_grids = 1 if stride == 0 else n_render
+    policy = _sdf_layout_policy
+    if policy == "dense" or (policy == "auto" and n_render * pixels < n_grids * R ** 3):
+        return sdf, stride, _lib.LAYOUT_DENSE
+    elems = _skewed_elems(R)
+    skewed = torch.empty((n_grids, elems), dtype=torch.float32, device=sdf.device)
+    _lib.check(_lib.lib().sdfr_skew_grids(sdf.data_ptr(), R, stride, n_grids, skewed.data_ptr(),
+                                          elems, _stream()), "sdfr_skew_grids")
+    return skewed, (0 if stride == 0 else elems), _lib.LAYOUT_SKEWED
+
+
 class Camera:
     """Pinhole camera parameters (reference sdf_renderer.py:31-133).
 
@@ -154,8 +205,9 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
         W, H, cx, cy, fx, fy = _camera_params(camera)
         with torch.cuda.device_of(sdf):
             image = torch.empty((H, W), dtype=torch.float32, device=sdf.device)
+            src, _, layout = _grid_operand(sdf, R, 0, 1, W * H)
             _lib.check(_lib.lib().sdfr_forward(
-                sdf.data_ptr(), R, 0, position.data_ptr(), orientation.data_ptr(),
+                src.data_ptr(), R, 0, layout, position.data_ptr(), orientation.data_ptr(),
                 inv_scale.data_ptr(), 1, W, H, cx, cy, fx, fy, float(threshold),
                 image.data_ptr(), _stream()), "sdfr_forward")
         ctx.save_for_backward(image, sdf, position, orientation, inv_scale)
@@ -189,7 +241,8 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
             with torch.cuda.device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward(
                     grad_depth_image.data_ptr(), image.data_ptr(), sdf.data_ptr(),
-                    int(sdf.shape[-1]), 0, position.data_ptr(), orientation.data_ptr(),
+                    int(sdf.shape[-1]), 0, _lib.LAYOUT_DENSE, position.data_ptr(),
+                    orientation.data_ptr(),
                     inv_scale.data_ptr(), 1, W, H, cx, cy, fx, fy, _ptr(g_sdf), 0, _ptr(g_p),
                     _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None
@@ -264,10 +317,11 @@ class _BatchedRender(torch.autograd.Function):
         W, H, cx, cy, fx, fy = _camera_params(camera)
         with torch.cuda.device_of(sdf):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
+            src, src_stride, layout = _grid_operand(sdf, R, stride, B, W * H)
             _lib.check(_lib.lib().sdfr_forward(
-                sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
-                inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
-                depth.data_ptr(), _stream()), "sdfr_forward")
+                src.data_ptr(), R, src_stride, layout, position.data_ptr(),
+                orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
+                float(threshold), depth.data_ptr(), _stream()), "sdfr_forward")
         ctx.save_for_backward(depth, sdf, position, orientation, inv_scale)
         ctx.meta = (B, R, stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
         return depth
@@ -289,9 +343,9 @@ class _BatchedRender(torch.autograd.Function):
             with torch.cuda.device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward(
                     grad_depth.data_ptr(), depth.data_ptr(), sdf.data_ptr(), R, stride,
-                    position.data_ptr(), orientation.data_ptr(), inv_scale.data_ptr(), B, W, H,
-                    cx, cy, fx, fy, _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is), flags,
-                    _stream()), "sdfr_backward")
+                    _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
+                    inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, _ptr(g_sdf), stride,
+                    _ptr(g_p), _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None
 
 
@@ -334,20 +388,23 @@ class _RenderAndCompare(torch.autograd.Function):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
             sums = torch.empty((2, B), dtype=torch.float32, device=sdf.device)
             lib = _lib.lib()
+            src, src_stride, layout = _grid_operand(sdf, R, stride, B, W * H)
             if fused:
                 flags = _grad_flags(needs, sdf_grad_mode) | _lib.ZERO_GRADS
                 grads = [torch.empty_like(t) if n else None
                          for t, n in zip((sdf, position, orientation, inv_scale), needs)]
                 _lib.check(lib.sdfr_compare_fused(
-                    sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
-                    inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
+                    src.data_ptr(), R, src_stride, layout, position.data_ptr(),
+                    orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
+                    float(threshold),
                     depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
                     sums[1].data_ptr(), _ptr(grads[0]), stride, _ptr(grads[1]), _ptr(grads[2]),
                     _ptr(grads[3]), flags, _stream()), "sdfr_compare_fused")
             else:
                 _lib.check(lib.sdfr_compare_forward(
-                    sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
-                    inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold),
+                    src.data_ptr(), R, src_stride, layout, position.data_ptr(),
+                    orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
+                    float(threshold),
                     depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
                     sums[1].data_ptr(), _lib.ZERO_GRADS, _stream()), "sdfr_compare_forward")
             loss = sums[0] / sums[1]  # NaN where nothing overlaps, as torch.mean of an empty set
@@ -383,8 +440,9 @@ class _RenderAndCompare(torch.autograd.Function):
                 g_is = torch.empty_like(inv_scale) if needs[3] else None
                 _lib.check(lib.sdfr_compare_backward(
                     depth.data_ptr(), depth_obs.data_ptr(), obs_stride, sums[1].data_ptr(),
-                    upstream.data_ptr(), sdf.data_ptr(), R, stride, position.data_ptr(),
-                    orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
+                    upstream.data_ptr(), sdf.data_ptr(), R, stride, _lib.LAYOUT_DENSE,
+                    position.data_ptr(), orientation.data_ptr(), inv_scale.data_ptr(), B, W, H,
+                    cx, cy, fx, fy,
                     _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is),
                     flags | _lib.ZERO_GRADS, _stream()), "sdfr_compare_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None, None
@@ -412,9 +470,11 @@ class _CompositeRender(torch.autograd.Function):
         with torch.cuda.device_of(sdf):
             depth = torch.empty((H, W), dtype=torch.float32, device=sdf.device)
             winner = torch.empty((H, W), dtype=torch.int32, device=sdf.device)
+            src, src_stride, layout = _grid_operand(sdf, R, stride, K, W * H // max(K, 1))
             _lib.check(_lib.lib().sdfr_forward_composite(
-                sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
-                inv_scale.data_ptr(), K, W, H, cx, cy, fx, fy, float(threshold),
+                src.data_ptr(), R, src_stride, layout, position.data_ptr(),
+                orientation.data_ptr(), inv_scale.data_ptr(), K, W, H, cx, cy, fx, fy,
+                float(threshold),
                 depth.data_ptr(), winner.data_ptr(), _stream()), "sdfr_forward_composite")
         ctx.save_for_backward(depth, winner, sdf, position, orientation, inv_scale)
         ctx.meta = (K, R, stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
@@ -438,7 +498,8 @@ class _CompositeRender(torch.autograd.Function):
             with torch.cuda.device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward_composite(
                     grad_depth.data_ptr(), depth.data_ptr(), winner.data_ptr(), sdf.data_ptr(), R,
-                    stride, position.data_ptr(), orientation.data_ptr(), inv_scale.data_ptr(), K,
+                    stride, _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
+                    inv_scale.data_ptr(), K,
                     W, H, cx, cy, fx, fy, _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is),
                     flags, _stream()), "sdfr_backward_composite")
         return g_sdf, g_p, g_q, g_is, None, None, None
@@ -468,7 +529,7 @@ def forward_stats(sdf, position, orientation, inv_scale, threshold, camera):
         depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
         stats = torch.zeros(4, dtype=torch.int64, device=sdf.device)
         _lib.check(_lib.lib().sdfr_forward_stats(
-            sdf.data_ptr(), R, stride, position.data_ptr(), orientation.data_ptr(),
+            sdf.data_ptr(), R, stride, _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
             inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold), depth.data_ptr(),
             stats.data_ptr(), _stream()), "sdfr_forward_stats")
         s = stats.tolist()

@@ -15,19 +15,22 @@
 
 using namespace sdfr;
 
-static void build_frame_host(Frame& F, const float* pos, const float* quat, const float* inv_scale,
-                             const Camera& cam) {
+static int build_frame_host(Frame& F, const float* pos, const float* quat, const float* inv_scale,
+                            const Camera& cam, HullEdge* edges = nullptr) {
   frame_pose(F, pos, quat, inv_scale);
   bool all_ok = true;
   float cmin = INFINITY, cmax = -INFINITY, rmin = INFINITY, rmax = -INFINITY;
+  float cols[8], rows[8];
   for (int k = 0; k < 8; ++k) {
     float col = 0.f, row = 0.f;
     const bool ok = project_corner(F, cam, k, col, row);
     all_ok = all_ok && ok;
+    cols[k] = col; rows[k] = row;
     cmin = fminf(cmin, col); cmax = fmaxf(cmax, col);
     rmin = fminf(rmin, row); rmax = fmaxf(rmax, row);
   }
   frame_rect(F, cam, all_ok, cmin, cmax, rmin, rmax);
+  return edges ? build_hull_serial(cols, rows, all_ok, edges) : 0;
 }
 
 extern "C" int emul_forward(const float* sdf, int R, const float* pos, const float* quat,
@@ -37,14 +40,23 @@ extern "C" int emul_forward(const float* sdf, int R, const float* pos, const flo
   const Grid G = make_grid(R);
   const Camera cam{W, H, cx, cy, fx, fy};
   Frame F;
-  build_frame_host(F, pos, quat, inv_scale, cam);
-  if (rect) { rect[0] = F.x0; rect[1] = F.y0; rect[2] = F.x1; rect[3] = F.y1; }
+  HullEdge edges[kMaxHullEdges];
+  const int n_edges = build_frame_host(F, pos, quat, inv_scale, cam, edges);
+  /* rect[4] = hull edges found, rect[5] = pixels the hull culls inside the rectangle */
+  if (rect) { rect[0] = F.x0; rect[1] = F.y0; rect[2] = F.x1; rect[3] = F.y1; rect[4] = n_edges; rect[5] = 0; }
   for (int py = 0; py < H; ++py)
     for (int px = 0; px < W; ++px) {
       float z = 0.f;
       int steps = 0;
       bool capped = false;
-      if (!use_rect || (px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1)) {
+      bool keep = !use_rect || (px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1);
+      if (keep && use_rect == 2) { /* the kernels test whole 8x4-pixel warp tiles */
+        const float bx = (float)(px & ~7), by = (float)(py & ~3);
+        for (int e = 0; e < kMaxHullEdges; ++e)
+          if (hull_block_outside(edges[e], bx, by, 8.0f, 4.0f)) keep = false;
+        if (!keep && rect) rect[5] += 1;
+      }
+      if (keep) {
         const Ray r = make_ray(F, pixel_dx(px, cx, fx), pixel_dy(py, cy, fy));
         float t_min, t_max;
         if (ray_box(F, r, t_min, t_max))

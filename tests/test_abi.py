@@ -59,21 +59,42 @@ def test_flag_values_match_header():
 def test_argument_errors_need_no_gpu(lib):
     cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
     # empty batch / empty image: success, nothing launched
-    assert lib.sdfr_forward(None, 4, 0, None, None, None, 0, *cam, 0.01, None, None) == 0
-    assert lib.sdfr_forward(None, 4, 0, None, None, None, 1, 0, 8, 4.0, 4.0, 4.0, 4.0, 0.01,
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 0, *cam, 0.01, None, None) == 0
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 1, 0, 8, 4.0, 4.0, 4.0, 4.0, 0.01,
                             None, None) == 0
     # NULL inputs
-    assert lib.sdfr_forward(None, 4, 0, None, None, None, 1, *cam, 0.01, None, None) == -1
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 1, *cam, 0.01, None, None) == -1
     assert b"NULL" in lib.sdfr_last_error()
     # bad resolution / negative sizes
-    assert lib.sdfr_forward(None, 1, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
-    assert lib.sdfr_forward(None, 4, 0, None, None, None, -1, *cam, 0.01, None, None) == -2
-    assert lib.sdfr_forward(None, 4, -5, None, None, None, 1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 1, 0, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, -1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 4, -5, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
     # unknown flags in backward
-    assert lib.sdfr_backward(None, None, None, 4, 0, None, None, None, 0, *cam, None, 0, None,
+    assert lib.sdfr_backward(None, None, None, 4, 0, 0, None, None, None, 0, *cam, None, 0, None,
                              None, None, 0x8000, None) == -3
     with pytest.raises(RuntimeError, match="argument error"):
         _lib.check(-1, "sdfr_forward")
+
+
+def test_skewed_layout_geometry():
+    """Pitches of the bank-conflict-free layout: pitch_y = 3, pitch_x = 9 (mod 32), no overlap."""
+    import ctypes
+
+    lib = _lib.lib()
+    for R in (2, 16, 24, 32, 48, 64, 100, 128):
+        py, px, n = ctypes.c_int(0), ctypes.c_int(0), ctypes.c_longlong(0)
+        assert lib.sdfr_skewed_pitches(R, ctypes.byref(py), ctypes.byref(px), ctypes.byref(n)) == 0
+        assert py.value >= R and py.value % 32 == 3 and py.value < R + 32
+        assert px.value >= R * py.value and px.value % 32 == 9 and px.value < R * py.value + 32
+        assert n.value == R * px.value
+    assert lib.sdfr_skewed_pitches(64, None, None, None) == 0
+    assert lib.sdfr_skewed_pitches(1, None, None, None) == -2
+    # argument checks of the copy (nothing is launched)
+    assert lib.sdfr_skew_grids(None, 64, 0, 0, None, 0, None) == 0
+    assert lib.sdfr_skew_grids(None, 64, 0, 1, None, 0, None) == -1
+    # unknown layout id
+    cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
+    assert lib.sdfr_forward(None, 4, 0, 7, None, None, None, 1, *cam, 0.01, None, None) == -3
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

@@ -390,7 +390,7 @@ def test_depth_buffer_is_fully_written(cuda_device):
     sdf, p = T(sdf_sphere(16), cuda_device), T([0.3, 0, -1.0], cuda_device)
     q, s = T([0, 0, 0, 1.0], cuda_device), T([4.0], cuda_device)
     out = torch.full((H, W), float("nan"), device=cuda_device)
-    _lib.check(lib.sdfr_forward(sdf.data_ptr(), 16, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1,
+    _lib.check(lib.sdfr_forward(sdf.data_ptr(), 16, 0, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1,
                                 W, H, cam["cx"], cam["cy"], cam["fx"], cam["fy"], 0.005,
                                 out.data_ptr(), torch.cuda.current_stream().cuda_stream), "fwd")
     assert not torch.isnan(out).any() and (out > 0).any() and (out == 0).any()
@@ -444,7 +444,7 @@ def test_non_default_stream_and_graph_capture(cuda_device):
     cp = default_camera(W, H)
     graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(graph):
-        _lib.check(lib.sdfr_forward(a[0].data_ptr(), 64, 0, a[1].data_ptr(), a[2].data_ptr(),
+        _lib.check(lib.sdfr_forward(a[0].data_ptr(), 64, 0, 0, a[1].data_ptr(), a[2].data_ptr(),
                                     a[3].data_ptr(), B, W, H, cp["cx"], cp["cy"], cp["fx"],
                                     cp["fy"], thr, out.data_ptr(),
                                     torch.cuda.current_stream().cuda_stream), "captured forward")
@@ -620,3 +620,51 @@ def test_hypothesis_optimizer_recovers_pose(cuda_device):
     err0 = torch.linalg.norm(hyp["position"][1:][best] - true_p[0]).item()
     err1 = torch.linalg.norm(opt.position[best].detach() - true_p[0]).item()
     assert err1 < max(0.5 * err0, 2e-3), (err0, err1)
+
+
+def test_skewed_layout_gives_identical_results(cuda_device):
+    """The pitched (bank-conflict-free) copy holds the same fp32 values: depth, loss and all four
+    gradients must be bit-identical between the two layouts (only float-atomic order differs for
+    the sums, hence allclose there), for compile-time (64, 32) and run-time (24) resolutions."""
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import get_sdf_layout_policy, set_sdf_layout_policy
+
+    old = get_sdf_layout_policy()
+    try:
+        for R in (64, 32, 24):
+            B, W, H, thr = 3, 160, 120, 0.005
+            cam = Camera(W, H, W / 2, W / 2, W / 2, H / 2, pixel_center=0.5)
+            hyp = syn.make_hypotheses(B, seed=3, device=cuda_device)
+            grids = syn.hypothesis_grids(hyp["shape_param"], R, cuda_device)
+            res = {}
+            for policy in ("dense", "skewed"):
+                set_sdf_layout_policy(policy)
+                a = [grids.clone().requires_grad_(True), hyp["position"].clone().requires_grad_(True),
+                     hyp["orientation"].clone().requires_grad_(True),
+                     hyp["inv_scale"].clone().requires_grad_(True)]
+                d = render_depth_batched(*a, thr, cam)
+                obs = d[0].detach().clone()
+                loss, depth, n = render_and_compare(*a, obs, thr, cam)
+                loss[1:].sum().backward()
+                res[policy] = (d.detach(), depth, n, loss.detach(), [x.grad for x in a])
+                assert (d > 0).sum() > 500
+            dd, ds = res["dense"], res["skewed"]
+            assert torch.equal(dd[0], ds[0]) and torch.equal(dd[1], ds[1]) and torch.equal(dd[2], ds[2])
+            assert torch.allclose(dd[3][1:], ds[3][1:], rtol=1e-5, atol=0)
+            for gd, gs in zip(dd[4], ds[4]):
+                scale = float(gd.abs().max())
+                assert scale > 0 and float((gd - gs).abs().max()) <= 2e-4 * scale
+        # single-frame reference API through the skewed copy
+        set_sdf_layout_policy("skewed")
+        z = load_golden("mug_z0_r64")
+        args = [torch.as_tensor(np.asarray(z[k], np.float32), device=cuda_device)
+                for k in ("sdf", "position", "orientation")]
+        inv = torch.tensor([float(z["inv_scale"])], device=cuda_device)
+        cam = Camera(z["W"], z["H"], z["cam"]["fx"], z["cam"]["fy"], z["cam"]["cx"], z["cam"]["cy"],
+                     pixel_center=0.5)
+        d_sk = render_depth_gpu(*args, inv, threshold=float(z["threshold"]), camera=cam)
+        set_sdf_layout_policy("dense")
+        d_de = render_depth_gpu(*args, inv, threshold=float(z["threshold"]), camera=cam)
+        assert torch.equal(d_sk, d_de)
+    finally:
+        set_sdf_layout_policy(old)

@@ -39,7 +39,7 @@ def run_forward(lib, sdf, pos, quat, inv_scale, W, H, cam, thr, use_rect=1):
     s = np.asarray([inv_scale], f32)
     depth = np.empty((H, W), f32)
     steps = np.empty((H, W), np.int32)
-    rect = np.zeros(4, np.int32)
+    rect = np.zeros(6, np.int32)
     cf = [ctypes.c_float(v) for v in (cam["cx"], cam["cy"], cam["fx"], cam["fy"], thr)]
     lib.emul_forward(P(sdf), sdf.shape[0], P(pos), P(quat), P(s), W, H, *cf, P(depth), P(steps),
                      P(rect), use_rect)
@@ -108,13 +108,36 @@ def test_rectangle_culling_is_conservative(emul):
     assert n_culled > 10  # the culling is actually exercised
 
 
+def test_hull_culling_is_conservative(emul):
+    """Same as above for the silhouette (convex hull of the projected corners) culling that the
+    kernels apply per 8x4-pixel warp tile: identical images, and it culls more than the rectangle."""
+    rng = np.random.default_rng(1)
+    grids = [sdf_sphere(16), sdf_box(20), sdf_torus(24)]
+    W, H = 96, 64
+    cam = default_camera(W, H)
+    culled, with_hull = 0, 0
+    for i in range(120):
+        sdf = grids[i % 3]
+        scale = rng.uniform(0.05, 0.6)
+        pos = np.array([rng.uniform(-0.8, 0.8), rng.uniform(-0.6, 0.6), rng.uniform(-1.5, 0.3)])
+        q = shoemake(500 + i) if i % 4 else np.array([0.0, 0.0, 0.0, 1.0])  # incl. face-on views
+        a, _, rect = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005, use_rect=2)
+        b, _, _ = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005, use_rect=0)
+        assert np.array_equal(a, b), (i, pos, scale, rect)
+        assert 0 <= rect[4] <= 8
+        with_hull += rect[4] >= 3
+        culled += int(rect[5])
+    assert with_hull > 40 and culled > 5000
+
+
 def test_full_size_mug_frame_matches_oracle(emul):
     """One 640x480 frame of the reference workload (mug SDF, default camera)."""
     sdf = mug_sdf()
     W, H = 640, 480
     cam = default_camera(W, H)
     pos, q, scale = [0.02, -0.01, -0.4], shoemake(1), 0.15
-    depth, steps, rect = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005)
+    depth, steps, rect = run_forward(emul, sdf, pos, q, 1 / scale, W, H, cam, 0.005, use_rect=2)
+    assert rect[4] >= 4 and rect[5] > 0.2 * (rect[2] - rect[0]) * (rect[3] - rect[1])
     d_or, st_or, _ = oracle.render(sdf, pos, q, 1 / scale, W, H, threshold=0.005, extras=True,
                                    nthreads=8, **cam)
     assert np.array_equal(depth, d_or)
