@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 2
+#define SDFR_ABI_VERSION 3
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -197,6 +197,30 @@ int sdfr_backward_composite(const float* grad_depth, const float* depth, const i
                             long long grad_sdf_stride, float* grad_position,
                             float* grad_orientation, float* grad_inv_scale, unsigned flags,
                             void* stream);
+
+/*
+ * Point-cloud loss of the render-and-compare loop, batched: replaces the caller-side torch helper
+ * estimation/losses.py:32-135 (pc_loss) as used by estimation/simple_setup.py:134-144
+ * (loss_pc = mean |pc_loss|).  points [n_points,3] in the camera frame (hypothesis b reads
+ * points + b*points_stride; 0 = one shared cloud); orientation is NOT required to be unit length
+ * (normalised inside, with the gradient of the normalisation, losses.py:56); `scale` (not its
+ * inverse) as in the reference.  Forward:  loss_sum[b] += sum_m |SDF_b(x_m) * scale_b|  with 0
+ * for points outside the grid.  Backward: gradients of  sum_b upstream[b]*loss_sum[b]  (upstream
+ * NULL = 1) accumulated into grad_sdf (dense, true trilinear weights), grad_position,
+ * grad_orientation and grad_scale (selected by SDFR_GRAD_INV_SCALE).  SDFR_ZERO_GRADS as above.
+ */
+int sdfr_point_loss_forward(const float* points, long long points_stride, int n_points,
+                            const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
+                            const float* position, const float* orientation, const float* scale,
+                            int batch, float* loss_sum, unsigned flags, void* stream);
+
+int sdfr_point_loss_backward(const float* points, long long points_stride, int n_points,
+                             const float* sdf, int resolution, long long sdf_stride,
+                             int sdf_layout, const float* position, const float* orientation,
+                             const float* scale, int batch, const float* upstream,
+                             float* grad_sdf, long long grad_sdf_stride, float* grad_position,
+                             float* grad_orientation, float* grad_scale, unsigned flags,
+                             void* stream);
 
 #ifdef __cplusplus
 }

@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libsdfrender.so")
 SOURCES = [os.path.join(CSRC, "sdfrender.cu")]
 HEADERS = [
     os.path.join(CSRC, "sdfr_core.cuh"),
+    os.path.join(CSRC, "sdfr_points.cuh"),
     os.path.join(os.path.dirname(PKG_DIR), "include", "sdfrender.h"),
 ]
 NVCC_FLAGS = [

@@ -471,8 +471,11 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
  * Only tiles inside the projected box are visited: `depth` must be the image the forward
  * produced for the same pose (it is zero everywhere else).
  * ---------------------------------------------------------------------------------------- */
+/* Register budget of the backward kernels: the SDF+pose variant needs ~80 registers; squeezed
+ * into 64 (4 CTAs/SM) it spills, and the spill traffic (7 M write sectors per launch at C2,
+ * profiles/r01d_bwd_ncu.txt) made it 4x slower than either single-purpose variant. */
 template <int RT, int LT, int MODE, bool WANT_SDF, bool WANT_POSE>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, (WANT_SDF && WANT_POSE) ? 3 : 4)
 sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
@@ -905,19 +908,52 @@ void launch_backward_rt(BwdParams& P, dim3 grid, size_t smem, bool want_sdf, boo
     sdfr_backward_kernel<RT, LT, MODE, false, true><<<grid, kThreads, smem, s>>>(P);
 }
 
+/*
+ * The backward is launched in chunks of hypotheses whose working set (gradient grid, SDF grid,
+ * depth and upstream images) fits comfortably in L2, each chunk's gradient grids being cleared
+ * right before its kernel: the scattered RED.ADDs then hit lines that are still L2-resident.
+ * Clearing all grids up front lets the streaming reads of the first hypotheses evict the zeroed
+ * lines of the later ones, and every RED becomes a 32-byte read-modify-write against HBM
+ * (measured at B = 64, 64^3, 640x480: 457 us against 105 us for the pose gradients alone).
+ */
 template <int MODE>
-int launch_backward(BwdParams P, int batch, cudaStream_t s) {
+int launch_backward(BwdParams P, int batch, bool zero_sdf, cudaStream_t s) {
   const bool want_sdf = (P.flags & SDFR_GRAD_SDF) != 0;
   const bool want_pose =
       (P.flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
   if (!want_sdf && !want_pose) return 0;
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
-  const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
   const bool skewed = P.grid.py != P.grid.R;
-  for (int z0 = 0; z0 < batch; z0 += 65535) {
+  const size_t grid_bytes = sizeof(float) * (size_t)P.grid.R * P.grid.R * P.grid.R;
+  int chunk = batch;
+  if (want_sdf && P.grad_sdf_stride != 0) {
+    const size_t per_hyp = grid_bytes + (P.sdf_stride != 0 ? grid_bytes : 0) +
+                           2 * sizeof(float) * (size_t)P.cam.W * P.cam.H;
+    size_t budget_mb = 0; /* 0 = one launch for the whole batch */
+    if (const char* env = getenv("SDFR_BWD_CHUNK_MB")) budget_mb = (size_t)atoll(env);
+    if (budget_mb > 0) {
+      chunk = (int)((budget_mb << 20) / per_hyp);
+      chunk = chunk < 1 ? 1 : (chunk > batch ? batch : chunk);
+    }
+  } else if (zero_sdf && want_sdf) { /* one shared gradient grid */
+    if (int rc = zero_async(P.grad_sdf, grid_bytes, s)) return rc;
+  }
+  if (chunk > 65535) chunk = 65535;
+  for (int z0 = 0; z0 < batch; z0 += chunk) {
+    const int nz = batch - z0 < chunk ? batch - z0 : chunk;
+    if (zero_sdf && want_sdf && P.grad_sdf_stride != 0) {
+      if ((size_t)P.grad_sdf_stride * sizeof(float) == grid_bytes) {
+        if (int rc = zero_async(P.grad_sdf + (size_t)z0 * P.grad_sdf_stride, grid_bytes * nz, s))
+          return rc;
+      } else {
+        for (int b = z0; b < z0 + nz; ++b)
+          if (int rc = zero_async(P.grad_sdf + (size_t)b * P.grad_sdf_stride, grid_bytes, s))
+            return rc;
+      }
+    }
     P.z_offset = z0;
-    const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
+    const dim3 grid(ctas_per_hypothesis(nz, P.cam.W, P.cam.H), nz);
 #define SDFR_CALL(RT, LT) launch_backward_rt<RT, LT, MODE>(P, grid, smem, want_sdf, want_pose, s)
     SDFR_DISPATCH_RT_LT(P.grid.R, skewed, SDFR_CALL);
 #undef SDFR_CALL
@@ -998,6 +1034,8 @@ BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_
   return P;
 }
 
+#include "sdfr_points.cuh"
+
 }  // namespace
 
 extern "C" {
@@ -1042,13 +1080,16 @@ int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf,
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (batch == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
-  if (W == 0 || H == 0) return 0;
+  const bool empty = W == 0 || H == 0;
+  if (int rc = zero_grads(empty ? flags : flags & ~SDFR_GRAD_SDF, R, batch, gs, gs_stride, gp, gq,
+                          gi, s))
+    return rc;
+  if (empty) return 0;
   if (!grad_depth || !depth) return fail(SDFR_E_NULL, "grad_depth or depth is NULL");
   BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
                            gs, gs_stride, gp, gq, gi, flags);
   P.grad_depth = grad_depth;
-  return launch_backward<0>(P, batch, s);
+  return launch_backward<0>(P, batch, (flags & SDFR_ZERO_GRADS) != 0, s);
 }
 
 int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
@@ -1088,8 +1129,11 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if (batch == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
-  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
-  if (W == 0 || H == 0) return 0;
+  const bool empty = W == 0 || H == 0;
+  if (int rc = zero_grads(empty ? flags : flags & ~SDFR_GRAD_SDF, R, batch, gs, gs_stride, gp, gq,
+                          gi, s))
+    return rc;
+  if (empty) return 0;
   if (!depth || !depth_obs || !n_overlap)
     return fail(SDFR_E_NULL, "depth, depth_obs or n_overlap is NULL");
   BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
@@ -1098,7 +1142,7 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   P.obs_stride = obs_stride;
   P.n_overlap = n_overlap;
   P.upstream = upstream;
-  return launch_backward<1>(P, batch, s);
+  return launch_backward<1>(P, batch, (flags & SDFR_ZERO_GRADS) != 0, s);
 }
 
 int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
@@ -1235,6 +1279,55 @@ int sdfr_skew_grids(const float* sdf, int R, long long sdf_stride, int batch, fl
         skewed_stride, R, G.py, G.px);
   }
   return check_launch("sdfr_skew_kernel");
+}
+
+int sdfr_point_loss_forward(const float* points, long long points_stride, int n_points,
+                            const float* sdf, int R, long long sdf_stride, int layout,
+                            const float* pos, const float* quat, const float* scale, int batch,
+                            float* loss_sum, unsigned flags, void* stream) {
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, scale, batch, 1, 1)) return rc;
+  if (flags & ~SDFR_ZERO_GRADS) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (n_points < 0 || points_stride < 0) return fail(SDFR_E_SHAPE, "negative n_points or stride");
+  if (batch == 0) return 0;
+  if (!loss_sum) return fail(SDFR_E_NULL, "loss_sum is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & SDFR_ZERO_GRADS)
+    if (int rc = zero_async(loss_sum, sizeof(float) * batch, s)) return rc;
+  if (n_points == 0) return 0;
+  if (!points) return fail(SDFR_E_NULL, "points is NULL");
+  PointParams P;
+  memset(&P, 0, sizeof(P));
+  P.points = points; P.points_stride = points_stride; P.n_points = n_points;
+  P.sdf = sdf; P.sdf_stride = sdf_stride; P.grid = make_grid(R, layout);
+  P.position = pos; P.orientation = quat; P.scale = scale;
+  P.loss_sum = loss_sum;
+  return launch_point_loss<false>(P, batch, s);
+}
+
+int sdfr_point_loss_backward(const float* points, long long points_stride, int n_points,
+                             const float* sdf, int R, long long sdf_stride, int layout,
+                             const float* pos, const float* quat, const float* scale, int batch,
+                             const float* upstream, float* gs, long long gs_stride, float* gp,
+                             float* gq, float* gscale, unsigned flags, void* stream) {
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, scale, batch, 1, 1)) return rc;
+  if (flags & SDFR_SDF_GRAD_EXACT) return fail(SDFR_E_FLAGS, "the point loss has one weight list");
+  if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gscale)) return rc;
+  if (n_points < 0 || points_stride < 0) return fail(SDFR_E_SHAPE, "negative n_points or stride");
+  if (batch == 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gscale, s)) return rc;
+  if (n_points == 0) return 0;
+  if (!points) return fail(SDFR_E_NULL, "points is NULL");
+  PointParams P;
+  memset(&P, 0, sizeof(P));
+  P.points = points; P.points_stride = points_stride; P.n_points = n_points;
+  P.sdf = sdf; P.sdf_stride = sdf_stride; P.grid = make_grid(R, layout);
+  P.position = pos; P.orientation = quat; P.scale = scale;
+  P.upstream = upstream;
+  P.grad_sdf = gs; P.grad_sdf_stride = gs_stride;
+  P.grad_position = gp; P.grad_orientation = gq; P.grad_scale = gscale;
+  P.flags = flags;
+  return launch_point_loss<true>(P, batch, s);
 }
 
 }  // extern "C"

@@ -164,6 +164,25 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NO_CTX = _NoCtx()
+
+
+def _on_device_of(t: torch.Tensor):
+    """Device guard (OptionalCUDAGuard of sdf_renderer.cpp:58, 82) that costs nothing in the
+    common case of the tensor living on the current device."""
+    if t.device.index == torch.cuda.current_device():
+        return _NO_CTX
+    return torch.cuda.device_of(t)
+
+
 def _grad_flags(needs, mode: Optional[str]) -> int:
     mode = _default_sdf_grad_mode if mode is None else mode
     if mode not in _SDF_GRAD_MODES:
@@ -203,9 +222,12 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
         _check_input(inv_scale, "inv_scale", 1)
         R = _check_grid(sdf, batched=False)
         W, H, cx, cy, fx, fy = _camera_params(camera)
-        with torch.cuda.device_of(sdf):
+        with _on_device_of(sdf):
             image = torch.empty((H, W), dtype=torch.float32, device=sdf.device)
-            src, _, layout = _grid_operand(sdf, R, 0, 1, W * H)
+            # one image: the layout pass would cost about what it saves, unless asked for
+            src, layout = sdf, _lib.LAYOUT_DENSE
+            if _sdf_layout_policy == "skewed":
+                src, _, layout = _grid_operand(sdf, R, 0, 1, W * H)
             _lib.check(_lib.lib().sdfr_forward(
                 src.data_ptr(), R, 0, layout, position.data_ptr(), orientation.data_ptr(),
                 inv_scale.data_ptr(), 1, W, H, cx, cy, fx, fy, float(threshold),
@@ -238,7 +260,7 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
         if any(needs):
             grad_depth_image = grad_depth_image.contiguous()
             _check_input(grad_depth_image, "grad_depth_image")
-            with torch.cuda.device_of(sdf):
+            with _on_device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward(
                     grad_depth_image.data_ptr(), image.data_ptr(), sdf.data_ptr(),
                     int(sdf.shape[-1]), 0, _lib.LAYOUT_DENSE, position.data_ptr(),
@@ -315,7 +337,7 @@ class _BatchedRender(torch.autograd.Function):
     def forward(ctx, sdf, position, orientation, inv_scale, threshold, camera, sdf_grad_mode):
         B, R, stride = _check_batch(sdf, position, orientation, inv_scale)
         W, H, cx, cy, fx, fy = _camera_params(camera)
-        with torch.cuda.device_of(sdf):
+        with _on_device_of(sdf):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
             src, src_stride, layout = _grid_operand(sdf, R, stride, B, W * H)
             _lib.check(_lib.lib().sdfr_forward(
@@ -340,7 +362,7 @@ class _BatchedRender(torch.autograd.Function):
         if any(needs):
             grad_depth = grad_depth.contiguous()
             _check_input(grad_depth, "grad_depth")
-            with torch.cuda.device_of(sdf):
+            with _on_device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward(
                     grad_depth.data_ptr(), depth.data_ptr(), sdf.data_ptr(), R, stride,
                     _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
@@ -384,7 +406,7 @@ class _RenderAndCompare(torch.autograd.Function):
         # a grid shared by several hypotheses cannot take the deferred per-hypothesis scaling
         fused = any(needs) and not (needs[0] and stride == 0 and B > 1)
         grads = [None, None, None, None]
-        with torch.cuda.device_of(sdf):
+        with _on_device_of(sdf):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
             sums = torch.empty((2, B), dtype=torch.float32, device=sdf.device)
             lib = _lib.lib()
@@ -425,7 +447,7 @@ class _RenderAndCompare(torch.autograd.Function):
         flags = _grad_flags(needs, mode)
         upstream = grad_loss.to(torch.float32).contiguous()
         lib = _lib.lib()
-        with torch.cuda.device_of(sdf):
+        with _on_device_of(sdf):
             if ctx.fused_grads is not None:
                 # the traversal already happened: only the deferred upstream/n_overlap factor is left
                 g_sdf, g_p, g_q, g_is = ctx.fused_grads
@@ -467,7 +489,7 @@ class _CompositeRender(torch.autograd.Function):
     def forward(ctx, sdf, position, orientation, inv_scale, threshold, camera, sdf_grad_mode):
         K, R, stride = _check_batch(sdf, position, orientation, inv_scale)
         W, H, cx, cy, fx, fy = _camera_params(camera)
-        with torch.cuda.device_of(sdf):
+        with _on_device_of(sdf):
             depth = torch.empty((H, W), dtype=torch.float32, device=sdf.device)
             winner = torch.empty((H, W), dtype=torch.int32, device=sdf.device)
             src, src_stride, layout = _grid_operand(sdf, R, stride, K, W * H // max(K, 1))
@@ -495,7 +517,7 @@ class _CompositeRender(torch.autograd.Function):
         if any(needs):
             grad_depth = grad_depth.contiguous()
             _check_input(grad_depth, "grad_depth")
-            with torch.cuda.device_of(sdf):
+            with _on_device_of(sdf):
                 _lib.check(_lib.lib().sdfr_backward_composite(
                     grad_depth.data_ptr(), depth.data_ptr(), winner.data_ptr(), sdf.data_ptr(), R,
                     stride, _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
@@ -525,7 +547,7 @@ def forward_stats(sdf, position, orientation, inv_scale, threshold, camera):
     """
     B, R, stride = _check_batch(sdf, position, orientation, inv_scale)
     W, H, cx, cy, fx, fy = _camera_params(camera)
-    with torch.cuda.device_of(sdf):
+    with _on_device_of(sdf):
         depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
         stats = torch.zeros(4, dtype=torch.int64, device=sdf.device)
         _lib.check(_lib.lib().sdfr_forward_stats(

@@ -68,7 +68,7 @@ class HypothesisOptimizer:
                  position: torch.Tensor, orientation: torch.Tensor, scale: torch.Tensor,
                  sdf: Optional[torch.Tensor] = None, latent: Optional[torch.Tensor] = None,
                  decoder: Optional[Callable] = None, depth_weight: float = 1.0,
-                 pc_weight: float = 3.0, max_points: int = 4096, group=None):
+                 pc_weight: float = 3.0, max_points: int = 0, group=None):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         self.camera, self.threshold, self.group = camera, float(threshold), group
@@ -87,12 +87,13 @@ class HypothesisOptimizer:
         self.optimizer = torch.optim.Adam(groups, capturable=self.position.is_cuda)
         # observed points, once (the only host sync), sub-sampled to a fixed size
         pts = losses.depth_to_pointcloud(self.depth_obs, camera)
-        if pts.shape[0] > max_points:
+        if max_points and pts.shape[0] > max_points:
             sel = torch.randperm(pts.shape[0], device=pts.device,
                                  generator=torch.Generator(pts.device).manual_seed(0))[:max_points]
             pts = pts[sel]
         self.points = pts.contiguous()
         self.last_losses = None
+        self._graph = None
 
     def _grids(self):
         if self.decoder is None:
@@ -100,8 +101,35 @@ class HypothesisOptimizer:
         g = self.decoder(self.latent)
         return g[:, 0].contiguous() if g.dim() == 5 else g.contiguous()
 
+    def capture(self, warmup: int = 3) -> None:
+        """Capture one whole iteration (decode, render-and-compare, point loss, backward, Adam,
+        renormalisation) in a CUDA graph; step() replays it afterwards.  The reference loop
+        cannot be captured: it synchronises with the host twice per iteration
+        (simple_setup.py:131, pointset_utils.py:60) and its renderer launches on the legacy
+        default stream (sdf_renderer_cuda.cu:495)."""
+        if not self.position.is_cuda:
+            raise RuntimeError("CUDA graphs need CUDA tensors")
+        side = torch.cuda.Stream(self.position.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(graph):
+            self._static_loss = self._eager_step()
+        self._graph = graph
+
     def step(self) -> torch.Tensor:
         """One iteration (simple_setup.py:408-470); returns the detached per-hypothesis loss."""
+        if self._graph is not None:
+            self._graph.replay()
+            self.last_losses = self._static_loss
+            return self.last_losses
+        return self._eager_step()
+
+    def _eager_step(self) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         grids = self._grids()
@@ -110,9 +138,11 @@ class HypothesisOptimizer:
                                               self.threshold, self.camera)
         loss = self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
         if self.pc_weight and self.points.shape[0] > 0:
-            pc = losses.pc_loss(self.points, self.position, q, self.scale,
-                                grids if grids.dim() == 4 else grids[None])
-            loss = loss + self.pc_weight * pc.abs().mean(dim=1)
+            # NB: the reference passes the un-normalised quaternion and lets pc_loss normalise it
+            # (simple_setup.py:436-443, losses.py:56); q is already unit here, same value
+            loss = loss + self.pc_weight * losses.point_loss(
+                self.points, self.position, q, self.scale,
+                grids if grids.dim() == 4 else grids[None])
         loss.sum().backward()
         self.optimizer.step()
         with torch.no_grad():

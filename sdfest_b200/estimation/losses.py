@@ -65,3 +65,88 @@ def pc_loss(points: torch.Tensor, position: torch.Tensor, orientation: torch.Ten
            + (corner(0, 1, 1) * (1 - ox) + corner(1, 1, 1) * ox) * oy) * oz
     val = torch.where(outside, torch.zeros_like(val), val)
     return val * scale[:, None]
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA path: the same loss as ONE kernel pair (sdfr_point_loss_forward / _backward)
+# --------------------------------------------------------------------------------------------
+class _PointLoss(torch.autograd.Function):
+    """mean_m |pc_loss(points, ...)[b, m]| per hypothesis, on the GPU through the C ABI."""
+
+    @staticmethod
+    def forward(ctx, points, position, orientation, scale, sdf):
+        from .. import _lib
+        from ..differentiable_renderer.sdf_renderer import _check_input, _on_device_of, _stream
+
+        for t, n in ((points, "points"), (position, "position"), (orientation, "orientation"),
+                     (scale, "scale"), (sdf, "sdf")):
+            _check_input(t, n)
+        B = position.shape[0]
+        if position.shape != (B, 3) or orientation.shape != (B, 4) or scale.numel() != B:
+            raise RuntimeError("position (B,3), orientation (B,4), scale (B,) expected")
+        if points.dim() == 2 and points.shape[1] == 3:
+            M, pstride = points.shape[0], 0
+        elif points.dim() == 3 and points.shape[0] == B and points.shape[2] == 3:
+            M, pstride = points.shape[1], points.shape[1] * 3
+        else:
+            raise RuntimeError(f"points must be (M,3) or ({B},M,3), got {tuple(points.shape)}")
+        R = sdf.shape[-1]
+        if sdf.dim() != 4 or sdf.shape[0] not in (1, B) or not (sdf.shape[1] == sdf.shape[2] == R):
+            raise RuntimeError(f"sdf must be (1|{B},R,R,R), got {tuple(sdf.shape)}")
+        stride = 0 if sdf.shape[0] == 1 else R ** 3
+        with _on_device_of(sdf):
+            loss_sum = torch.empty(B, dtype=torch.float32, device=sdf.device)
+            _lib.check(_lib.lib().sdfr_point_loss_forward(
+                points.data_ptr(), pstride, M, sdf.data_ptr(), R, stride, _lib.LAYOUT_DENSE,
+                position.data_ptr(), orientation.data_ptr(), scale.data_ptr(), B,
+                loss_sum.data_ptr(), _lib.ZERO_GRADS, _stream()), "sdfr_point_loss_forward")
+        ctx.save_for_backward(points, position, orientation, scale, sdf)
+        ctx.meta = (B, M, pstride, R, stride)
+        return loss_sum / max(M, 1)
+
+    @staticmethod
+    def backward(ctx, grad_loss):
+        from .. import _lib
+        from ..differentiable_renderer.sdf_renderer import _on_device_of, _ptr, _stream
+
+        points, position, orientation, scale, sdf = ctx.saved_tensors
+        B, M, pstride, R, stride = ctx.meta
+        needs = ctx.needs_input_grad
+        if needs[0]:
+            raise RuntimeError("the point loss is not differentiable w.r.t. the observed points")
+        flags = _lib.ZERO_GRADS
+        for need, bit in zip(needs[1:], (_lib.GRAD_POSITION, _lib.GRAD_ORIENTATION,
+                                         _lib.GRAD_INV_SCALE, _lib.GRAD_SDF)):
+            if need:
+                flags |= bit
+        g_p = torch.empty_like(position) if needs[1] else None
+        g_q = torch.empty_like(orientation) if needs[2] else None
+        g_s = torch.empty_like(scale) if needs[3] else None
+        g_sdf = torch.empty_like(sdf) if needs[4] else None
+        if any(needs[1:]):
+            upstream = (grad_loss.to(torch.float32) / max(M, 1)).contiguous()
+            with _on_device_of(sdf):
+                _lib.check(_lib.lib().sdfr_point_loss_backward(
+                    points.data_ptr(), pstride, M, sdf.data_ptr(), R, stride, _lib.LAYOUT_DENSE,
+                    position.data_ptr(), orientation.data_ptr(), scale.data_ptr(), B,
+                    upstream.data_ptr(), _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_s), flags,
+                    _stream()), "sdfr_point_loss_backward")
+        return None, g_p, g_q, g_s, g_sdf
+
+
+def point_loss(points: torch.Tensor, position: torch.Tensor, orientation: torch.Tensor,
+               scale: torch.Tensor, sdf: torch.Tensor) -> torch.Tensor:
+    """Per-hypothesis ``mean_m |pc_loss[b, m]|`` (estimation/simple_setup.py:134-144).
+
+    CUDA tensors run the fused kernels of ``libsdfrender.so`` (all observed points, no
+    sub-sampling, no intermediate (B,M) tensors); CPU tensors -- the gloo host tests -- evaluate
+    the torch restatement above.  points (M,3) or (B,M,3); sdf (B|1,R,R,R).
+    """
+    if points.is_cuda:
+        return _PointLoss.apply(points.contiguous(), position.contiguous(), orientation.contiguous(),
+                                scale.contiguous(), sdf.contiguous())
+    if points.dim() == 3:
+        return torch.stack([pc_loss(points[b], position[b:b + 1], orientation[b:b + 1],
+                                    scale[b:b + 1], sdf[b:b + 1] if sdf.shape[0] > 1 else sdf)[0]
+                            for b in range(position.shape[0])]).abs().mean(dim=1)
+    return pc_loss(points, position, orientation, scale, sdf).abs().mean(dim=1)

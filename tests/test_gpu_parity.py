@@ -668,3 +668,105 @@ def test_skewed_layout_gives_identical_results(cuda_device):
         assert torch.equal(d_sk, d_de)
     finally:
         set_sdf_layout_policy(old)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_streamed_host_buffers_match_device_path(cuda_device, graph):
+    """estimation.StreamedRenderCompare (pinned host inputs, chunked 3-stream pipeline, optional
+    CUDA-graph replay) returns the losses and gradients of render_and_compare + autograd."""
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.estimation import StreamedRenderCompare
+
+    B, R, W, H, thr = 5, 32, 160, 120, 0.005
+    cam = Camera(W, H, W / 2, W / 2, W / 2, H / 2, pixel_center=0.5)
+    hyp = syn.make_hypotheses(B, seed=5, device=cuda_device)
+    grids = syn.hypothesis_grids(hyp["shape_param"], R, cuda_device)
+    a = [grids.clone().requires_grad_(True), hyp["position"].clone().requires_grad_(True),
+         hyp["orientation"].clone().requires_grad_(True), hyp["inv_scale"].clone().requires_grad_(True)]
+    obs = render_depth_batched(grids[:1], hyp["position"][:1] + 0.01, hyp["orientation"][:1],
+                               hyp["inv_scale"][:1], thr, cam)[0].contiguous()
+    loss, depth, n = render_and_compare(*a, obs, thr, cam)
+    loss.sum().backward()
+    host = [t.detach().cpu().pin_memory() for t in (grids, hyp["position"], hyp["orientation"],
+                                                    hyp["inv_scale"], obs)]
+    for sdf_to_host in (False, True):
+        ev = StreamedRenderCompare(cam, thr, B, R, cuda_device, chunk=2, sdf_grads_to_host=sdf_to_host)
+        for _ in range(2):  # second call replays the captured graph
+            out = ev(*host, graph=graph)
+        assert torch.allclose(out["loss"], loss.detach().cpu(), rtol=1e-5, atol=0)
+        assert torch.equal(out["n_overlap"], n.cpu())
+        assert torch.equal(out["depth_device"], depth)
+        for got, want in ((out["g_position"], a[1].grad), (out["g_orientation"], a[2].grad),
+                          (out["g_inv_scale"], a[3].grad), (out["g_sdf_device"], a[0].grad)):
+            want = want.cpu()
+            assert float((got.cpu() - want).abs().max()) <= 2e-4 * float(want.abs().max())
+        if sdf_to_host:
+            assert torch.equal(out["g_sdf_host"].view(B, R, R, R), out["g_sdf_device"].cpu())
+
+
+def _pcloss_reference(points, pos, quat, scale, sdf):
+    """float64 torch restatement of the reference's pc_loss (pinned to its golden vector by
+    tests/test_estimation_host.py) -> per-hypothesis mean |.| and autograd gradients."""
+    from sdfest_b200.estimation import pc_loss
+
+    a = [t.detach().double().cpu().requires_grad_(True) for t in (pos, quat, scale, sdf)]
+    pts = points.detach().double().cpu()
+    if pts.dim() == 2:
+        val = pc_loss(pts, *a).abs().mean(dim=1)
+    else:
+        val = torch.stack([pc_loss(pts[b], a[0][b:b + 1], a[1][b:b + 1], a[2][b:b + 1],
+                                   a[3][b:b + 1] if a[3].shape[0] > 1 else a[3])[0].abs().mean()
+                           for b in range(pts.shape[0])])
+    return val, a
+
+
+@pytest.mark.parametrize("shared_cloud", [True, False])
+@pytest.mark.parametrize("shared_grid", [True, False])
+def test_point_loss_kernel_matches_reference_formula(cuda_device, shared_cloud, shared_grid):
+    """sdfr_point_loss_forward/backward against estimation/losses.py:32-135 (values 1e-5,
+    gradients 1e-3 relative), un-normalised quaternions, points outside the grid included."""
+    from sdfest_b200.estimation import point_loss
+
+    g = torch.Generator().manual_seed(7)
+    B, M, R = 4, 3000, 24
+    sdf = torch.as_tensor(np.stack([sdf_torus(R), sdf_sphere(R), sdf_box(R), sdf_torus(R) * 0.7]),
+                          dtype=torch.float32)
+    if shared_grid:
+        sdf = sdf[:1]
+    pos = torch.tensor([0.05, -0.03, -0.8]) + 0.02 * torch.randn(B, 3, generator=g)
+    quat = torch.as_tensor(np.stack([shoemake(20 + i) for i in range(B)]), dtype=torch.float32)
+    quat = quat * (0.5 + torch.rand(B, 1, generator=g))  # un-normalised on purpose
+    scale = 0.3 * (1 + 0.2 * (torch.rand(B, generator=g) - 0.5))
+    pts = torch.tensor([0.05, -0.03, -0.8]) + (torch.rand(M if shared_cloud else B * M, 3, generator=g) - 0.5) * 0.8
+    if not shared_cloud:
+        pts = pts.view(B, M, 3)
+    w = torch.tensor([1.0, 0.4, 2.0, 1.3])
+    ref, a = _pcloss_reference(pts, pos, quat, scale, sdf)
+    (ref * w.double()).sum().backward()
+    d = [t.to(cuda_device).requires_grad_(True) for t in (pos, quat, scale, sdf)]
+    got = point_loss(pts.to(cuda_device), *d)
+    (got * w.to(cuda_device)).sum().backward()
+    assert np.abs(got.detach().cpu().numpy() - ref.detach().numpy()).max() <= 1e-5 * ref.max().item()
+    assert 0.05 < float((ref > 0).float().mean()) <= 1.0
+    for nm, x, y in zip(("position", "orientation", "scale", "sdf"), d, a):
+        grad_close(x.grad.cpu().numpy(), y.grad.numpy(), GRAD_RTOL, "point loss " + nm)
+        assert float(y.grad.abs().max()) > 0
+
+
+def test_point_loss_kernel_matches_reference_golden(cuda_device):
+    """The reference's own pc_loss outputs and autograd gradients (tests/golden/pcloss_torus16)."""
+    import os
+
+    from sdfest_b200.estimation import point_loss
+    from util import GOLDEN_DIR
+
+    z = np.load(os.path.join(GOLDEN_DIR, "pcloss_torus16.npz"))
+    t = lambda k: torch.tensor(np.asarray(z[k], np.float32), device=cuda_device)  # noqa: E731
+    pos, quat = t("position")[None].requires_grad_(True), t("orientation")[None].requires_grad_(True)
+    scale, sdf = t("scale").reshape(1).requires_grad_(True), t("sdf")[None].requires_grad_(True)
+    got = point_loss(t("points"), pos, quat, scale, sdf)
+    got.sum().backward()
+    want = np.abs(z["value"]).mean()
+    assert abs(got.item() - want) <= 1e-5 * want
+    for x, key in ((pos, "g_position"), (quat, "g_orientation"), (scale, "g_scale"), (sdf, "g_sdf")):
+        grad_close(x.grad.cpu().numpy().reshape(z[key].shape), z[key], GRAD_RTOL, key)
