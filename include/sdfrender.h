@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 3
+#define SDFR_ABI_VERSION 4
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -221,6 +221,37 @@ int sdfr_point_loss_backward(const float* points, long long points_stride, int n
                              float* grad_sdf, long long grad_sdf_stride, float* grad_position,
                              float* grad_orientation, float* grad_scale, unsigned flags,
                              void* stream);
+
+/*
+ * Decoder tail: the last two operators of the reference SDF decoder,
+ *   interpolate(x -> (R,R,R), mode="trilinear", align_corners=False)   sdfest/vae/sdf_vae.py:235-244
+ *   Conv3d(channels -> 1, kernel_size=1), no ReLU                       sdfest/vae/sdf_vae.py:245-247
+ * as ONE pass that never materialises the channels x R^3 intermediate and writes the grid in the
+ * layout the renderer reads (dense or skewed; sdf_stride >= elements of one grid in that layout).
+ * x [batch, channels, in_size^3]; weight [channels] (the conv weight (1,C,1,1,1) flattened); bias
+ * [1] or NULL; base: an optional dense [R,R,R] grid added to every hypothesis' output (residual
+ * decoding around a fixed shape; NULL for the reference decoder).  channels <= 16; in_size,
+ * resolution <= 128.  Interpolation indices and weights
+ * are ATen's (upsample_trilinear3d, align_corners = false); the channel contraction is done before
+ * the interpolation (both are linear), so results agree with torch to fp32 rounding.
+ */
+int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const float* weight,
+                              const float* bias, const float* base, int batch, int resolution,
+                              float* sdf, long long sdf_stride, int sdf_layout, void* stream);
+
+/*
+ * Adjoint of sdfr_decoder_tail_forward w.r.t. x (the decoder is frozen in the estimation loop,
+ * simple_setup.py:65: no weight / bias gradients):  grad_x[b] = (written, not accumulated)
+ *   weight[c] * W^T ( coef[b] * grad_sdf[b] + grad_sdf_extra[b] ),
+ * coef[b] = (upstream ? upstream[b] : 1) / n_overlap[b] (0 where n_overlap[b] == 0) when n_overlap
+ * is given -- the normalisation sdfr_compare_fused defers -- else upstream[b] (or 1).  Both
+ * gradient grids are dense; grad_sdf_extra may be NULL.
+ */
+int sdfr_decoder_tail_backward(const float* grad_sdf, long long grad_sdf_stride,
+                               const float* n_overlap, const float* upstream,
+                               const float* grad_sdf_extra, long long extra_stride,
+                               const float* weight, int channels, int in_size, int batch,
+                               int resolution, float* grad_x, void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sdfest_b200 import synthetic as syn  # noqa: E402
 from sdfest_b200.differentiable_renderer import Camera, render_and_compare, render_depth_batched  # noqa: E402
-from sdfest_b200.estimation import HypothesisOptimizer, SurfaceDecoder, losses  # noqa: E402
+from sdfest_b200.estimation import (FusedTailDecoder, HypothesisOptimizer, SDFDecoder,  # noqa: E402
+                                    SurfaceDecoder, losses)
 
 W, H, R, THR = 640, 480, 64, 0.005
 B = int(os.environ.get("LOOP_B", "64"))
@@ -42,8 +43,13 @@ def make(decoder):
     return HypothesisOptimizer(cam, THR, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"], **kw)
 
 
+torch.manual_seed(0)
+_plain = SDFDecoder(R)
+_fused = FusedTailDecoder(SDFDecoder(R))
+_fused.decoder.load_state_dict(_plain.state_dict())
 for name, dec in (("pose_only", None),
-                  ("pose_latent", SurfaceDecoder(syn.sdf_mug(R, dev)).to(dev).eval())):
+                  ("pose_latent", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_plain).to(dev).eval()),
+                  ("pose_latent_fused_tail", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_fused).to(dev).eval())):
     if dec is not None:
         for p in dec.parameters():
             p.requires_grad_(False)

@@ -19,6 +19,7 @@ SOURCES = [os.path.join(CSRC, "sdfrender.cu")]
 HEADERS = [
     os.path.join(CSRC, "sdfr_core.cuh"),
     os.path.join(CSRC, "sdfr_points.cuh"),
+    os.path.join(CSRC, "sdfr_decoder.cuh"),
     os.path.join(os.path.dirname(PKG_DIR), "include", "sdfrender.h"),
 ]
 NVCC_FLAGS = [

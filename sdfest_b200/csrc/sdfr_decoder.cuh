@@ -1,0 +1,246 @@
+/*
+ * sdfr_decoder.cuh -- the tail of the SDF decoder as sm_100a kernels.
+ * Included by sdfrender.cu inside its anonymous namespace.
+ *
+ * The reference decoder (sdfest/vae/sdf_vae.py:217-259, layer sizes
+ * estimation/configs/models/mug.yaml:2-12) ends with
+ *     interpolate(x[N,C,S,S,S] -> (R,R,R), mode="trilinear", align_corners=False)   sdf_vae.py:235-244
+ *     Conv3d(C -> 1, kernel_size=1), no ReLU                                          sdf_vae.py:245-247
+ * (C = 4, S = 30, R = 64 for every shipped model).  Run through torch this materialises a
+ * C x R^3 intermediate per hypothesis (4 MiB at 64^3; 256 MiB for 64 hypotheses) that is written,
+ * read back by the convolution, and -- in the backward -- produced and consumed once more.  Both
+ * operators are linear and act on different axes (channels vs. space), so they commute:
+ *     sdf[o] = bias + sum_s W(o, s) * (sum_c weight[c] * x[c, s])
+ * and the tail becomes ONE pass that reads the 4 x 30^3 input and writes the R^3 grid directly in
+ * whichever layout the renderer wants (dense, or the bank-conflict-free skewed layout of
+ * sdfr_core.cuh -- which also removes the separate sdfr_skew_grids pass from the loop).
+ *
+ * Interpolation weights follow ATen's upsample_trilinear3d exactly (align_corners = False,
+ * no scale_factor):  src = max(0, (S/R) * (o + 0.5) - 0.5),  i0 = (int)src,
+ * i1 = i0 + (i0 < S-1),  l1 = src - i0,  l0 = 1 - l1.  Floating point: the summation order differs
+ * from torch's (channel contraction first), so parity is to fp32 rounding, not bit-exact.
+ *
+ * Backward = the adjoint: grad_x[c, s] = weight[c] * sum_o W(o, s) * g[o], evaluated separably
+ * (x, then z, then y) in shared memory by one CTA per source x-plane, with the deferred
+ * per-hypothesis normalisation of the fused render-and-compare gradient (upstream/n_overlap,
+ * sdfr_compare_fused) and an optional second gradient grid (the point-cloud loss) folded into the
+ * load:  g = coef[b] * grad_sdf + grad_sdf_extra.  The decoder weights are frozen in the
+ * estimation loop (simple_setup.py:65), so no weight/bias gradients are produced.
+ */
+#ifndef SDFR_DECODER_CUH_
+#define SDFR_DECODER_CUH_
+
+constexpr int kTailMaxChannels = 16;
+constexpr int kTailMaxSize = 128; /* S, R <= 128: the separable backward keeps an R x R plane in shared memory */
+
+struct TailParams {
+  const float* __restrict__ x;       /* [B, C, S, S, S] */
+  const float* __restrict__ weight;  /* [C] */
+  const float* __restrict__ bias;    /* [1] or NULL */
+  const float* __restrict__ base;    /* [R,R,R] dense, added to every hypothesis' grid, or NULL */
+  int C, S, R;
+  /* forward */
+  float* __restrict__ out;
+  long long out_stride;
+  int py, px; /* output pitches (elements) between consecutive y / x */
+  /* backward */
+  const float* __restrict__ g_main;
+  long long g_main_stride;
+  const float* __restrict__ n_overlap; /* [B] or NULL */
+  const float* __restrict__ upstream;  /* [B] or NULL */
+  const float* __restrict__ g_extra;   /* or NULL */
+  long long g_extra_stride;
+  float* __restrict__ g_x; /* [B, C, S, S, S] */
+  int z_offset;
+};
+
+/* ATen area_pixel_compute_source_index, align_corners = false, linear */
+__device__ __forceinline__ void tail_source(int o, float ratio, int S, int& i0, int& i1, float& l1) {
+  float src = ratio * ((float)o + 0.5f) - 0.5f;
+  src = src < 0.0f ? 0.0f : src;
+  i0 = (int)src;
+  i0 = i0 < S - 1 ? i0 : S - 1;
+  i1 = i0 + (i0 < S - 1 ? 1 : 0);
+  l1 = src - (float)i0;
+}
+
+/* One CTA per (output x-plane, hypothesis). */
+__global__ void __launch_bounds__(256)
+sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
+  extern __shared__ float tail_smem[];
+  const int S = P.S, R = P.R, C = P.C;
+  float* plane = tail_smem;             /* [S*S]  channel-contracted, x-collapsed source plane */
+  int* ti0 = (int*)(plane + S * S);     /* [R] */
+  int* ti1 = ti0 + R;                   /* [R] */
+  float* tl1 = (float*)(ti1 + R);       /* [R] */
+  const int b = blockIdx.y + P.z_offset, ox = blockIdx.x;
+  const float ratio = (float)S / (float)R;
+  for (int o = threadIdx.x; o < R; o += blockDim.x) {
+    int i0, i1;
+    float l1;
+    tail_source(o, ratio, S, i0, i1, l1);
+    ti0[o] = i0; ti1[o] = i1; tl1[o] = l1;
+  }
+  int x0, x1;
+  float lx1;
+  tail_source(ox, ratio, S, x0, x1, lx1);
+  const float lx0 = 1.0f - lx1;
+  float w[kTailMaxChannels];
+#pragma unroll
+  for (int c = 0; c < kTailMaxChannels; ++c) w[c] = c < C ? __ldg(P.weight + c) : 0.0f;
+  const size_t S2 = (size_t)S * S, S3 = S2 * S;
+  const float* __restrict__ xb = P.x + (size_t)b * C * S3;
+  for (int i = threadIdx.x; i < (int)S2; i += blockDim.x) {
+    float v0 = 0.0f, v1 = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kTailMaxChannels; ++c) {
+      if (c < C) {
+        v0 += w[c] * __ldg(xb + c * S3 + x0 * S2 + i);
+        v1 += w[c] * __ldg(xb + c * S3 + x1 * S2 + i);
+      }
+    }
+    plane[i] = lx0 * v0 + lx1 * v1;
+  }
+  __syncthreads();
+  const float bias = P.bias ? __ldg(P.bias) : 0.0f;
+  float* __restrict__ o = P.out + (size_t)b * P.out_stride + (size_t)ox * P.px;
+  const float* __restrict__ base = P.base ? P.base + (size_t)ox * R * R : nullptr;
+  for (int j = threadIdx.x; j < R * R; j += blockDim.x) {
+    const int oy = j / R, oz = j - oy * R;
+    const int y0 = ti0[oy], y1 = ti1[oy], z0 = ti0[oz], z1 = ti1[oz];
+    const float ly1 = tl1[oy], lz1 = tl1[oz];
+    const float ly0 = 1.0f - ly1, lz0 = 1.0f - lz1;
+    const float a = lz0 * plane[y0 * S + z0] + lz1 * plane[y0 * S + z1];
+    const float c = lz0 * plane[y1 * S + z0] + lz1 * plane[y1 * S + z1];
+    float v = (ly0 * a + ly1 * c) + bias;
+    if (base) v += __ldg(base + j);
+    o[oy * P.py + oz] = v;
+  }
+}
+
+/* weight of output index o on source index s along one axis */
+__device__ __forceinline__ float tail_weight(const int* ti0, const int* ti1, const float* tl1, int o,
+                                             int s) {
+  const float l1 = tl1[o];
+  return (ti0[o] == s ? 1.0f - l1 : 0.0f) + (ti1[o] == s ? l1 : 0.0f);
+}
+
+/* One CTA per (source x-plane, hypothesis). */
+__global__ void __launch_bounds__(256)
+sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
+  extern __shared__ float tail_smem[];
+  const int S = P.S, R = P.R, C = P.C;
+  float* Pl = tail_smem;              /* [R][R]  x-collapsed gradient plane */
+  float* Q = Pl + R * R;              /* [R][S]  ... z-collapsed */
+  int* ti0 = (int*)(Q + R * S);       /* [R] */
+  int* ti1 = ti0 + R;
+  float* tl1 = (float*)(ti1 + R);
+  int* lo = (int*)(tl1 + R);          /* [S] first / last output index touching source s */
+  int* hi = lo + S;
+  const int b = blockIdx.y + P.z_offset, sx = blockIdx.x;
+  const float ratio = (float)S / (float)R;
+  for (int o = threadIdx.x; o < R; o += blockDim.x) {
+    int i0, i1;
+    float l1;
+    tail_source(o, ratio, S, i0, i1, l1);
+    ti0[o] = i0; ti1[o] = i1; tl1[o] = l1;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    int l = R, h = -1;
+    for (int o = 0; o < R; ++o)
+      if (ti0[o] == s || ti1[o] == s) {
+        l = o < l ? o : l;
+        h = o;
+      }
+    lo[s] = l;
+    hi[s] = h;
+  }
+  __syncthreads();
+
+  float coef = 1.0f;
+  if (P.n_overlap) {
+    const float n = __ldg(P.n_overlap + b);
+    coef = n > 0.0f ? (P.upstream ? __ldg(P.upstream + b) : 1.0f) / n : 0.0f;
+  } else if (P.upstream) {
+    coef = __ldg(P.upstream + b);
+  }
+  const size_t R2 = (size_t)R * R;
+  const float* __restrict__ ga = P.g_main + (size_t)b * P.g_main_stride;
+  const float* __restrict__ ge = P.g_extra ? P.g_extra + (size_t)b * P.g_extra_stride : nullptr;
+  const int xlo = lo[sx], xhi = hi[sx];
+  /* 1. collapse x:  Pl[oy][oz] = sum_ox W(ox, sx) g[ox][oy][oz] */
+  for (int j = threadIdx.x; j < (int)R2; j += blockDim.x) {
+    float acc = 0.0f;
+    for (int ox = xlo; ox <= xhi; ++ox) {
+      const float wgt = tail_weight(ti0, ti1, tl1, ox, sx);
+      float g = coef != 0.0f ? coef * __ldg(ga + ox * R2 + j) : 0.0f;
+      if (ge) g += __ldg(ge + ox * R2 + j);
+      acc += wgt * g;
+    }
+    Pl[j] = acc;
+  }
+  __syncthreads();
+  /* 2. collapse z:  Q[oy][sz] = sum_oz W(oz, sz) Pl[oy][oz] */
+  for (int j = threadIdx.x; j < R * S; j += blockDim.x) {
+    const int oy = j / S, sz = j - oy * S;
+    float acc = 0.0f;
+    for (int oz = lo[sz]; oz <= hi[sz]; ++oz) acc += tail_weight(ti0, ti1, tl1, oz, sz) * Pl[oy * R + oz];
+    Q[j] = acc;
+  }
+  __syncthreads();
+  /* 3. collapse y and fan out over the channels */
+  const size_t S2 = (size_t)S * S, S3 = S2 * S;
+  float* __restrict__ gx = P.g_x + (size_t)b * C * S3 + (size_t)sx * S2;
+  for (int j = threadIdx.x; j < (int)S2; j += blockDim.x) {
+    const int sy = j / S, sz = j - sy * S;
+    float acc = 0.0f;
+    for (int oy = lo[sy]; oy <= hi[sy]; ++oy) acc += tail_weight(ti0, ti1, tl1, oy, sy) * Q[oy * S + sz];
+    for (int c = 0; c < C; ++c) gx[c * S3 + j] = __ldg(P.weight + c) * acc;
+  }
+}
+
+size_t tail_forward_smem(int S, int R) { return sizeof(float) * ((size_t)S * S + 3 * (size_t)R); }
+size_t tail_backward_smem(int S, int R) {
+  return sizeof(float) * ((size_t)R * R + (size_t)R * S + 3 * (size_t)R + 2 * (size_t)S);
+}
+
+int tail_check(int C, int S, int R, int batch) {
+  if (C < 1 || C > kTailMaxChannels) return fail(SDFR_E_SHAPE, "decoder tail: channels must be in [1, 16]");
+  if (S < 1 || S > kTailMaxSize || R < 2 || R > kTailMaxSize)
+    return fail(SDFR_E_SHAPE, "decoder tail: in_size must be in [1, 128] and resolution in [2, 128]");
+  if (batch < 0) return fail(SDFR_E_SHAPE, "negative batch");
+  return 0;
+}
+
+int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
+  const size_t smem = tail_forward_smem(P.S, P.R);
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_forward_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "decoder tail forward: shared memory opt-in failed");
+  }
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    P.z_offset = z0;
+    const dim3 grid(P.R, batch - z0 < 65535 ? batch - z0 : 65535);
+    sdfr_decoder_tail_forward_kernel<<<grid, 256, smem, s>>>(P);
+  }
+  return check_launch("sdfr_decoder_tail_forward_kernel");
+}
+
+int launch_tail_backward(TailParams P, int batch, cudaStream_t s) {
+  const size_t smem = tail_backward_smem(P.S, P.R);
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_backward_kernel,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "decoder tail backward: shared memory opt-in failed");
+  }
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    P.z_offset = z0;
+    const dim3 grid(P.S, batch - z0 < 65535 ? batch - z0 : 65535);
+    sdfr_decoder_tail_backward_kernel<<<grid, 256, smem, s>>>(P);
+  }
+  return check_launch("sdfr_decoder_tail_backward_kernel");
+}
+
+#endif /* SDFR_DECODER_CUH_ */

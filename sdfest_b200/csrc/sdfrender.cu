@@ -1035,6 +1035,7 @@ BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_
 }
 
 #include "sdfr_points.cuh"
+#include "sdfr_decoder.cuh"
 
 }  // namespace
 
@@ -1328,6 +1329,46 @@ int sdfr_point_loss_backward(const float* points, long long points_stride, int n
   P.grad_position = gp; P.grad_orientation = gq; P.grad_scale = gscale;
   P.flags = flags;
   return launch_point_loss<true>(P, batch, s);
+}
+
+int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const float* weight,
+                              const float* bias, const float* base, int batch, int R, float* sdf,
+                              long long sdf_stride, int layout, void* stream) {
+  if (int rc = tail_check(channels, in_size, R, batch)) return rc;
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED)
+    return fail(SDFR_E_FLAGS, "unknown sdf_layout");
+  if (batch == 0) return 0;
+  if (!x || !weight || !sdf) return fail(SDFR_E_NULL, "decoder tail: x, weight or sdf is NULL");
+  const Grid G = make_grid(R, layout);
+  if (sdf_stride < (long long)R * G.px)
+    return fail(SDFR_E_SHAPE, "decoder tail: sdf_stride smaller than one grid in this layout");
+  TailParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = x; P.weight = weight; P.bias = bias; P.base = base;
+  P.C = channels; P.S = in_size; P.R = R;
+  P.out = sdf; P.out_stride = sdf_stride; P.py = G.py; P.px = G.px;
+  return launch_tail_forward(P, batch, (cudaStream_t)stream);
+}
+
+int sdfr_decoder_tail_backward(const float* grad_sdf, long long grad_sdf_stride,
+                               const float* n_overlap, const float* upstream,
+                               const float* grad_sdf_extra, long long extra_stride,
+                               const float* weight, int channels, int in_size, int batch, int R,
+                               float* grad_x, void* stream) {
+  if (int rc = tail_check(channels, in_size, R, batch)) return rc;
+  if (grad_sdf_stride < 0 || extra_stride < 0) return fail(SDFR_E_SHAPE, "negative gradient stride");
+  if (batch == 0) return 0;
+  if (!grad_sdf || !weight || !grad_x)
+    return fail(SDFR_E_NULL, "decoder tail: grad_sdf, weight or grad_x is NULL");
+  TailParams P;
+  memset(&P, 0, sizeof(P));
+  P.weight = weight;
+  P.C = channels; P.S = in_size; P.R = R;
+  P.g_main = grad_sdf; P.g_main_stride = grad_sdf_stride;
+  P.n_overlap = n_overlap; P.upstream = upstream;
+  P.g_extra = grad_sdf_extra; P.g_extra_stride = extra_stride;
+  P.g_x = grad_x;
+  return launch_tail_backward(P, batch, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -2,4 +2,4 @@
 from .hypotheses import HypothesisOptimizer, gather_losses, global_best, shard_range  # noqa: F401
 from .losses import depth_to_pointcloud, pc_loss, point_loss  # noqa: F401
 from .streaming import StreamedRenderCompare  # noqa: F401
-from .decoder import SDFDecoder, SurfaceDecoder  # noqa: F401
+from .decoder import FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail  # noqa: F401

@@ -17,6 +17,8 @@ from typing import Optional, Sequence
 import torch
 from torch import nn
 
+from .. import _lib
+
 MUG_FC = (20, 50, 8192)
 MUG_CONV = ((8, 16, 16, 3, True), (16, 16, 8, 3, True), (32, 8, 4, 3, True), (64, 4, 1, 1, False))
 
@@ -64,3 +66,125 @@ class SurfaceDecoder(nn.Module):
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         d = self.decoder(z)
         return self.base[None, None] + self.gain * (d - d.mean(dim=(2, 3, 4), keepdim=True))
+
+
+# --------------------------------------------------------------------------------------------
+# CUDA path: the decoder tail (final trilinear interpolation + 1x1x1 convolution) as one kernel
+# --------------------------------------------------------------------------------------------
+class _DecoderTail(torch.autograd.Function):
+    """``conv1x1(interpolate(x, (R,R,R), "trilinear", align_corners=False))[:, 0]`` through
+    ``sdfr_decoder_tail_forward`` / ``_backward`` (reference sdf_vae.py:235-247)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, resolution):
+        from ..differentiable_renderer.sdf_renderer import _check_input, _on_device_of, _stream
+
+        _check_input(x, "x")
+        _check_input(weight, "weight")
+        if x.dim() != 5 or not (x.shape[2] == x.shape[3] == x.shape[4]):
+            raise RuntimeError(f"x must have shape (B,C,S,S,S), got {tuple(x.shape)}")
+        B, C, S = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        if weight.numel() != C:
+            raise RuntimeError(f"weight must have {C} elements, got {weight.numel()}")
+        if bias is not None:
+            _check_input(bias, "bias", 1)
+        if weight.requires_grad or (bias is not None and bias.requires_grad):
+            raise RuntimeError("the fused decoder tail is for a frozen decoder (no weight/bias "
+                               "gradients; the estimation loop never trains it, simple_setup.py:65)")
+        R = int(resolution)
+        with _on_device_of(x):
+            out = torch.empty((B, R, R, R), dtype=torch.float32, device=x.device)
+            _lib.check(_lib.lib().sdfr_decoder_tail_forward(
+                x.data_ptr(), C, S, weight.data_ptr(), None if bias is None else bias.data_ptr(),
+                None, B, R, out.data_ptr(), R ** 3, _lib.LAYOUT_DENSE, _stream()),
+                "sdfr_decoder_tail_forward")
+        ctx.save_for_backward(weight)
+        ctx.meta = (B, C, S, R)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        from ..differentiable_renderer.sdf_renderer import _on_device_of, _stream
+
+        (weight,) = ctx.saved_tensors
+        B, C, S, R = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None
+        grad_out = grad_out.contiguous()
+        with _on_device_of(grad_out):
+            g_x = torch.empty((B, C, S, S, S), dtype=torch.float32, device=grad_out.device)
+            _lib.check(_lib.lib().sdfr_decoder_tail_backward(
+                grad_out.data_ptr(), R ** 3, None, None, None, 0, weight.data_ptr(), C, S, B, R,
+                g_x.data_ptr(), _stream()), "sdfr_decoder_tail_backward")
+        return g_x, None, None, None
+
+
+def decoder_tail(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+                 resolution: int) -> torch.Tensor:
+    """Fused last stage of the reference decoder: x (B,C,S,S,S) -> SDF grids (B,R,R,R).
+
+    Equals ``F.conv3d(F.interpolate(x, (R,R,R), mode="trilinear", align_corners=False),
+    weight.view(1,C,1,1,1), bias)[:, 0]`` to fp32 rounding, without the C x R^3 intermediate.
+    CUDA only; differentiable w.r.t. ``x``.
+    """
+    return _DecoderTail.apply(x.contiguous(), weight.reshape(-1).contiguous(), bias, resolution)
+
+
+def _decoder_parts(decoder: nn.Module):
+    """(fc layers, conv layers, conv infos as (in_size, relu, kernel, out_channels), volume size)
+    of either this package's ``SDFDecoder`` or the reference's (sdfest/vae/sdf_vae.py:170-259:
+    ``_fc_layers``, ``_conv_layers``, ``_conv_info`` dicts, ``_volume_size``)."""
+    if hasattr(decoder, "_conv_layers"):  # reference class
+        info = [(d["in_size"], bool(d["relu"])) for d in decoder._conv_info]
+        return list(decoder._fc_layers), list(decoder._conv_layers), info, int(decoder._volume_size)
+    info = [(size, bool(relu)) for size, _, _, _, relu in decoder.conv_info]
+    return list(decoder.fc), list(decoder.conv), info, int(decoder.volume_size)
+
+
+class FusedTailDecoder(nn.Module):
+    """A frozen SDF decoder whose last stage runs as the fused CUDA tail.
+
+    Wraps this package's ``SDFDecoder`` or the reference's ``sdfest.vae.sdf_vae.SDFDecoder``
+    (same weights, no copy).  Everything up to the last convolution stage stays on
+    PyTorch/cuDNN; the last stage -- interpolate to the grid resolution + 1x1x1 convolution to one
+    channel, 4.8 of the 6.5 ms the whole decoder forward+backward takes for 64 hypotheses on a
+    B200 (profiles/r01g_decoder_ops.txt) -- is ``decoder_tail``.  Returns (B,1,R,R,R) like the
+    reference.  Raises at construction when the architecture does not end that way.
+    """
+
+    def __init__(self, decoder: nn.Module):
+        super().__init__()
+        self.decoder = decoder
+        fc, conv, info, volume = _decoder_parts(decoder)
+        last = conv[-1]
+        if (tuple(last.kernel_size) != (1, 1, 1) or last.out_channels != 1 or info[-1][1]
+                or info[-1][0] != volume or tuple(last.stride) != (1, 1, 1)):
+            raise ValueError("FusedTailDecoder needs a last stage of interpolate-to-volume-size + "
+                             "Conv3d(C, 1, kernel_size=1) without ReLU")
+        for p in decoder.parameters():
+            p.requires_grad_(False)
+        self._fc, self._conv, self._info, self.volume_size = fc, conv, info, volume
+
+    def trunk(self, z: torch.Tensor) -> torch.Tensor:
+        """Everything before the last stage's interpolation: (B,L) -> (B,C,S,S,S)."""
+        out = z
+        for layer in self._fc:
+            out = torch.relu(layer(out))
+        c0, s0 = self._conv[0].in_channels, self._info[0][0]
+        out = out.view(-1, c0, s0, s0, s0)
+        for (size, relu), layer in zip(self._info[:-1], self._conv[:-1]):
+            if out.shape[2] != size:
+                out = nn.functional.interpolate(out, size=(size,) * 3, mode="trilinear",
+                                                align_corners=False)
+            out = layer(out)
+            if relu:
+                out = torch.relu(out)
+        return out
+
+    def tail_parameters(self):
+        last = self._conv[-1]
+        return last.weight.reshape(-1), last.bias
+
+    def forward(self, z: torch.Tensor) -> torch.Tensor:
+        w, b = self.tail_parameters()
+        return decoder_tail(self.trunk(z), w, b, self.volume_size)[:, None]
