@@ -31,6 +31,8 @@ for v in variants:
     if v == "fused_tail":
         d = FusedTailDecoder(d)
     dec = SurfaceDecoder(syn.sdf_mug(R, dev), decoder=d).to(dev).eval()
+    if v == "fused_iteration":
+        dec = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
     for p in dec.parameters():
         p.requires_grad_(False)
     opt = HypothesisOptimizer(cam, THR, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],

@@ -3,3 +3,4 @@ from .hypotheses import HypothesisOptimizer, gather_losses, global_best, shard_r
 from .losses import depth_to_pointcloud, pc_loss, point_loss  # noqa: F401
 from .streaming import StreamedRenderCompare  # noqa: F401
 from .decoder import FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail  # noqa: F401
+from .fused import decode_render_compare  # noqa: F401

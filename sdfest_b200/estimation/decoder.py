@@ -76,7 +76,7 @@ class _DecoderTail(torch.autograd.Function):
     ``sdfr_decoder_tail_forward`` / ``_backward`` (reference sdf_vae.py:235-247)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, resolution):
+    def forward(ctx, x, weight, bias, resolution, base=None):
         from ..differentiable_renderer.sdf_renderer import _check_input, _on_device_of, _stream
 
         _check_input(x, "x")
@@ -92,11 +92,13 @@ class _DecoderTail(torch.autograd.Function):
             raise RuntimeError("the fused decoder tail is for a frozen decoder (no weight/bias "
                                "gradients; the estimation loop never trains it, simple_setup.py:65)")
         R = int(resolution)
+        if base is not None:
+            _check_input(base, "base", R ** 3)
         with _on_device_of(x):
             out = torch.empty((B, R, R, R), dtype=torch.float32, device=x.device)
             _lib.check(_lib.lib().sdfr_decoder_tail_forward(
                 x.data_ptr(), C, S, weight.data_ptr(), None if bias is None else bias.data_ptr(),
-                None, B, R, out.data_ptr(), R ** 3, _lib.LAYOUT_DENSE, _stream()),
+                None if base is None else base.data_ptr(), B, R, out.data_ptr(), R ** 3, _lib.LAYOUT_DENSE, _stream()),
                 "sdfr_decoder_tail_forward")
         ctx.save_for_backward(weight)
         ctx.meta = (B, C, S, R)
@@ -109,25 +111,27 @@ class _DecoderTail(torch.autograd.Function):
         (weight,) = ctx.saved_tensors
         B, C, S, R = ctx.meta
         if not ctx.needs_input_grad[0]:
-            return None, None, None, None
+            return None, None, None, None, None
         grad_out = grad_out.contiguous()
         with _on_device_of(grad_out):
             g_x = torch.empty((B, C, S, S, S), dtype=torch.float32, device=grad_out.device)
             _lib.check(_lib.lib().sdfr_decoder_tail_backward(
                 grad_out.data_ptr(), R ** 3, None, None, None, 0, weight.data_ptr(), C, S, B, R,
                 g_x.data_ptr(), _stream()), "sdfr_decoder_tail_backward")
-        return g_x, None, None, None
+        return g_x, None, None, None, None
 
 
 def decoder_tail(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
-                 resolution: int) -> torch.Tensor:
+                 resolution: int, base: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Fused last stage of the reference decoder: x (B,C,S,S,S) -> SDF grids (B,R,R,R).
 
     Equals ``F.conv3d(F.interpolate(x, (R,R,R), mode="trilinear", align_corners=False),
-    weight.view(1,C,1,1,1), bias)[:, 0]`` to fp32 rounding, without the C x R^3 intermediate.
+    weight.view(1,C,1,1,1), bias)[:, 0]`` to fp32 rounding, without the C x R^3 intermediate;
+    ``base`` (R,R,R), if given, is added to every grid (residual decoding around a fixed shape).
     CUDA only; differentiable w.r.t. ``x``.
     """
-    return _DecoderTail.apply(x.contiguous(), weight.reshape(-1).contiguous(), bias, resolution)
+    return _DecoderTail.apply(x.contiguous(), weight.reshape(-1).contiguous(), bias, resolution,
+                              None if base is None else base.contiguous())
 
 
 def _decoder_parts(decoder: nn.Module):
@@ -150,11 +154,19 @@ class FusedTailDecoder(nn.Module):
     channel, 4.8 of the 6.5 ms the whole decoder forward+backward takes for 64 hypotheses on a
     B200 (profiles/r01g_decoder_ops.txt) -- is ``decoder_tail``.  Returns (B,1,R,R,R) like the
     reference.  Raises at construction when the architecture does not end that way.
+
+    ``base`` (R,R,R): optional fixed grid added to the decoded one (a randomly initialised decoder
+    emits a near-constant field without a surface; the benchmark decodes residuals around
+    an analytic shape).  ``channels_last=True`` stores the trunk's convolution weights in
+    ``torch.channels_last_3d``, which makes cuDNN pick its NDHWC tensor-core kernels (2.6 instead of
+    4.7 ms for the trunk forward+backward of 64 hypotheses on a B200).
     """
 
-    def __init__(self, decoder: nn.Module):
+    def __init__(self, decoder: nn.Module, base: Optional[torch.Tensor] = None,
+                 channels_last: bool = True):
         super().__init__()
         self.decoder = decoder
+        self.register_buffer("base", None if base is None else base.detach().clone().contiguous())
         fc, conv, info, volume = _decoder_parts(decoder)
         last = conv[-1]
         if (tuple(last.kernel_size) != (1, 1, 1) or last.out_channels != 1 or info[-1][1]
@@ -164,6 +176,11 @@ class FusedTailDecoder(nn.Module):
         for p in decoder.parameters():
             p.requires_grad_(False)
         self._fc, self._conv, self._info, self.volume_size = fc, conv, info, volume
+        if base is not None and tuple(base.shape) != (volume,) * 3:
+            raise ValueError(f"base must have shape {(volume,) * 3}, got {tuple(base.shape)}")
+        if channels_last:
+            for layer in conv[:-1]:
+                layer.to(memory_format=torch.channels_last_3d)
 
     def trunk(self, z: torch.Tensor) -> torch.Tensor:
         """Everything before the last stage's interpolation: (B,L) -> (B,C,S,S,S)."""
@@ -187,4 +204,4 @@ class FusedTailDecoder(nn.Module):
 
     def forward(self, z: torch.Tensor) -> torch.Tensor:
         w, b = self.tail_parameters()
-        return decoder_tail(self.trunk(z), w, b, self.volume_size)[:, None]
+        return decoder_tail(self.trunk(z), w, b, self.volume_size, self.base)[:, None]

@@ -16,6 +16,8 @@ import torch.distributed as dist
 
 from ..differentiable_renderer import Camera, render_and_compare
 from . import losses
+from .decoder import FusedTailDecoder
+from .fused import decode_render_compare
 
 
 def shard_range(n_total: int, rank: int, world: int):
@@ -129,9 +131,29 @@ class HypothesisOptimizer:
             return self.last_losses
         return self._eager_step()
 
+    def _fused_loss(self, q: torch.Tensor) -> torch.Tensor:
+        """Decoder tail, render-and-compare and point loss chained through the C ABI
+        (estimation/fused.py): no dense grid, no separate layout / scaling / add passes."""
+        dec = self.decoder
+        w, b = dec.tail_parameters()
+        loss, _, _, _ = decode_render_compare(
+            dec.trunk(self.latent), w, b, self.position, q.contiguous(), self.scale,
+            self.depth_obs, self.points if self.pc_weight and self.points.shape[0] > 0 else None,
+            dec.volume_size, self.threshold, self.camera, base=dec.base,
+            depth_weight=self.depth_weight, pc_weight=self.pc_weight)
+        return loss
+
     def _eager_step(self) -> torch.Tensor:
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+        if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda:
+            loss = self._fused_loss(q)
+            loss.sum().backward()
+            self.optimizer.step()
+            with torch.no_grad():
+                self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+            self.last_losses = loss.detach()
+            return self.last_losses
         grids = self._grids()
         loss_depth, _, _ = render_and_compare(grids, self.position, q.contiguous(),
                                               (1.0 / self.scale).contiguous(), self.depth_obs,

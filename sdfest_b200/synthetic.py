@@ -131,3 +131,25 @@ def hypothesis_grids(shape_params, R: int, device, categories=("mug",)) -> torch
     for i, p in enumerate(params):
         out[i] = category_grid(categories[i % len(categories)], R, "cpu", p)
     return out
+
+
+def residual_decoder(R: int, device, base: torch.Tensor, seed: int = 0, gain: float = 1.0):
+    """A decoder of the reference's architecture that always has a surface: a randomly initialised
+    ``SDFDecoder`` (frozen) decoding RESIDUALS around the analytic grid ``base`` through the fused
+    CUDA tail (``estimation.FusedTailDecoder``).  The last convolution is rescaled by ``gain`` and its
+    bias re-centred so that the residual of latent 0 has zero mean -- a random-init decoder emits a
+    near-constant field (0.37 everywhere for seed 0) that would otherwise push the
+    surface out of the grid."""
+    from .estimation.decoder import FusedTailDecoder, SDFDecoder
+
+    gen_state = torch.random.get_rng_state()
+    torch.manual_seed(seed)
+    dec = SDFDecoder(R).to(device).eval()
+    torch.random.set_rng_state(gen_state)
+    with torch.no_grad():
+        last = dec.conv[-1]
+        last.weight.mul_(gain)
+        last.bias.mul_(gain)
+        mean0 = dec(torch.zeros(1, dec.fc[0].in_features, device=device)).mean()
+        last.bias.sub_(mean0)
+    return FusedTailDecoder(dec, base=base.to(device)).to(device).eval()

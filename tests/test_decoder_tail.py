@@ -223,3 +223,84 @@ def test_fused_tail_decoder_matches_plain_decoder(cuda_device):
     a.backward(g)
     b.backward(g)
     assert rel(z1.grad.cpu().numpy(), z2.grad.cpu().numpy().astype(np.float64)) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_points", [True, False])
+def test_decode_render_compare_equals_the_composition_of_its_parts(cuda_device, with_points):
+    """estimation.decode_render_compare (tail -> skewed grids -> fused compare -> point loss, one
+    chain of C-ABI kernels) against the same loss assembled from the separate autograd operators."""
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, render_and_compare, render_depth_batched
+    from sdfest_b200.estimation import decode_render_compare, losses
+
+    dev = cuda_device
+    torch.manual_seed(2)
+    B, R, W, H, thr = 3, 64, 160, 120, 0.005
+    cam = Camera(W, H, 80.0, 80.0, 80.0, 60.0, pixel_center=0.5)
+    hyp = syn.make_hypotheses(B, seed=3, device=dev)
+    base = syn.sdf_mug(R, dev)
+    x0 = 0.05 * torch.randn(B, 4, 30, 30, 30, device=dev)
+    w = torch.randn(4, device=dev)
+    bias = torch.tensor([0.01], device=dev)
+    obs = render_depth_batched(base, hyp["position"][:1], hyp["orientation"][:1], hyp["inv_scale"][:1],
+                               thr, cam)[0].contiguous()
+    pts = losses.depth_to_pointcloud(obs, cam).contiguous() if with_points else None
+
+    def leaves():
+        return (x0.clone().requires_grad_(True), hyp["position"].clone().requires_grad_(True),
+                hyp["orientation"].clone().requires_grad_(True),
+                (1.0 / hyp["inv_scale"]).clone().requires_grad_(True))
+
+    x, p, q, s = leaves()
+    loss, depth, n, loss_d = decode_render_compare(x, w, bias, p, q, s, obs, pts, R, thr, cam, base=base,
+                                                   depth_weight=1.0, pc_weight=3.0)
+    up = torch.tensor([1.0, 0.5, 2.0], device=dev)
+    (loss * up).sum().backward()
+
+    x2, p2, q2, s2 = leaves()
+    grids = decoder_tail(x2, w, bias, R, base)
+    ld, depth2, n2 = render_and_compare(grids, p2, q2, (1.0 / s2).contiguous(), obs, thr, cam)
+    ref = torch.nan_to_num(ld, nan=0.0)
+    if with_points:
+        ref = ref + 3.0 * losses.point_loss(pts, p2, q2, s2, grids)
+    (ref * up).sum().backward()
+
+    assert torch.equal(depth, depth2) and torch.equal(n, n2) and int(n.min()) > 0
+    assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-7) and torch.allclose(loss_d, ld, rtol=1e-5)
+    for got, want in ((x.grad, x2.grad), (p.grad, p2.grad), (q.grad, q2.grad), (s.grad, s2.grad)):
+        assert rel(got.cpu().numpy(), want.cpu().numpy().astype(np.float64)) < 1e-3
+    # evaluation only (no gradient requested) takes the compare-forward path
+    with torch.no_grad():
+        l3, d3, _, _ = decode_render_compare(x.detach(), w, bias, p.detach(), q.detach(), s.detach(), obs,
+                                             pts, R, thr, cam, base=base)
+    assert torch.equal(d3, depth) and torch.allclose(l3, loss.detach(), rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.gpu
+def test_optimizer_uses_the_fused_chain_and_descends(cuda_device):
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, render_depth_batched
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    dev = cuda_device
+    torch.manual_seed(0)
+    B, R, W, H, thr = 4, 64, 160, 120, 0.005
+    cam = Camera(W, H, 80.0, 80.0, 80.0, 60.0, pixel_center=0.5)
+    hyp = syn.make_hypotheses(B, seed=5, device=dev)
+    base = syn.sdf_mug(R, dev)
+    obs = render_depth_batched(base, hyp["position"][:1], hyp["orientation"][:1], hyp["inv_scale"][:1],
+                               thr, cam)[0].contiguous()
+    dec = syn.residual_decoder(R, dev, base)
+    opt = HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                              latent=torch.zeros(B, 8, device=dev), decoder=dec)
+    first = opt.step().clone()
+    for _ in range(25):
+        last = opt.step()
+    assert torch.isfinite(last).all() and float(last.mean()) < float(first.mean())
+    assert float(opt.latent.abs().max()) > 0  # the latent moved: gradients reached the trunk
+    opt2 = HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                               latent=torch.zeros(B, 8, device=dev), decoder=dec)
+    opt2.capture()
+    l2 = opt2.step()
+    assert torch.isfinite(l2).all()
