@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 4
+#define SDFR_ABI_VERSION 5
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -252,6 +252,33 @@ int sdfr_decoder_tail_backward(const float* grad_sdf, long long grad_sdf_stride,
                                const float* grad_sdf_extra, long long extra_stride,
                                const float* weight, int channels, int in_size, int batch,
                                int resolution, float* grad_x, void* stream);
+
+/*
+ * Decoder trunk stages (sdfest/vae/sdf_vae.py:225-247: per stage `interpolate(..., "trilinear",
+ * align_corners=False)` to the stage's in_size, Conv3d, optional ReLU).  Every decoder the reference
+ * ships (vae/configs/*.yaml, initialization/configs/vae_models/*.yaml) uses 3x3x3 "valid"
+ * convolutions between 4..32 channels.  All tensors contiguous NCDHW fp32.
+ *
+ * sdfr_upsample3d_forward:  y[n] = trilinear resize of x[n] (in_size^3 -> out_size^3) for n_volumes
+ *   volumes (batch*channels); ATen's align_corners = false indices / weights.  _backward: its adjoint
+ *   (grad_x written, not accumulated).  Sizes <= 128.
+ * sdfr_conv3d_forward:  y [batch, out_channels, (in_size-2)^3] = conv3d(x, weight [Co,Ci,3,3,3]) + bias
+ *   (NULL = none), ReLU if `relu`.  out_channels in {4, 8, 16, 32}.
+ * sdfr_conv3d_backward_data:  grad_x [batch, in_channels, in_size^3] = transposed convolution of
+ *   grad_y * (y > 0)  (y = the forward's output, the ReLU mask; NULL = no ReLU) with weight;
+ *   in_channels in {4, 8, 16, 32}.  The decoder is frozen in the estimation loop
+ *   (simple_setup.py:65): there is no weight gradient.
+ */
+int sdfr_upsample3d_forward(const float* x, int n_volumes, int in_size, int out_size, float* y,
+                            void* stream);
+int sdfr_upsample3d_backward(const float* grad_y, int n_volumes, int in_size, int out_size,
+                             float* grad_x, void* stream);
+int sdfr_conv3d_forward(const float* x, int batch, int in_channels, int in_size, const float* weight,
+                        const float* bias, int out_channels, int kernel_size, int relu, float* y,
+                        void* stream);
+int sdfr_conv3d_backward_data(const float* grad_y, const float* y, int batch, int in_channels,
+                              int in_size, const float* weight, int out_channels, int kernel_size,
+                              float* grad_x, void* stream);
 
 #ifdef __cplusplus
 }

@@ -62,3 +62,76 @@ def tail_backward(g, weight, S: int, coef=None, g_extra=None) -> np.ndarray:
     W = axis_weights(S, R)
     gv = np.einsum("xi,yj,zk,bxyz->bijk", W, W, W, g, optimize=True)
     return np.einsum("c,bijk->bcijk", np.asarray(weight, dtype=np.float64), gv).astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------
+# trunk stages (sdfest/vae/sdf_vae.py:225-247): interpolate -> Conv3d(k=3, valid) -> optional ReLU
+# ---------------------------------------------------------------------------------------------
+def upsample(x, out_size: int) -> np.ndarray:
+    """x (..., S, S, S) -> (..., U, U, U) float64: ATen trilinear, align_corners = False."""
+    x = np.asarray(x, dtype=np.float64)
+    W = axis_weights(x.shape[-1], out_size)
+    return np.einsum("xi,yj,zk,...ijk->...xyz", W, W, W, x, optimize=True)
+
+
+def upsample_backward(g, in_size: int) -> np.ndarray:
+    g = np.asarray(g, dtype=np.float64)
+    W = axis_weights(in_size, g.shape[-1])
+    return np.einsum("xi,yj,zk,...xyz->...ijk", W, W, W, g, optimize=True)
+
+
+def conv3d(x, weight, bias=None, relu=False) -> np.ndarray:
+    """'valid' cross-correlation as torch.nn.Conv3d: x (B,Ci,U,U,U), weight (Co,Ci,k,k,k)."""
+    x = np.asarray(x, dtype=np.float64)
+    w = np.asarray(weight, dtype=np.float64)
+    k = w.shape[-1]
+    O = x.shape[-1] - k + 1
+    out = np.zeros((x.shape[0], w.shape[0], O, O, O))
+    for dx in range(k):
+        for dy in range(k):
+            for dz in range(k):
+                out += np.einsum("oc,bcxyz->boxyz", w[:, :, dx, dy, dz],
+                                 x[:, :, dx:dx + O, dy:dy + O, dz:dz + O])
+    if bias is not None:
+        out += np.asarray(bias, dtype=np.float64)[None, :, None, None, None]
+    return np.maximum(out, 0.0) if relu else out
+
+
+def conv3d_backward_data(g, y, weight) -> np.ndarray:
+    """Gradient w.r.t. the input of conv3d(+ReLU): g, y (B,Co,O,O,O); y = forward output (ReLU mask,
+    None = no ReLU)."""
+    g = np.asarray(g, dtype=np.float64)
+    if y is not None:
+        g = g * (np.asarray(y) > 0)
+    w = np.asarray(weight, dtype=np.float64)
+    k = w.shape[-1]
+    O = g.shape[-1]
+    U = O + k - 1
+    gx = np.zeros((g.shape[0], w.shape[1], U, U, U))
+    for dx in range(k):
+        for dy in range(k):
+            for dz in range(k):
+                gx[:, :, dx:dx + O, dy:dy + O, dz:dz + O] += np.einsum("oc,boxyz->bcxyz", w[:, :, dx, dy, dz], g)
+    return gx
+
+
+def decoder_forward(z, fc, conv, volume_size: int) -> np.ndarray:
+    """The whole reference decoder (sdf_vae.py:217-259) in float64.  fc: [(W (out,in), b)], conv:
+    [(in_size, W (Co,Ci,k,k,k), b, relu)]."""
+    out = np.asarray(z, dtype=np.float64)
+    for W, b in fc:
+        out = np.maximum(out @ np.asarray(W, dtype=np.float64).T + np.asarray(b, dtype=np.float64), 0.0)
+    s0, c0 = conv[0][0], conv[0][1].shape[1]
+    out = out.reshape(-1, c0, s0, s0, s0)
+    for in_size, W, b, relu in conv:
+        if out.shape[2] != in_size:
+            out = upsample(out, in_size)
+        if W.shape[-1] == 1:
+            out = np.einsum("oc,bcxyz->boxyz", np.asarray(W, dtype=np.float64)[:, :, 0, 0, 0], out) \
+                + np.asarray(b, dtype=np.float64)[None, :, None, None, None]
+            out = np.maximum(out, 0.0) if relu else out
+        else:
+            out = conv3d(out, W, b, relu)
+    if out.shape[2] != volume_size:
+        out = upsample(out, volume_size)
+    return out

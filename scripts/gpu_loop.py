@@ -45,11 +45,13 @@ def make(decoder):
 
 torch.manual_seed(0)
 _plain = SDFDecoder(R)
-_fused = FusedTailDecoder(SDFDecoder(R))
+_fused = FusedTailDecoder(SDFDecoder(R), trunk="torch")
 _fused.decoder.load_state_dict(_plain.state_dict())
 for name, dec in (("pose_only", None),
                   ("pose_latent", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_plain).to(dev).eval()),
                   ("pose_latent_fused_tail", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_fused).to(dev).eval()),
+                  ("pose_latent_fused_iteration_torch_trunk",
+                   syn.residual_decoder(R, dev, syn.sdf_mug(R, dev), trunk="torch")),
                   ("pose_latent_fused_iteration", syn.residual_decoder(R, dev, syn.sdf_mug(R, dev)))):
     if dec is not None:
         for p in dec.parameters():

@@ -87,7 +87,8 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
   const float lx0 = 1.0f - lx1;
   float w[kTailMaxChannels];
 #pragma unroll
-  for (int c = 0; c < kTailMaxChannels; ++c) w[c] = c < C ? __ldg(P.weight + c) : 0.0f;
+  for (int c = 0; c < kTailMaxChannels; ++c)
+    w[c] = c < C ? (P.weight ? __ldg(P.weight + c) : 1.0f) : 0.0f; /* NULL weight: plain upsampling */
   const size_t S2 = (size_t)S * S, S3 = S2 * S;
   const float* __restrict__ xb = P.x + (size_t)b * C * S3;
   for (int i = threadIdx.x; i < (int)S2; i += blockDim.x) {
@@ -196,7 +197,7 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
     const int sy = j / S, sz = j - sy * S;
     float acc = 0.0f;
     for (int oy = lo[sy]; oy <= hi[sy]; ++oy) acc += tail_weight(ti0, ti1, tl1, oy, sy) * Q[oy * S + sz];
-    for (int c = 0; c < C; ++c) gx[c * S3 + j] = __ldg(P.weight + c) * acc;
+    for (int c = 0; c < C; ++c) gx[c * S3 + j] = (P.weight ? __ldg(P.weight + c) : 1.0f) * acc;
   }
 }
 
@@ -241,6 +242,162 @@ int launch_tail_backward(TailParams P, int batch, cudaStream_t s) {
     sdfr_decoder_tail_backward_kernel<<<grid, 256, smem, s>>>(P);
   }
   return check_launch("sdfr_decoder_tail_backward_kernel");
+}
+
+
+/* ------------------------------------------------------------------------------------------
+ * Decoder trunk stages (sdfest/vae/sdf_vae.py:225-247): per stage
+ *     interpolate(x -> in_size^3, trilinear, align_corners=False)      -> the tail kernels above with
+ *                                                                         weight = NULL (C = 1)
+ *     Conv3d(Ci -> Co, kernel_size=3), + bias, optional ReLU           -> sdfr_conv3_kernel
+ * and the data gradient of the convolution (the decoder is frozen: no weight gradients).
+ * Every shipped decoder (vae/configs/*.yaml, initialization/configs/vae_models/*.yaml) uses 3x3x3
+ * "valid" convolutions with 4..32 channels on 8^3..32^3 volumes: ~37 MFLOP-pairs per hypothesis, for
+ * which cuDNN picks kernels that take 1.5 ms per layer and direction at 64 hypotheses
+ * (profiles/r01g_decoder_ops.txt).  Direct fp32 convolution: a CTA owns a 4 x 8 x (8*ZR) tile of
+ * output positions for ALL output channels, input tile + weights staged in shared memory 4 input
+ * channels at a time, each thread accumulating CO x ZR outputs (a run of ZR consecutive z) in
+ * registers: per (ci, dx, dy) it reads ZR+2 inputs and 3*CO broadcast weights for 3*ZR*CO FFMAs.
+ * DGRAD = true computes the transposed convolution with the same code: input = grad_out (times the
+ * ReLU mask y > 0) shifted by K-1 with zero padding, weights flipped and channel-transposed while
+ * they are staged.
+ * ---------------------------------------------------------------------------------------- */
+struct ConvParams {
+  const float* __restrict__ in;   /* fwd: x [B,CI,n_in^3];  dgrad: grad_y [B,CI,n_in^3] */
+  const float* __restrict__ mask; /* dgrad: y [B,CI,n_in^3] (ReLU mask y > 0) or NULL */
+  const float* __restrict__ w;    /* [Co_orig, Ci_orig, 27] as torch stores it */
+  const float* __restrict__ bias; /* fwd: [CO] or NULL */
+  float* __restrict__ out;        /* fwd: y [B,CO,n_out^3];  dgrad: grad_x [B,CO,n_out^3] */
+  int CI, n_in, n_out, relu;
+  int tiles_y, tiles_z;
+  int z_offset;
+};
+
+template <int CO, int ZR, bool DGRAD>
+__global__ void __launch_bounds__(256)
+sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
+  constexpr int K = 3, TX = 4, TY = 8, TZ = 8 * ZR, CC = 4;
+  constexpr int IX = TX + K - 1, IY = TY + K - 1, IZ = TZ + K - 1;
+  constexpr int PZ = ((IZ + 2) / 4) * 4 + 1; /* = 1 (mod 4): the 32 lanes of a warp hit 32 banks */
+  __shared__ float tile[CC][IX][IY][PZ];
+  __shared__ __align__(16) float ws[CC][K * K * K][CO];
+
+  const int b = blockIdx.y + P.z_offset;
+  int t = blockIdx.x;
+  const int tz = t % P.tiles_z; t /= P.tiles_z;
+  const int tyy = t % P.tiles_y;
+  const int txx = t / P.tiles_y;
+  const int X0 = txx * TX, Y0 = tyy * TY, Z0 = tz * TZ;
+  const int zr = threadIdx.x & 7, ly = (threadIdx.x >> 3) & 7, lx = threadIdx.x >> 6;
+  const int z0 = zr * ZR;
+  const int n_in = P.n_in, n_out = P.n_out, CI = P.CI;
+  const size_t in_vol = (size_t)n_in * n_in * n_in;
+  const int shift = DGRAD ? K - 1 : 0; /* input coordinate = output coordinate + tap - shift */
+
+  float acc[CO][ZR];
+#pragma unroll
+  for (int co = 0; co < CO; ++co)
+#pragma unroll
+    for (int i = 0; i < ZR; ++i) acc[co][i] = 0.0f;
+
+  for (int ci0 = 0; ci0 < CI; ci0 += CC) {
+    const int nc = CI - ci0 < CC ? CI - ci0 : CC;
+    /* stage the input tile (zero outside the volume) */
+    for (int e = threadIdx.x; e < nc * IX * IY * IZ; e += 256) {
+      int r = e;
+      const int z = r % IZ; r /= IZ;
+      const int y = r % IY; r /= IY;
+      const int x = r % IX;
+      const int c = r / IX;
+      const int gx = X0 + x - shift, gy = Y0 + y - shift, gz = Z0 + z - shift;
+      float v = 0.0f;
+      if (gx >= 0 && gx < n_in && gy >= 0 && gy < n_in && gz >= 0 && gz < n_in) {
+        const size_t idx = ((size_t)b * CI + ci0 + c) * in_vol + ((size_t)gx * n_in + gy) * n_in + gz;
+        v = __ldg(P.in + idx);
+        if (DGRAD && P.mask && !(__ldg(P.mask + idx) > 0.0f)) v = 0.0f;
+      }
+      tile[c][x][y][z] = v;
+    }
+    /* stage the weights of these input channels as [c][tap][co] */
+    for (int e = threadIdx.x; e < nc * 27 * CO; e += 256) {
+      const int co = e % CO;
+      const int tap = (e / CO) % 27;
+      const int c = e / (CO * 27);
+      float v;
+      if (!DGRAD) v = __ldg(P.w + ((size_t)co * CI + ci0 + c) * 27 + tap);
+      else v = __ldg(P.w + ((size_t)(ci0 + c) * CO + co) * 27 + (26 - tap)); /* w[co_orig = in ch][ci_orig = out ch], flipped */
+      ws[c][tap][co] = v;
+    }
+    __syncthreads();
+    for (int c = 0; c < nc; ++c) {
+#pragma unroll
+      for (int dx = 0; dx < K; ++dx) {
+#pragma unroll
+        for (int dy = 0; dy < K; ++dy) {
+          float v[ZR + K - 1];
+          const float* __restrict__ row = &tile[c][lx + dx][ly + dy][z0];
+#pragma unroll
+          for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
+#pragma unroll
+          for (int dz = 0; dz < K; ++dz) {
+            const float* __restrict__ wp = &ws[c][(dx * K + dy) * K + dz][0];
+#pragma unroll
+            for (int co = 0; co < CO; ++co) {
+              const float wv = wp[co];
+#pragma unroll
+              for (int i = 0; i < ZR; ++i) acc[co][i] = fmaf(wv, v[i + dz], acc[co][i]);
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const int ox = X0 + lx, oy = Y0 + ly;
+  if (ox >= n_out || oy >= n_out) return;
+  const size_t out_vol = (size_t)n_out * n_out * n_out;
+#pragma unroll
+  for (int co = 0; co < CO; ++co) {
+    const float bias = (!DGRAD && P.bias) ? __ldg(P.bias + co) : 0.0f;
+    float* __restrict__ o = P.out + ((size_t)b * CO + co) * out_vol + ((size_t)ox * n_out + oy) * n_out;
+#pragma unroll
+    for (int i = 0; i < ZR; ++i) {
+      const int oz = Z0 + z0 + i;
+      if (oz < n_out) {
+        float v = acc[co][i] + bias;
+        if (!DGRAD && P.relu) v = v > 0.0f ? v : 0.0f;
+        o[oz] = v;
+      }
+    }
+  }
+}
+
+template <int CO, int ZR, bool DGRAD>
+void launch_conv3_t(ConvParams P, int batch, cudaStream_t s) {
+  constexpr int TX = 4, TY = 8, TZ = 8 * ZR;
+  const int tiles_x = (P.n_out + TX - 1) / TX;
+  P.tiles_y = (P.n_out + TY - 1) / TY;
+  P.tiles_z = (P.n_out + TZ - 1) / TZ;
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    P.z_offset = z0;
+    const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535);
+    sdfr_conv3_kernel<CO, ZR, DGRAD><<<grid, 256, 0, s>>>(P);
+  }
+}
+
+/* CO = output channels of THIS launch (forward: Co; dgrad: Ci of the layer) */
+template <bool DGRAD>
+int launch_conv3(ConvParams P, int CO, int batch, cudaStream_t s) {
+  switch (CO) {
+    case 4: launch_conv3_t<4, 4, DGRAD>(P, batch, s); break;
+    case 8: launch_conv3_t<8, 4, DGRAD>(P, batch, s); break;
+    case 16: launch_conv3_t<16, 4, DGRAD>(P, batch, s); break;
+    case 32: launch_conv3_t<32, 2, DGRAD>(P, batch, s); break;
+    default:
+      return fail(SDFR_E_SHAPE, "conv3d: this launch's output channels must be 4, 8, 16 or 32");
+  }
+  return check_launch("sdfr_conv3_kernel");
 }
 
 #endif /* SDFR_DECODER_CUH_ */

@@ -1371,4 +1371,69 @@ int sdfr_decoder_tail_backward(const float* grad_sdf, long long grad_sdf_stride,
   return launch_tail_backward(P, batch, (cudaStream_t)stream);
 }
 
+int sdfr_upsample3d_forward(const float* x, int n_volumes, int in_size, int out_size, float* y,
+                            void* stream) {
+  if (int rc = tail_check(1, in_size, out_size, n_volumes)) return rc;
+  if (n_volumes == 0) return 0;
+  if (!x || !y) return fail(SDFR_E_NULL, "upsample3d: x or y is NULL");
+  TailParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = x; P.C = 1; P.S = in_size; P.R = out_size;
+  P.out = y; P.out_stride = (long long)out_size * out_size * out_size;
+  P.py = out_size; P.px = out_size * out_size;
+  return launch_tail_forward(P, n_volumes, (cudaStream_t)stream);
+}
+
+int sdfr_upsample3d_backward(const float* grad_y, int n_volumes, int in_size, int out_size,
+                             float* grad_x, void* stream) {
+  if (int rc = tail_check(1, in_size, out_size, n_volumes)) return rc;
+  if (n_volumes == 0) return 0;
+  if (!grad_y || !grad_x) return fail(SDFR_E_NULL, "upsample3d: grad_y or grad_x is NULL");
+  TailParams P;
+  memset(&P, 0, sizeof(P));
+  P.C = 1; P.S = in_size; P.R = out_size;
+  P.g_main = grad_y; P.g_main_stride = (long long)out_size * out_size * out_size;
+  P.g_x = grad_x;
+  return launch_tail_backward(P, n_volumes, (cudaStream_t)stream);
+}
+
+static int conv3_check(int batch, int ci, int co, int in_size, int k) {
+  if (k != 3) return fail(SDFR_E_SHAPE, "conv3d: only kernel_size 3 is implemented (every reference decoder trunk uses 3)");
+  if (batch < 0 || ci < 1 || ci > 4096 || co < 1 || co > 4096)
+    return fail(SDFR_E_SHAPE, "conv3d: bad batch or channel count");
+  if (in_size < k || in_size > 512) return fail(SDFR_E_SHAPE, "conv3d: in_size must be in [3, 512]");
+  return 0;
+}
+
+int sdfr_conv3d_forward(const float* x, int batch, int in_channels, int in_size, const float* weight,
+                        const float* bias, int out_channels, int kernel_size, int relu, float* y,
+                        void* stream) {
+  if (int rc = conv3_check(batch, in_channels, out_channels, in_size, kernel_size)) return rc;
+  if (out_channels != 4 && out_channels != 8 && out_channels != 16 && out_channels != 32)
+    return fail(SDFR_E_SHAPE, "conv3d forward: out_channels must be 4, 8, 16 or 32");
+  if (batch == 0) return 0;
+  if (!x || !weight || !y) return fail(SDFR_E_NULL, "conv3d: x, weight or y is NULL");
+  ConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.in = x; P.w = weight; P.bias = bias; P.out = y;
+  P.CI = in_channels; P.n_in = in_size; P.n_out = in_size - kernel_size + 1; P.relu = relu != 0;
+  return launch_conv3<false>(P, out_channels, batch, (cudaStream_t)stream);
+}
+
+int sdfr_conv3d_backward_data(const float* grad_y, const float* y, int batch, int in_channels,
+                              int in_size, const float* weight, int out_channels, int kernel_size,
+                              float* grad_x, void* stream) {
+  if (int rc = conv3_check(batch, in_channels, out_channels, in_size, kernel_size)) return rc;
+  if (in_channels != 4 && in_channels != 8 && in_channels != 16 && in_channels != 32)
+    return fail(SDFR_E_SHAPE, "conv3d backward: in_channels must be 4, 8, 16 or 32");
+  if (batch == 0) return 0;
+  if (!grad_y || !weight || !grad_x) return fail(SDFR_E_NULL, "conv3d: grad_y, weight or grad_x is NULL");
+  ConvParams P;
+  memset(&P, 0, sizeof(P));
+  P.in = grad_y; P.mask = y; P.w = weight; P.out = grad_x;
+  P.CI = out_channels; /* the transposed convolution reads the layer's OUTPUT channels */
+  P.n_in = in_size - kernel_size + 1; P.n_out = in_size;
+  return launch_conv3<true>(P, in_channels, batch, (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -2,5 +2,8 @@
 from .hypotheses import HypothesisOptimizer, gather_losses, global_best, shard_range  # noqa: F401
 from .losses import depth_to_pointcloud, pc_loss, point_loss  # noqa: F401
 from .streaming import StreamedRenderCompare  # noqa: F401
-from .decoder import FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail  # noqa: F401
+from .decoder import (FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail,  # noqa: F401
+                      trunk_stage)
 from .fused import decode_render_compare  # noqa: F401
+from .view_dataset import BatchedSDFViewGenerator  # noqa: F401
+from . import runtime_analysis  # noqa: F401

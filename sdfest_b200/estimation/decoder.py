@@ -134,6 +134,86 @@ def decoder_tail(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Ten
                               None if base is None else base.contiguous())
 
 
+class _TrunkStage(torch.autograd.Function):
+    """One decoder stage (sdf_vae.py:225-247): interpolate to ``in_size`` (if the input is smaller
+    or larger), Conv3d 3x3x3 + bias, optional ReLU -- ``sdfr_upsample3d_*`` and ``sdfr_conv3d_*``.
+    Differentiable w.r.t. the input only (frozen decoder)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, in_size, relu):
+        from ..differentiable_renderer.sdf_renderer import _check_input, _on_device_of, _stream
+
+        _check_input(x, "x")
+        _check_input(weight, "weight")
+        if bias is not None:
+            _check_input(bias, "bias")
+        if x.dim() != 5 or not (x.shape[2] == x.shape[3] == x.shape[4]):
+            raise RuntimeError(f"x must have shape (B,C,S,S,S), got {tuple(x.shape)}")
+        if weight.requires_grad or (bias is not None and bias.requires_grad):
+            raise RuntimeError("the CUDA decoder trunk is for a frozen decoder (no weight gradients)")
+        B, Ci, S = int(x.shape[0]), int(x.shape[1]), int(x.shape[2])
+        Co, k, U = int(weight.shape[0]), int(weight.shape[-1]), int(in_size)
+        if tuple(weight.shape) != (Co, Ci, k, k, k):
+            raise RuntimeError(f"weight must have shape ({Co},{Ci},k,k,k), got {tuple(weight.shape)}")
+        lib = _lib.lib()
+        with _on_device_of(x):
+            u = x
+            if S != U:
+                u = torch.empty((B, Ci, U, U, U), dtype=torch.float32, device=x.device)
+                _lib.check(lib.sdfr_upsample3d_forward(x.data_ptr(), B * Ci, S, U, u.data_ptr(),
+                                                       _stream()), "sdfr_upsample3d_forward")
+            O = U - k + 1
+            y = torch.empty((B, Co, O, O, O), dtype=torch.float32, device=x.device)
+            _lib.check(lib.sdfr_conv3d_forward(
+                u.data_ptr(), B, Ci, U, weight.data_ptr(), None if bias is None else bias.data_ptr(),
+                Co, k, int(bool(relu)), y.data_ptr(), _stream()), "sdfr_conv3d_forward")
+        ctx.save_for_backward(weight, y if relu else None)
+        ctx.meta = (B, Ci, S, U, Co, k)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        from ..differentiable_renderer.sdf_renderer import _on_device_of, _stream
+
+        weight, y = ctx.saved_tensors
+        B, Ci, S, U, Co, k = ctx.meta
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        grad_y = grad_y.contiguous()
+        lib = _lib.lib()
+        with _on_device_of(grad_y):
+            g_u = torch.empty((B, Ci, U, U, U), dtype=torch.float32, device=grad_y.device)
+            _lib.check(lib.sdfr_conv3d_backward_data(
+                grad_y.data_ptr(), None if y is None else y.data_ptr(), B, Ci, U, weight.data_ptr(),
+                Co, k, g_u.data_ptr(), _stream()), "sdfr_conv3d_backward_data")
+            g_x = g_u
+            if S != U:
+                g_x = torch.empty((B, Ci, S, S, S), dtype=torch.float32, device=grad_y.device)
+                _lib.check(lib.sdfr_upsample3d_backward(g_u.data_ptr(), B * Ci, S, U, g_x.data_ptr(),
+                                                        _stream()), "sdfr_upsample3d_backward")
+        return g_x, None, None, None, None
+
+
+def trunk_stage(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], in_size: int,
+                relu: bool) -> torch.Tensor:
+    """``relu?(conv3d(interpolate(x, in_size, "trilinear", align_corners=False), weight, bias))`` as
+    CUDA kernels of ``libsdfrender.so`` (3x3x3 kernels, 4/8/16/32 channels)."""
+    return _TrunkStage.apply(x.contiguous(), weight, bias, in_size, relu)
+
+
+_CUDA_TRUNK_CHANNELS = (4, 8, 16, 32)
+
+
+def _cuda_trunk_supported(conv, info) -> bool:
+    for layer, (size, _) in zip(conv[:-1], info[:-1]):
+        if (tuple(layer.kernel_size) != (3, 3, 3) or tuple(layer.stride) != (1, 1, 1)
+                or tuple(layer.padding) != (0, 0, 0) or tuple(layer.dilation) != (1, 1, 1)
+                or layer.groups != 1 or layer.in_channels not in _CUDA_TRUNK_CHANNELS
+                or layer.out_channels not in _CUDA_TRUNK_CHANNELS or not (3 <= size <= 128)):
+            return False
+    return True
+
+
 def _decoder_parts(decoder: nn.Module):
     """(fc layers, conv layers, conv infos as (in_size, relu, kernel, out_channels), volume size)
     of either this package's ``SDFDecoder`` or the reference's (sdfest/vae/sdf_vae.py:170-259:
@@ -160,10 +240,16 @@ class FusedTailDecoder(nn.Module):
     an analytic shape).  ``channels_last=True`` stores the trunk's convolution weights in
     ``torch.channels_last_3d``, which makes cuDNN pick its NDHWC tensor-core kernels (2.6 instead of
     4.7 ms for the trunk forward+backward of 64 hypotheses on a B200).
+
+    ``trunk``: ``"cuda"`` runs the convolution stages before the tail through this package's own
+    kernels too (``trunk_stage``: every decoder the reference ships is 3x3x3 convolutions between
+    4..32 channels with trilinear resizes in between); ``"torch"`` leaves them on PyTorch/cuDNN;
+    ``"auto"`` (default) picks ``"cuda"`` when the architecture qualifies.  The fully-connected
+    layers stay on PyTorch/cuBLAS either way.  ``trunk_impl`` tells which one runs.
     """
 
     def __init__(self, decoder: nn.Module, base: Optional[torch.Tensor] = None,
-                 channels_last: bool = True):
+                 trunk: str = "auto", channels_last: bool = True):
         super().__init__()
         self.decoder = decoder
         self.register_buffer("base", None if base is None else base.detach().clone().contiguous())
@@ -178,7 +264,14 @@ class FusedTailDecoder(nn.Module):
         self._fc, self._conv, self._info, self.volume_size = fc, conv, info, volume
         if base is not None and tuple(base.shape) != (volume,) * 3:
             raise ValueError(f"base must have shape {(volume,) * 3}, got {tuple(base.shape)}")
-        if channels_last:
+        if trunk not in ("auto", "cuda", "torch"):
+            raise ValueError("trunk must be 'auto', 'cuda' or 'torch'")
+        supported = _cuda_trunk_supported(conv, info)
+        if trunk == "cuda" and not supported:
+            raise ValueError("trunk='cuda' needs 3x3x3, stride-1, unpadded convolutions between "
+                             "4/8/16/32 channels")
+        self.trunk_impl = "cuda" if (trunk != "torch" and supported) else "torch"
+        if channels_last and self.trunk_impl == "torch":
             for layer in conv[:-1]:
                 layer.to(memory_format=torch.channels_last_3d)
 
@@ -189,6 +282,10 @@ class FusedTailDecoder(nn.Module):
             out = torch.relu(layer(out))
         c0, s0 = self._conv[0].in_channels, self._info[0][0]
         out = out.view(-1, c0, s0, s0, s0)
+        if self.trunk_impl == "cuda" and out.is_cuda:
+            for (size, relu), layer in zip(self._info[:-1], self._conv[:-1]):
+                out = trunk_stage(out, layer.weight, layer.bias, size, relu)
+            return out
         for (size, relu), layer in zip(self._info[:-1], self._conv[:-1]):
             if out.shape[2] != size:
                 out = nn.functional.interpolate(out, size=(size,) * 3, mode="trilinear",

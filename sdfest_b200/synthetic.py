@@ -133,7 +133,8 @@ def hypothesis_grids(shape_params, R: int, device, categories=("mug",)) -> torch
     return out
 
 
-def residual_decoder(R: int, device, base: torch.Tensor, seed: int = 0, gain: float = 1.0):
+def residual_decoder(R: int, device, base: torch.Tensor, seed: int = 0, gain: float = 1.0,
+                     trunk: str = "auto"):
     """A decoder of the reference's architecture that always has a surface: a randomly initialised
     ``SDFDecoder`` (frozen) decoding RESIDUALS around the analytic grid ``base`` through the fused
     CUDA tail (``estimation.FusedTailDecoder``).  The last convolution is rescaled by ``gain`` and its
@@ -152,4 +153,4 @@ def residual_decoder(R: int, device, base: torch.Tensor, seed: int = 0, gain: fl
         last.bias.mul_(gain)
         mean0 = dec(torch.zeros(1, dec.fc[0].in_features, device=device)).mean()
         last.bias.sub_(mean0)
-    return FusedTailDecoder(dec, base=base.to(device)).to(device).eval()
+    return FusedTailDecoder(dec, base=base.to(device), trunk=trunk).to(device).eval()

@@ -95,6 +95,37 @@ def small():
     print("decoder_tail_small:", tuple(x.shape), "->", tuple(out.shape), f"{os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def full_decoder():
+    """A whole (small, random-init) reference SDFDecoder with the shipped models' structure:
+    fc stack, three 3x3x3 stages with interpolation in between, 1x1x1 tail; weights, latents, the
+    decoded grids and d<g, out>/dz recorded through the reference's own forward/autograd."""
+    torch.manual_seed(9)
+    conv_layers = [{"in_size": 4, "in_channels": 8, "out_channels": 16, "kernel_size": 3, "relu": True},
+                   {"in_size": 7, "in_channels": 16, "out_channels": 8, "kernel_size": 3, "relu": True},
+                   {"in_size": 11, "in_channels": 8, "out_channels": 4, "kernel_size": 3, "relu": True},
+                   {"in_size": 20, "in_channels": 4, "out_channels": 1, "kernel_size": 1, "relu": False}]
+    dec = SDFDecoder(volume_size=20, latent_size=3, fc_layers=[{"out": 10}, {"out": 8 * 4 ** 3}],
+                     conv_layers=conv_layers)
+    dec.eval()
+    with torch.no_grad():  # default init gives mostly-dead ReLUs; spread the activations
+        for layer in dec._conv_layers:
+            layer.bias.add_(0.05)
+    z = torch.randn(2, 3, requires_grad=True)
+    g = torch.randn(2, 1, 20, 20, 20)
+    out = dec(z)
+    out.backward(g)
+    blobs = {f"fc{i}_w": l.weight.detach().numpy() for i, l in enumerate(dec._fc_layers)}
+    blobs.update({f"fc{i}_b": l.bias.detach().numpy() for i, l in enumerate(dec._fc_layers)})
+    blobs.update({f"conv{i}_w": l.weight.detach().numpy() for i, l in enumerate(dec._conv_layers)})
+    blobs.update({f"conv{i}_b": l.bias.detach().numpy() for i, l in enumerate(dec._conv_layers)})
+    path = os.path.join(HERE, "decoder_full_small.npz")
+    np.savez_compressed(path, z=z.detach().numpy(), g=g.numpy()[:, 0], out=out.detach().numpy()[:, 0],
+                        g_z=z.grad.numpy(), in_sizes=np.array([c["in_size"] for c in conv_layers]),
+                        relus=np.array([c["relu"] for c in conv_layers]), **blobs)
+    print("decoder_full_small:", tuple(out.shape), f"{os.path.getsize(path) / 1024:.0f} KiB")
+
+
 if __name__ == "__main__":
     mug()
     small()
+    full_decoder()

@@ -21,7 +21,7 @@ def lib():
 def declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(sdfr_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(sdfr_[a-z0-9_]+)\s*\(", text)))
 
 
 def test_header_declares_the_expected_entry_points():
