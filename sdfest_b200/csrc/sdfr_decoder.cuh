@@ -52,6 +52,7 @@ struct TailParams {
   long long g_extra_stride;
   float* __restrict__ g_x; /* [B, C, S, S, S] */
   int z_offset;
+  int xb; /* forward: output x-planes per CTA */
 };
 
 /* ATen area_pixel_compute_source_index, align_corners = false, linear */
@@ -64,16 +65,34 @@ __device__ __forceinline__ void tail_source(int o, float ratio, int S, int& i0, 
   l1 = src - (float)i0;
 }
 
-/* One CTA per (output x-plane, hypothesis). */
+/* Host copy of tail_source (same fp32 arithmetic) for sizing the staging buffer. */
+inline void tail_source_host(int o, int S, int R, int& i0, int& i1) {
+  const float ratio = (float)S / (float)R;
+  float src = ratio * ((float)o + 0.5f) - 0.5f;
+  src = src < 0.0f ? 0.0f : src;
+  i0 = (int)src;
+  i0 = i0 < S - 1 ? i0 : S - 1;
+  i1 = i0 + (i0 < S - 1 ? 1 : 0);
+}
+
+/*
+ * One CTA per (slab of P.xb consecutive output x-planes, hypothesis): the source x-planes the slab
+ * reads are channel-contracted once into shared memory, then every output is a trilinear blend of
+ * 8 shared-memory values.  (First version: one CTA per output x-plane -- 4096..16384 CTAs of three
+ * barrier-separated phases each, 60 M warp instructions for the 64^3 tail and bound by CTA turnover,
+ * not bandwidth: profiles/r01j_ncu_decoder.txt.)
+ */
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
   extern __shared__ float tail_smem[];
   const int S = P.S, R = P.R, C = P.C;
-  float* plane = tail_smem;             /* [S*S]  channel-contracted, x-collapsed source plane */
-  int* ti0 = (int*)(plane + S * S);     /* [R] */
-  int* ti1 = ti0 + R;                   /* [R] */
-  float* tl1 = (float*)(ti1 + R);       /* [R] */
-  const int b = blockIdx.y + P.z_offset, ox = blockIdx.x;
+  int* ti0 = (int*)tail_smem;         /* [R] */
+  int* ti1 = ti0 + R;                 /* [R] */
+  float* tl1 = (float*)(ti1 + R);     /* [R] */
+  float* src = tl1 + R;               /* [np][S*S] channel-contracted source planes */
+  const int b = blockIdx.y + P.z_offset;
+  const int ox0 = blockIdx.x * P.xb;
+  const int nxo = R - ox0 < P.xb ? R - ox0 : P.xb;
   const float ratio = (float)S / (float)R;
   for (int o = threadIdx.x; o < R; o += blockDim.x) {
     int i0, i1;
@@ -81,41 +100,67 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
     tail_source(o, ratio, S, i0, i1, l1);
     ti0[o] = i0; ti1[o] = i1; tl1[o] = l1;
   }
-  int x0, x1;
-  float lx1;
-  tail_source(ox, ratio, S, x0, x1, lx1);
-  const float lx0 = 1.0f - lx1;
+  __syncthreads();
+  const int xs_lo = ti0[ox0], np = ti1[ox0 + nxo - 1] - xs_lo + 1;
   float w[kTailMaxChannels];
 #pragma unroll
   for (int c = 0; c < kTailMaxChannels; ++c)
     w[c] = c < C ? (P.weight ? __ldg(P.weight + c) : 1.0f) : 0.0f; /* NULL weight: plain upsampling */
-  const size_t S2 = (size_t)S * S, S3 = S2 * S;
-  const float* __restrict__ xb = P.x + (size_t)b * C * S3;
-  for (int i = threadIdx.x; i < (int)S2; i += blockDim.x) {
-    float v0 = 0.0f, v1 = 0.0f;
+  const int S2 = S * S;
+  const size_t S3 = (size_t)S2 * S;
+  const float* __restrict__ xb = P.x + (size_t)b * C * S3 + (size_t)xs_lo * S2;
+  for (int e = threadIdx.x; e < np * S2; e += blockDim.x) {
+    float v = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kTailMaxChannels; ++c) {
-      if (c < C) {
-        v0 += w[c] * __ldg(xb + c * S3 + x0 * S2 + i);
-        v1 += w[c] * __ldg(xb + c * S3 + x1 * S2 + i);
-      }
-    }
-    plane[i] = lx0 * v0 + lx1 * v1;
+    for (int c = 0; c < kTailMaxChannels; ++c)
+      if (c < C) v += w[c] * __ldg(xb + c * S3 + e);
+    src[e] = v;
   }
   __syncthreads();
   const float bias = P.bias ? __ldg(P.bias) : 0.0f;
-  float* __restrict__ o = P.out + (size_t)b * P.out_stride + (size_t)ox * P.px;
-  const float* __restrict__ base = P.base ? P.base + (size_t)ox * R * R : nullptr;
-  for (int j = threadIdx.x; j < R * R; j += blockDim.x) {
-    const int oy = j / R, oz = j - oy * R;
-    const int y0 = ti0[oy], y1 = ti1[oy], z0 = ti0[oz], z1 = ti1[oz];
-    const float ly1 = tl1[oy], lz1 = tl1[oz];
-    const float ly0 = 1.0f - ly1, lz0 = 1.0f - lz1;
-    const float a = lz0 * plane[y0 * S + z0] + lz1 * plane[y0 * S + z1];
-    const float c = lz0 * plane[y1 * S + z0] + lz1 * plane[y1 * S + z1];
-    float v = (ly0 * a + ly1 * c) + bias;
-    if (base) v += __ldg(base + j);
-    o[oy * P.py + oz] = v;
+  float* __restrict__ out = P.out + (size_t)b * P.out_stride;
+  if (R <= 256 && (256 % R) == 0) {
+    /* a thread keeps ONE output column oz (z-interpolation constants in registers) and walks the
+     * rows of every plane of the slab; x / y constants are warp-uniform (broadcast loads) */
+    const int oz = threadIdx.x % R, rows = 256 / R;
+    const int z0 = ti0[oz], z1 = ti1[oz];
+    const float lz1 = tl1[oz], lz0 = 1.0f - lz1;
+    for (int dx = 0; dx < nxo; ++dx) {
+      const int ox = ox0 + dx;
+      const float* __restrict__ pa = src + (ti0[ox] - xs_lo) * S2;
+      const float* __restrict__ pb = src + (ti1[ox] - xs_lo) * S2;
+      const float lx1 = tl1[ox], lx0 = 1.0f - lx1;
+      float* __restrict__ o = out + (size_t)ox * P.px;
+      const float* __restrict__ base = P.base ? P.base + (size_t)ox * R * R : nullptr;
+      for (int oy = threadIdx.x / R; oy < R; oy += rows) {
+        const int r0 = ti0[oy] * S, r1 = ti1[oy] * S;
+        const float ly1 = tl1[oy], ly0 = 1.0f - ly1;
+        const float a0 = lz0 * pa[r0 + z0] + lz1 * pa[r0 + z1];
+        const float a1 = lz0 * pa[r1 + z0] + lz1 * pa[r1 + z1];
+        const float b0 = lz0 * pb[r0 + z0] + lz1 * pb[r0 + z1];
+        const float b1 = lz0 * pb[r1 + z0] + lz1 * pb[r1 + z1];
+        float v = (lx0 * (ly0 * a0 + ly1 * a1) + lx1 * (ly0 * b0 + ly1 * b1)) + bias;
+        if (base) v += __ldg(base + oy * R + oz);
+        o[oy * P.py + oz] = v;
+      }
+    }
+    return;
+  }
+  for (int j = threadIdx.x; j < nxo * R * R; j += blockDim.x) {
+    const int dx = j / (R * R), r = j - dx * R * R;
+    const int oy = r / R, oz = r - oy * R, ox = ox0 + dx;
+    const float* __restrict__ pa = src + (ti0[ox] - xs_lo) * S2;
+    const float* __restrict__ pb = src + (ti1[ox] - xs_lo) * S2;
+    const int r0 = ti0[oy] * S, r1 = ti1[oy] * S, z0 = ti0[oz], z1 = ti1[oz];
+    const float lx1 = tl1[ox], ly1 = tl1[oy], lz1 = tl1[oz];
+    const float lx0 = 1.0f - lx1, ly0 = 1.0f - ly1, lz0 = 1.0f - lz1;
+    const float a0 = lz0 * pa[r0 + z0] + lz1 * pa[r0 + z1];
+    const float a1 = lz0 * pa[r1 + z0] + lz1 * pa[r1 + z1];
+    const float b0 = lz0 * pb[r0 + z0] + lz1 * pb[r0 + z1];
+    const float b1 = lz0 * pb[r1 + z0] + lz1 * pb[r1 + z1];
+    float v = (lx0 * (ly0 * a0 + ly1 * a1) + lx1 * (ly0 * b0 + ly1 * b1)) + bias;
+    if (P.base) v += __ldg(P.base + (size_t)ox * R * R + r);
+    out[(size_t)ox * P.px + oy * P.py + oz] = v;
   }
 }
 
@@ -126,14 +171,19 @@ __device__ __forceinline__ float tail_weight(const int* ti0, const int* ti1, con
   return (ti0[o] == s ? 1.0f - l1 : 0.0f) + (ti1[o] == s ? l1 : 0.0f);
 }
 
+/* upper bound on the number of output indices that read one source index along an axis */
+__host__ __device__ inline int tail_taps(int S, int R) { return 2 * ((R + S - 1) / S) + 2; }
+
 /* One CTA per (source x-plane, hypothesis). */
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   extern __shared__ float tail_smem[];
   const int S = P.S, R = P.R, C = P.C;
+  const int KW = tail_taps(S, R);
   float* Pl = tail_smem;              /* [R][R]  x-collapsed gradient plane */
   float* Q = Pl + R * R;              /* [R][S]  ... z-collapsed */
-  int* ti0 = (int*)(Q + R * S);       /* [R] */
+  float* Wt = Q + R * S;              /* [S][KW] weight of output lo[s]+k on source s (0 past hi[s]) */
+  int* ti0 = (int*)(Wt + S * KW);     /* [R] */
   int* ti1 = ti0 + R;
   float* tl1 = (float*)(ti1 + R);
   int* lo = (int*)(tl1 + R);          /* [S] first / last output index touching source s */
@@ -158,6 +208,11 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
     hi[s] = h;
   }
   __syncthreads();
+  for (int e = threadIdx.x; e < S * KW; e += blockDim.x) {
+    const int s = e / KW, o = lo[s] + (e - s * KW);
+    Wt[e] = o <= hi[s] ? tail_weight(ti0, ti1, tl1, o, s) : 0.0f;
+  }
+  __syncthreads();
 
   float coef = 1.0f;
   if (P.n_overlap) {
@@ -169,15 +224,16 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   const size_t R2 = (size_t)R * R;
   const float* __restrict__ ga = P.g_main + (size_t)b * P.g_main_stride;
   const float* __restrict__ ge = P.g_extra ? P.g_extra + (size_t)b * P.g_extra_stride : nullptr;
-  const int xlo = lo[sx], xhi = hi[sx];
+  const int xlo = lo[sx], nx = hi[sx] - xlo + 1;
+  const float* __restrict__ wx = Wt + sx * KW;
   /* 1. collapse x:  Pl[oy][oz] = sum_ox W(ox, sx) g[ox][oy][oz] */
   for (int j = threadIdx.x; j < (int)R2; j += blockDim.x) {
     float acc = 0.0f;
-    for (int ox = xlo; ox <= xhi; ++ox) {
-      const float wgt = tail_weight(ti0, ti1, tl1, ox, sx);
-      float g = coef != 0.0f ? coef * __ldg(ga + ox * R2 + j) : 0.0f;
-      if (ge) g += __ldg(ge + ox * R2 + j);
-      acc += wgt * g;
+    for (int k = 0; k < nx; ++k) {
+      const size_t idx = (size_t)(xlo + k) * R2 + j;
+      float g = coef != 0.0f ? coef * __ldg(ga + idx) : 0.0f;
+      if (ge) g += __ldg(ge + idx);
+      acc += wx[k] * g;
     }
     Pl[j] = acc;
   }
@@ -185,8 +241,11 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   /* 2. collapse z:  Q[oy][sz] = sum_oz W(oz, sz) Pl[oy][oz] */
   for (int j = threadIdx.x; j < R * S; j += blockDim.x) {
     const int oy = j / S, sz = j - oy * S;
+    const float* __restrict__ w = Wt + sz * KW;
+    const float* __restrict__ p = Pl + oy * R + lo[sz];
+    const int n = hi[sz] - lo[sz] + 1;
     float acc = 0.0f;
-    for (int oz = lo[sz]; oz <= hi[sz]; ++oz) acc += tail_weight(ti0, ti1, tl1, oz, sz) * Pl[oy * R + oz];
+    for (int k = 0; k < n; ++k) acc += w[k] * p[k];
     Q[j] = acc;
   }
   __syncthreads();
@@ -195,15 +254,37 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   float* __restrict__ gx = P.g_x + (size_t)b * C * S3 + (size_t)sx * S2;
   for (int j = threadIdx.x; j < (int)S2; j += blockDim.x) {
     const int sy = j / S, sz = j - sy * S;
+    const float* __restrict__ w = Wt + sy * KW;
+    const float* __restrict__ q = Q + lo[sy] * S + sz;
+    const int n = hi[sy] - lo[sy] + 1;
     float acc = 0.0f;
-    for (int oy = lo[sy]; oy <= hi[sy]; ++oy) acc += tail_weight(ti0, ti1, tl1, oy, sy) * Q[oy * S + sz];
+    for (int k = 0; k < n; ++k) acc += w[k] * q[k * S];
     for (int c = 0; c < C; ++c) gx[c * S3 + j] = (P.weight ? __ldg(P.weight + c) : 1.0f) * acc;
   }
 }
 
-size_t tail_forward_smem(int S, int R) { return sizeof(float) * ((size_t)S * S + 3 * (size_t)R); }
+/* Slab thickness (output x-planes per CTA) and the shared memory it needs: aim at ~32 K outputs
+ * per CTA, shrink while the staged source planes do not fit. */
+size_t tail_forward_plan(int S, int R, int& xb) {
+  xb = 32768 / (R * R);
+  xb = xb < 1 ? 1 : (xb > R ? R : xb);
+  for (;;) {
+    int np = 1;
+    for (int ox0 = 0; ox0 < R; ox0 += xb) {
+      const int last = ox0 + xb - 1 < R - 1 ? ox0 + xb - 1 : R - 1;
+      int a0, a1, b0, b1;
+      tail_source_host(ox0, S, R, a0, a1);
+      tail_source_host(last, S, R, b0, b1);
+      np = b1 - a0 + 1 > np ? b1 - a0 + 1 : np;
+    }
+    const size_t bytes = sizeof(float) * ((size_t)np * S * S + 3 * (size_t)R);
+    if (bytes <= 160 * 1024 || xb == 1) return bytes;
+    xb = xb / 2;
+  }
+}
 size_t tail_backward_smem(int S, int R) {
-  return sizeof(float) * ((size_t)R * R + (size_t)R * S + 3 * (size_t)R + 2 * (size_t)S);
+  return sizeof(float) * ((size_t)R * R + (size_t)R * S + (size_t)S * tail_taps(S, R) + 3 * (size_t)R +
+                          2 * (size_t)S);
 }
 
 int tail_check(int C, int S, int R, int batch) {
@@ -215,7 +296,7 @@ int tail_check(int C, int S, int R, int batch) {
 }
 
 int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
-  const size_t smem = tail_forward_smem(P.S, P.R);
+  const size_t smem = tail_forward_plan(P.S, P.R, P.xb);
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_forward_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -223,7 +304,7 @@ int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
   }
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
-    const dim3 grid(P.R, batch - z0 < 65535 ? batch - z0 : 65535);
+    const dim3 grid((P.R + P.xb - 1) / P.xb, batch - z0 < 65535 ? batch - z0 : 65535);
     sdfr_decoder_tail_forward_kernel<<<grid, 256, smem, s>>>(P);
   }
   return check_launch("sdfr_decoder_tail_forward_kernel");
@@ -274,7 +355,7 @@ struct ConvParams {
 };
 
 template <int CO, int ZR, bool DGRAD>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, (CO * ZR <= 32 ? 4 : (CO * ZR <= 64 ? 2 : 1)))
 sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   constexpr int K = 3, TX = 4, TY = 8, TZ = 8 * ZR, CC = 4;
   constexpr int IX = TX + K - 1, IY = TY + K - 1, IZ = TZ + K - 1;
@@ -300,23 +381,49 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
     for (int i = 0; i < ZR; ++i) acc[co][i] = 0.0f;
 
+  /* staging plan, fixed for the whole kernel: within one (channel, x) plane of the input tile this
+   * thread copies the (y, z) elements number threadIdx.x and threadIdx.x + 256 (IY * IZ <= 512);
+   * only the plane base changes from plane to plane */
+  static_assert(IY * IZ <= 512, "two staging slots per thread");
+  int s_goff[2], s_soff[2];
+  bool s_ok[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const int e = threadIdx.x + 256 * k;
+    const int y = e / IZ, z = e - y * IZ;
+    const int gy = Y0 + y - shift, gz = Z0 + z - shift;
+    s_ok[k] = e < IY * IZ && gy >= 0 && gy < n_in && gz >= 0 && gz < n_in;
+    s_goff[k] = gy * n_in + gz;
+    s_soff[k] = e < IY * IZ ? y * PZ + z : -1;
+  }
+
   for (int ci0 = 0; ci0 < CI; ci0 += CC) {
     const int nc = CI - ci0 < CC ? CI - ci0 : CC;
-    /* stage the input tile (zero outside the volume) */
-    for (int e = threadIdx.x; e < nc * IX * IY * IZ; e += 256) {
-      int r = e;
-      const int z = r % IZ; r /= IZ;
-      const int y = r % IY; r /= IY;
-      const int x = r % IX;
-      const int c = r / IX;
-      const int gx = X0 + x - shift, gy = Y0 + y - shift, gz = Z0 + z - shift;
-      float v = 0.0f;
-      if (gx >= 0 && gx < n_in && gy >= 0 && gy < n_in && gz >= 0 && gz < n_in) {
-        const size_t idx = ((size_t)b * CI + ci0 + c) * in_vol + ((size_t)gx * n_in + gy) * n_in + gz;
-        v = __ldg(P.in + idx);
-        if (DGRAD && P.mask && !(__ldg(P.mask + idx) > 0.0f)) v = 0.0f;
+    /* stage the input tile (zero outside the volume): all loads of one channel are issued before
+     * the first store -- the kernel is bound by the latency of these loads, not by their count */
+    constexpr int XB = DGRAD ? IX / 2 : IX; /* x-planes per batch: 12 loads in flight either way */
+    for (int cx = 0; cx < nc * (IX / XB); ++cx) {
+      const int c = cx / (IX / XB), xb = (cx - c * (IX / XB)) * XB;
+      const size_t cbase = ((size_t)b * CI + ci0 + c) * in_vol;
+      float v[XB][2], m[XB][2];
+#pragma unroll
+      for (int x = 0; x < XB; ++x) {
+        const int gx = X0 + xb + x - shift;
+        const bool xok = gx >= 0 && gx < n_in;
+        const size_t pbase = cbase + (size_t)(xok ? gx : 0) * n_in * n_in;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const bool ok = xok && s_ok[k];
+          v[x][k] = ok ? __ldg(P.in + pbase + s_goff[k]) : 0.0f;
+          m[x][k] = (DGRAD && P.mask && ok) ? __ldg(P.mask + pbase + s_goff[k]) : 1.0f;
+        }
       }
-      tile[c][x][y][z] = v;
+#pragma unroll
+      for (int x = 0; x < XB; ++x) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+          if (s_soff[k] >= 0) (&tile[c][xb + x][0][0])[s_soff[k]] = m[x][k] > 0.0f ? v[x][k] : 0.0f;
+      }
     }
     /* stage the weights of these input channels as [c][tap][co] */
     for (int e = threadIdx.x; e < nc * 27 * CO; e += 256) {
@@ -386,14 +493,23 @@ void launch_conv3_t(ConvParams P, int batch, cudaStream_t s) {
   }
 }
 
+/* z-extent of the CTA tile (8 * ZR) follows the volume: 32 for n_out > 16, 16 for > 8, else 8 --
+ * a 14^3 output in 32-deep tiles would leave 56 % of the lanes idle */
+template <int CO, bool DGRAD>
+void launch_conv3_zr(const ConvParams& P, int batch, cudaStream_t s) {
+  if (P.n_out > 16 && CO <= 16) launch_conv3_t<CO, (CO <= 16 ? 4 : 2), DGRAD>(P, batch, s);
+  else if (P.n_out > 8) launch_conv3_t<CO, 2, DGRAD>(P, batch, s);
+  else launch_conv3_t<CO, 1, DGRAD>(P, batch, s);
+}
+
 /* CO = output channels of THIS launch (forward: Co; dgrad: Ci of the layer) */
 template <bool DGRAD>
 int launch_conv3(ConvParams P, int CO, int batch, cudaStream_t s) {
   switch (CO) {
-    case 4: launch_conv3_t<4, 4, DGRAD>(P, batch, s); break;
-    case 8: launch_conv3_t<8, 4, DGRAD>(P, batch, s); break;
-    case 16: launch_conv3_t<16, 4, DGRAD>(P, batch, s); break;
-    case 32: launch_conv3_t<32, 2, DGRAD>(P, batch, s); break;
+    case 4: launch_conv3_zr<4, DGRAD>(P, batch, s); break;
+    case 8: launch_conv3_zr<8, DGRAD>(P, batch, s); break;
+    case 16: launch_conv3_zr<16, DGRAD>(P, batch, s); break;
+    case 32: launch_conv3_zr<32, DGRAD>(P, batch, s); break;
     default:
       return fail(SDFR_E_SHAPE, "conv3d: this launch's output channels must be 4, 8, 16 or 32");
   }
