@@ -65,6 +65,16 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu
+    capture of this same command (profiles/ncu_traffic.json); None when there is no capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------
 # clocks: sampled through NVML while the timed region runs
 # ---------------------------------------------------------------------------------------------
@@ -411,6 +421,45 @@ def main():
     e2e_s = min(e2e_eager_s, e2e_graph_s) if e2e_graph_s else e2e_eager_s
     e2e_value = world * B * P * Ke / e2e_s / 1e6
 
+    # ---- the whole loop of BASELINE config 2: 50 Adam steps on pose / scale / latent -------------
+    # decoder (reference architecture, trunk + fused tail on this library's kernels) -> fused
+    # render-and-compare -> point-cloud loss -> backward -> Adam, B hypotheses at once, replayed as a
+    # CUDA graph (estimation.HypothesisOptimizer).  Reported beside the render metric, not instead.
+    loop = None
+    try:
+        from sdfest_b200.estimation import HypothesisOptimizer
+
+        dec = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
+        opt = HypothesisOptimizer(cam, THRESHOLD, obs, pos, quat, 1.0 / inv_s,
+                                  latent=torch.zeros(B, 8, device=dev), decoder=dec)
+        opt.capture()
+        for _ in range(5):
+            opt.step()
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        n_it = 50
+        a, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_it):
+            opt.step()
+        b_ev.record()
+        torch.cuda.synchronize()
+        loop_ms = a.elapsed_time(b_ev)
+        if distributed:
+            t = torch.tensor([loop_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            loop_ms = float(t.item())
+            final = opt.run(1)  # one more step with the all_gather of the per-hypothesis losses
+            assert final.numel() == world * B
+        loop = {"hyp_iter_per_s": world * B * n_it / (loop_ms * 1e-3), "ms_per_iteration": loop_ms / n_it,
+                "iterations": n_it, "hypotheses_per_gpu": B,
+                "what": "50 Adam steps on position/orientation/scale/latent: decoder trunk + fused tail, "
+                        "fused render-and-compare, point loss, backward, Adam; CUDA-graph replay",
+                "final_mean_loss": float(opt.last_losses.mean())}
+    except Exception as e:  # the loop demo never blocks the render metric
+        loop = {"unavailable": str(e)[:200]}
+
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -429,7 +478,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": "sdfr_forward_kernel<64, skewed, MODE=2> (fused render+compare+backward, incl. its memsets)",
         "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("fused"), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
         "note": ("algorithmic bytes = SURVEY 8d formula (32 B per trilinear sample + compulsory "
                  "image/grid traffic); the 32*S gather term is served by L1/L2, so frac is against "
@@ -455,7 +504,8 @@ def main():
                    "resolution": R, "threshold": THRESHOLD, "sdf": "analytic mug grids, one per hypothesis",
                    "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset, outside the event pair)",
                    "collective": "all_gather of per-hypothesis losses" if distributed else "none"},
-        "hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
+        "render_hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
+        "loop": loop,
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": Ke, "ms_per_step": e2e_s / Ke * 1e3,

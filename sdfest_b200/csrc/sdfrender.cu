@@ -283,6 +283,34 @@ __device__ __forceinline__ void scatter_sdf(float* __restrict__ gs, const Grid& 
   atomicAdd(gs + R2 + R + 1, pg.w[7]);
 }
 
+/*
+ * Warp-aggregated scatter: neighbouring rays of an 8x4 warp tile mostly end in the same grid cell
+ * (a 64^3 grid seen at 640x480 spans ~4 pixels per cell), so their 8 corner contributions are first
+ * merged inside the warp -- a 5-level butterfly in which two lanes merge when both still carry a
+ * contribution for the SAME cell -- and only the surviving lanes issue RED.ADD.F32.  Must be called
+ * by all 32 lanes; `has` marks lanes that carry a contribution.
+ */
+template <int RT>
+__device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const Grid& G, PixelGrad& pg,
+                                                 bool has, int lane) {
+  const int key = has ? pg.base : -1;
+  bool alive = has;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const int pkey = __shfl_xor_sync(kFull, key, 1 << k);
+    const bool palive = __shfl_xor_sync(kFull, (int)alive, 1 << k) != 0;
+    const bool merge = alive && palive && pkey == key;
+    const bool lower = (lane & (1 << k)) == 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float o = __shfl_xor_sync(kFull, pg.w[i], 1 << k);
+      if (merge && lower) pg.w[i] += o;
+    }
+    if (merge && !lower) alive = false;
+  }
+  if (alive) scatter_sdf<RT>(gs, G, pg);
+}
+
 /* registers -> warp shuffle -> shared -> 8 atomics per CTA (the reference issues 8 same-address
  * atomics per hit pixel, cu:459-466).  Contains one barrier: call from uniform control flow. */
 __device__ __forceinline__ void reduce_pose(float (&acc)[8], float (*red)[8], int b,
@@ -449,6 +477,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
           }
         }
       }
+      float sgn = 0.0f; /* MODE 2: sign(est - obs) on overlap pixels, 0 = nothing to back-propagate */
       if (inimg) {
         const unsigned pix = (unsigned)py * (unsigned)W + (unsigned)px;
         out[pix] = z;
@@ -458,19 +487,25 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
           if (obs > 0.0f) {
             err_acc += fabsf(z - obs);
             cnt_acc += 1.0f;
-            if (MODE == 2 && z != obs) {
-              const float sgn = z > obs ? 1.0f : -1.0f;
-              PixelGrad pg;
-              pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, z, sgn,
-                                                          (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
-              if (WANT_SDF)
-                scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg);
-              if (WANT_POSE) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
-              }
-            }
+            if (MODE == 2 && z != obs) sgn = z > obs ? 1.0f : -1.0f;
           }
+        }
+      }
+      if (MODE == 2 && __any_sync(kFull, sgn != 0.0f)) {
+        PixelGrad pg;
+        if (sgn != 0.0f)
+          pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, z, sgn,
+                                                      (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+        if (WANT_SDF) {
+#ifdef SDFR_NO_WARP_AGGREGATION
+          if (sgn != 0.0f) scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg);
+#else
+          scatter_sdf_warp<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg, sgn != 0.0f, lane);
+#endif
+        }
+        if (WANT_POSE && sgn != 0.0f) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
         }
       }
       if (lane == 0) q = atomicAdd(&next_q, 1);
