@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 5
+#define SDFR_ABI_VERSION 6
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -68,6 +68,10 @@ extern "C" {
  * (simple_renderer.py:399-408). */
 #define SDFR_SDF_GRAD_EXACT 0x10u
 #define SDFR_ZERO_GRADS 0x20u /* clear the requested gradient buffers before accumulating */
+
+/* flags of sdfr_hypothesis_step */
+#define SDFR_STEP_CLEAR_INPUTS 0x100u /* zero the sums / gradient inputs after consuming them */
+#define SDFR_STEP_NO_UPDATE 0x200u    /* only derive unit_orientation / inv_scale / loss */
 
 int sdfr_abi_version(void);
 const char* sdfr_last_error(void);
@@ -221,6 +225,54 @@ int sdfr_point_loss_backward(const float* points, long long points_stride, int n
                              float* grad_sdf, long long grad_sdf_stride, float* grad_position,
                              float* grad_orientation, float* grad_scale, unsigned flags,
                              void* stream);
+
+/*
+ * sdfr_point_loss_forward and _backward in ONE traversal: valid whenever `upstream` does not depend
+ * on this call's loss_sum -- in the loop it is the constant pc_weight / n_points
+ * (estimation/simple_setup.py:447-452).  loss_sum as in _forward, gradients as in _backward;
+ * SDFR_ZERO_GRADS clears loss_sum and the requested gradient buffers first.
+ */
+int sdfr_point_loss_fused(const float* points, long long points_stride, int n_points,
+                          const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
+                          const float* position, const float* orientation, const float* scale,
+                          int batch, const float* upstream, float* loss_sum, float* grad_sdf,
+                          long long grad_sdf_stride, float* grad_position, float* grad_orientation,
+                          float* grad_scale, unsigned flags, void* stream);
+
+/*
+ * The optimiser side of one render-and-compare iteration for `batch` hypotheses, one kernel:
+ * replaces torch.optim.Adam over the four parameter groups of estimation/simple_setup.py:400-406
+ * (learning rates lr[4] = position, orientation, scale, latent; HOST array), the chain rule through
+ * norm_orientation = orientation/|orientation| (:411) and 1/scale (:431), the weighted loss (:447-452)
+ * and the renormalisation orientation /= |orientation| (:462).  Per hypothesis b:
+ *   coef     = n_overlap[b] > 0 ? depth_weight / n_overlap[b] : 0
+ *   g_pos    = coef * gr_position + g2_position
+ *   g_unit_q = coef * gr_orientation + g2_orientation;  g_orient = (g_unit_q - q (q.g_unit_q)) / |orientation|
+ *   g_scale  = -coef * gr_inv_scale / scale^2 + g2_scale;  g_latent as given
+ *   Adam with bias correction (torch/optim/adam.py, no weight decay, no amsgrad), state
+ *   exp_avg / exp_avg_sq [batch, 8 + latent_size] (position 0-2, orientation 3-6, scale 7, latent
+ *   8..) and step [batch] (int32), all caller-zeroed before the first call;
+ *   then orientation is renormalised in place and, if given,
+ *   unit_orientation = orientation/|orientation|, inv_scale = 1/scale  (the next iteration's
+ *   renderer inputs), loss = depth_weight * loss_sum/n_overlap (0 without overlap, the reference's
+ *   nan_to_num) + point_weight * point_sum.
+ * gr_* are the RAW gradients of sdfr_compare_fused (w.r.t. the unit quaternion and inv_scale);
+ * g2_* an already weighted second set (sdfr_point_loss_fused: w.r.t. the quaternion it was given --
+ * the unit one -- and scale).  Any gradient pointer may be NULL (= 0); latent / g_latent NULL or
+ * latent_size 0 = no latent group (latent_size <= 64).  With SDFR_STEP_CLEAR_INPUTS the kernel zeroes
+ * loss_sum, n_overlap, point_sum and every gradient input after reading them (the next
+ * iteration's kernels then accumulate without memsets); with SDFR_STEP_NO_UPDATE parameters and
+ * state are left untouched and only unit_orientation / inv_scale / loss are written.
+ */
+int sdfr_hypothesis_step(float* position, float* orientation, float* scale, float* latent,
+                         int latent_size, int batch, float* loss_sum, float* n_overlap,
+                         float* gr_position, float* gr_orientation, float* gr_inv_scale,
+                         float depth_weight, float* point_sum, float point_weight,
+                         float* g2_position, float* g2_orientation, float* g2_scale,
+                         float* g_latent, float* exp_avg, float* exp_avg_sq, int* step,
+                         const float* lr, float beta1, float beta2, float eps,
+                         float* unit_orientation, float* inv_scale, float* loss, unsigned flags,
+                         void* stream);
 
 /*
  * Decoder tail: the last two operators of the reference SDF decoder,

@@ -38,28 +38,34 @@ def timeit(fn, n=20, warm=3):
     return (time.perf_counter() - t0) / n * 1e3
 
 
-def make(decoder):
+def make(decoder, optimizer="auto"):
     kw = dict(sdf=grids) if decoder is None else dict(latent=torch.zeros(B, 8, device=dev), decoder=decoder)
-    return HypothesisOptimizer(cam, THR, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"], **kw)
+    return HypothesisOptimizer(cam, THR, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                               optimizer=optimizer, **kw)
 
 
 torch.manual_seed(0)
 _plain = SDFDecoder(R)
 _fused = FusedTailDecoder(SDFDecoder(R), trunk="torch")
 _fused.decoder.load_state_dict(_plain.state_dict())
-for name, dec in (("pose_only", None),
-                  ("pose_latent", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_plain).to(dev).eval()),
-                  ("pose_latent_fused_tail", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_fused).to(dev).eval()),
-                  ("pose_latent_fused_iteration_torch_trunk",
-                   syn.residual_decoder(R, dev, syn.sdf_mug(R, dev), trunk="torch")),
-                  ("pose_latent_fused_iteration", syn.residual_decoder(R, dev, syn.sdf_mug(R, dev)))):
+ALL = os.environ.get("LOOP_ALL", "0") == "1"  # also the slow historical variants
+variants = [("pose_only_torch_adam", None, "torch"), ("pose_only", None, "fused")]
+if ALL:
+    variants += [
+        ("pose_latent", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_plain).to(dev).eval(), "torch"),
+        ("pose_latent_fused_tail", SurfaceDecoder(syn.sdf_mug(R, dev), decoder=_fused).to(dev).eval(), "torch"),
+        ("pose_latent_fused_iteration_torch_trunk",
+         syn.residual_decoder(R, dev, syn.sdf_mug(R, dev), trunk="torch"), "torch")]
+variants += [("pose_latent_fused_iteration_torch_adam", syn.residual_decoder(R, dev, syn.sdf_mug(R, dev)), "torch"),
+             ("pose_latent_fused_iteration", syn.residual_decoder(R, dev, syn.sdf_mug(R, dev)), "fused")]
+for name, dec, optimizer in variants:
     if dec is not None:
         for p in dec.parameters():
             p.requires_grad_(False)
-    opt = make(dec)
+    opt = make(dec, optimizer)
     eager = timeit(opt.step)
     l0 = float(opt.last_losses.mean())
-    opt2 = make(dec)
+    opt2 = make(dec, optimizer)
     try:
         opt2.capture()
         graph = timeit(opt2.step, n=50)

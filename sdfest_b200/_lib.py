@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -22,6 +22,8 @@ GRAD_INV_SCALE = 0x08
 GRAD_ALL = 0x0F
 SDF_GRAD_EXACT = 0x10
 ZERO_GRADS = 0x20
+STEP_CLEAR_INPUTS = 0x100
+STEP_NO_UPDATE = 0x200
 LAYOUT_DENSE = 0
 LAYOUT_SKEWED = 1
 
@@ -57,6 +59,12 @@ SIGNATURES = {
     "sdfr_point_loss_backward": (
         c_int, [_P, c_longlong, c_int, _P, c_int, c_longlong, c_int, *_POSE, c_int, _P, *_GRADS,
                 c_uint, _P]),
+    "sdfr_point_loss_fused": (
+        c_int, [_P, c_longlong, c_int, _P, c_int, c_longlong, c_int, *_POSE, c_int, _P, _P, *_GRADS,
+                c_uint, _P]),
+    "sdfr_hypothesis_step": (
+        c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, _P, c_float, _P, _P, _P, _P,
+                _P, _P, _P, ctypes.POINTER(c_float), c_float, c_float, c_float, _P, _P, _P, c_uint, _P]),
     "sdfr_decoder_tail_forward": (
         c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_longlong, c_int, _P]),
     "sdfr_decoder_tail_backward": (

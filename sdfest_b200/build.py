@@ -20,6 +20,7 @@ HEADERS = [
     os.path.join(CSRC, "sdfr_core.cuh"),
     os.path.join(CSRC, "sdfr_points.cuh"),
     os.path.join(CSRC, "sdfr_decoder.cuh"),
+    os.path.join(CSRC, "sdfr_step.cuh"),
     os.path.join(os.path.dirname(PKG_DIR), "include", "sdfrender.h"),
 ]
 NVCC_FLAGS = [

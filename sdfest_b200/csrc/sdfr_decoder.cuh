@@ -352,16 +352,35 @@ struct ConvParams {
   int CI, n_in, n_out, relu;
   int tiles_y, tiles_z;
   int z_offset;
+  int cc; /* channels staged per pass = min(CI, ConvTile::CC) */
 };
 
-template <int CO, int ZR, bool DGRAD>
-__global__ void __launch_bounds__(256, (CO * ZR <= 32 ? 4 : (CO * ZR <= 64 ? 2 : 1)))
+/* Shared-memory geometry of one CTA: CC input channels of the (TX+2) x (TY+2) x (TZ+2) input tile,
+ * z-pitch PZ a multiple of 4 floats so that staging and the inner loop use 128 / 64-bit accesses. */
+template <int CO, int ZR>
+struct ConvTile {
+  static constexpr int K = 3, TX = 4, TY = 8, TZ = 8 * ZR, CC = 8;
+  static constexpr int IX = TX + K - 1, IY = TY + K - 1, IZ = TZ + K - 1;
+  static constexpr int PZ = ((IZ + 3) / 4) * 4;
+  static constexpr int CH = IX * IY * PZ; /* floats per staged channel */
+  static size_t bytes(int cc) { return sizeof(float) * (size_t)cc * (CH + 27 * CO); }
+};
+
+/* VEC = floats per staging access: 4 (forward, n_in % 4 == 0), 2 (n_in even: every dgrad of a
+ * decoder whose stage sizes are even), 1 (anything).  A staging "slot" is VEC consecutive z of one
+ * (channel, x, y) row of the tile; every slot of the tile is written (zero outside the volume),
+ * so there is no separate clearing pass.  First version: per-element staging with 2 slots per
+ * thread and plane -- ~29 instructions per element, 43 % of all instructions executed
+ * (profiles/r01j_ncu_decoder.txt: 127 M warp instructions for 56 M warp-FFMAs). */
+template <int CO, int ZR, bool DGRAD, int VEC>
+__global__ void __launch_bounds__(256, (CO * ZR <= 16 ? 4 : (CO * ZR <= 32 ? 3 : (CO * ZR <= 64 ? 2 : 1))))
 sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
-  constexpr int K = 3, TX = 4, TY = 8, TZ = 8 * ZR, CC = 4;
-  constexpr int IX = TX + K - 1, IY = TY + K - 1, IZ = TZ + K - 1;
-  constexpr int PZ = ((IZ + 2) / 4) * 4 + 1; /* = 1 (mod 4): the 32 lanes of a warp hit 32 banks */
-  __shared__ float tile[CC][IX][IY][PZ];
-  __shared__ __align__(16) float ws[CC][K * K * K][CO];
+  using T = ConvTile<CO, ZR>;
+  constexpr int K = 3, TX = T::TX, TY = T::TY, TZ = T::TZ, CC = T::CC;
+  constexpr int IX = T::IX, IY = T::IY, PZ = T::PZ;
+  extern __shared__ __align__(16) float conv_smem[];
+  float* __restrict__ tile = conv_smem;          /* [CC][IX][IY][PZ] */
+  float* __restrict__ ws = conv_smem + P.cc * T::CH;  /* [CC][27][CO] */
 
   const int b = blockIdx.y + P.z_offset;
   int t = blockIdx.x;
@@ -373,7 +392,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   const int z0 = zr * ZR;
   const int n_in = P.n_in, n_out = P.n_out, CI = P.CI;
   const size_t in_vol = (size_t)n_in * n_in * n_in;
-  const int shift = DGRAD ? K - 1 : 0; /* input coordinate = output coordinate + tap - shift */
+  constexpr int shift = DGRAD ? K - 1 : 0; /* input coordinate = output coordinate + tap - shift */
 
   float acc[CO][ZR];
 #pragma unroll
@@ -381,48 +400,49 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
     for (int i = 0; i < ZR; ++i) acc[co][i] = 0.0f;
 
-  /* staging plan, fixed for the whole kernel: within one (channel, x) plane of the input tile this
-   * thread copies the (y, z) elements number threadIdx.x and threadIdx.x + 256 (IY * IZ <= 512);
-   * only the plane base changes from plane to plane */
-  static_assert(IY * IZ <= 512, "two staging slots per thread");
-  int s_goff[2], s_soff[2];
-  bool s_ok[2];
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    const int e = threadIdx.x + 256 * k;
-    const int y = e / IZ, z = e - y * IZ;
-    const int gy = Y0 + y - shift, gz = Z0 + z - shift;
-    s_ok[k] = e < IY * IZ && gy >= 0 && gy < n_in && gz >= 0 && gz < n_in;
-    s_goff[k] = gy * n_in + gz;
-    s_soff[k] = e < IY * IZ ? y * PZ + z : -1;
-  }
-
   for (int ci0 = 0; ci0 < CI; ci0 += CC) {
     const int nc = CI - ci0 < CC ? CI - ci0 : CC;
-    /* stage the input tile (zero outside the volume): all loads of one channel are issued before
-     * the first store -- the kernel is bound by the latency of these loads, not by their count */
-    constexpr int XB = DGRAD ? IX / 2 : IX; /* x-planes per batch: 12 loads in flight either way */
-    for (int cx = 0; cx < nc * (IX / XB); ++cx) {
-      const int c = cx / (IX / XB), xb = (cx - c * (IX / XB)) * XB;
-      const size_t cbase = ((size_t)b * CI + ci0 + c) * in_vol;
-      float v[XB][2], m[XB][2];
-#pragma unroll
-      for (int x = 0; x < XB; ++x) {
-        const int gx = X0 + xb + x - shift;
-        const bool xok = gx >= 0 && gx < n_in;
-        const size_t pbase = cbase + (size_t)(xok ? gx : 0) * n_in * n_in;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const bool ok = xok && s_ok[k];
-          v[x][k] = ok ? __ldg(P.in + pbase + s_goff[k]) : 0.0f;
-          m[x][k] = (DGRAD && P.mask && ok) ? __ldg(P.mask + pbase + s_goff[k]) : 1.0f;
+    /* stage the input tile */
+    constexpr int SL = PZ / VEC; /* slots per row */
+    const int n_slots = nc * IX * IY * SL;
+    const float* __restrict__ src = P.in + ((size_t)b * CI + ci0) * in_vol;
+    const float* __restrict__ msk = (DGRAD && P.mask) ? P.mask + ((size_t)b * CI + ci0) * in_vol : nullptr;
+    for (int e = threadIdx.x; e < n_slots; e += 256) {
+      const int row = e / SL, j = (e - row * SL) * VEC;
+      const int c = row / (IX * IY), r2 = row - c * (IX * IY);
+      const int x = r2 / IY, y = r2 - x * IY;
+      const int gx = X0 + x - shift, gy = Y0 + y - shift, gz = Z0 + j - shift;
+      const bool ok = gx >= 0 && gx < n_in && gy >= 0 && gy < n_in && gz >= 0 && gz < n_in;
+      const size_t g = (size_t)c * in_vol + ((size_t)gx * n_in + gy) * n_in + gz;
+      float* __restrict__ d = tile + ((c * IX + x) * IY + y) * PZ + j;
+      if constexpr (VEC == 4) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          v = __ldg(reinterpret_cast<const float4*>(src + g));
+          if (msk) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(msk + g));
+            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+            v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+          }
         }
-      }
-#pragma unroll
-      for (int x = 0; x < XB; ++x) {
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          if (s_soff[k] >= 0) (&tile[c][xb + x][0][0])[s_soff[k]] = m[x][k] > 0.0f ? v[x][k] : 0.0f;
+        *reinterpret_cast<float4*>(d) = v;
+      } else if constexpr (VEC == 2) {
+        float2 v = make_float2(0.f, 0.f);
+        if (ok) {
+          v = __ldg(reinterpret_cast<const float2*>(src + g));
+          if (msk) {
+            const float2 m = __ldg(reinterpret_cast<const float2*>(msk + g));
+            v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+          }
+        }
+        *reinterpret_cast<float2*>(d) = v;
+      } else {
+        float v = 0.f;
+        if (ok) {
+          v = __ldg(src + g);
+          if (msk) v = __ldg(msk + g) > 0.f ? v : 0.f;
+        }
+        *d = v;
       }
     }
     /* stage the weights of these input channels as [c][tap][co] */
@@ -433,7 +453,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
       float v;
       if (!DGRAD) v = __ldg(P.w + ((size_t)co * CI + ci0 + c) * 27 + tap);
       else v = __ldg(P.w + ((size_t)(ci0 + c) * CO + co) * 27 + (26 - tap)); /* w[co_orig = in ch][ci_orig = out ch], flipped */
-      ws[c][tap][co] = v;
+      ws[e] = v;
     }
     __syncthreads();
     for (int c = 0; c < nc; ++c) {
@@ -442,23 +462,39 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
         for (int dy = 0; dy < K; ++dy) {
           float v[ZR + K - 1];
-          const float* __restrict__ row = &tile[c][lx + dx][ly + dy][z0];
+          const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly + dy) * PZ + z0;
+          if constexpr (ZR == 4) {
+            const float4 a = *reinterpret_cast<const float4*>(row);
+            const float2 e2 = *reinterpret_cast<const float2*>(row + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e2.x; v[5] = e2.y;
+          } else if constexpr (ZR == 2) {
+            const float2 a = *reinterpret_cast<const float2*>(row);
+            const float2 e2 = *reinterpret_cast<const float2*>(row + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = e2.x; v[3] = e2.y;
+          } else {
 #pragma unroll
-          for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
+            for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
+          }
 #pragma unroll
           for (int dz = 0; dz < K; ++dz) {
-            const float* __restrict__ wp = &ws[c][(dx * K + dy) * K + dz][0];
+            const float4* __restrict__ wp =
+                reinterpret_cast<const float4*>(ws + (c * 27 + (dx * K + dy) * K + dz) * CO);
 #pragma unroll
-            for (int co = 0; co < CO; ++co) {
-              const float wv = wp[co];
+            for (int c4 = 0; c4 < CO / 4; ++c4) {
+              const float4 w4 = wp[c4];
 #pragma unroll
-              for (int i = 0; i < ZR; ++i) acc[co][i] = fmaf(wv, v[i + dz], acc[co][i]);
+              for (int i = 0; i < ZR; ++i) {
+                acc[4 * c4 + 0][i] = fmaf(w4.x, v[i + dz], acc[4 * c4 + 0][i]);
+                acc[4 * c4 + 1][i] = fmaf(w4.y, v[i + dz], acc[4 * c4 + 1][i]);
+                acc[4 * c4 + 2][i] = fmaf(w4.z, v[i + dz], acc[4 * c4 + 2][i]);
+                acc[4 * c4 + 3][i] = fmaf(w4.w, v[i + dz], acc[4 * c4 + 3][i]);
+              }
             }
           }
         }
       }
     }
-    __syncthreads();
+    if (ci0 + CC < CI) __syncthreads();
   }
 
   const int ox = X0 + lx, oy = Y0 + ly;
@@ -480,40 +516,60 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   }
 }
 
-template <int CO, int ZR, bool DGRAD>
-void launch_conv3_t(ConvParams P, int batch, cudaStream_t s) {
-  constexpr int TX = 4, TY = 8, TZ = 8 * ZR;
-  const int tiles_x = (P.n_out + TX - 1) / TX;
-  P.tiles_y = (P.n_out + TY - 1) / TY;
-  P.tiles_z = (P.n_out + TZ - 1) / TZ;
+template <int CO, int ZR, bool DGRAD, int VEC>
+int launch_conv3_v(ConvParams P, int batch, cudaStream_t s) {
+  using T = ConvTile<CO, ZR>;
+  const int tiles_x = (P.n_out + T::TX - 1) / T::TX;
+  P.tiles_y = (P.n_out + T::TY - 1) / T::TY;
+  P.tiles_z = (P.n_out + T::TZ - 1) / T::TZ;
+  P.cc = P.CI < T::CC ? P.CI : T::CC;
+  const size_t smem = T::bytes(P.cc);
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(sdfr_conv3_kernel<CO, ZR, DGRAD, VEC>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "conv3d: shared memory opt-in failed");
+  }
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535);
-    sdfr_conv3_kernel<CO, ZR, DGRAD><<<grid, 256, 0, s>>>(P);
+    sdfr_conv3_kernel<CO, ZR, DGRAD, VEC><<<grid, 256, smem, s>>>(P);
   }
+  return 0;
+}
+
+/* widest staging access the operands allow: rows start at multiples of n_in elements and tiles at
+ * multiples of 8 (minus 2 for dgrad), so alignment follows from n_in and the base pointers */
+template <int CO, int ZR, bool DGRAD>
+int launch_conv3_t(const ConvParams& P, int batch, cudaStream_t s) {
+  const uintptr_t a = reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.mask);
+  if constexpr (!DGRAD)
+    if (P.n_in % 4 == 0 && (a & 15) == 0) return launch_conv3_v<CO, ZR, DGRAD, 4>(P, batch, s);
+  if (P.n_in % 2 == 0 && (a & 7) == 0) return launch_conv3_v<CO, ZR, DGRAD, 2>(P, batch, s);
+  return launch_conv3_v<CO, ZR, DGRAD, 1>(P, batch, s);
 }
 
 /* z-extent of the CTA tile (8 * ZR) follows the volume: 32 for n_out > 16, 16 for > 8, else 8 --
  * a 14^3 output in 32-deep tiles would leave 56 % of the lanes idle */
 template <int CO, bool DGRAD>
-void launch_conv3_zr(const ConvParams& P, int batch, cudaStream_t s) {
-  if (P.n_out > 16 && CO <= 16) launch_conv3_t<CO, (CO <= 16 ? 4 : 2), DGRAD>(P, batch, s);
-  else if (P.n_out > 8) launch_conv3_t<CO, 2, DGRAD>(P, batch, s);
-  else launch_conv3_t<CO, 1, DGRAD>(P, batch, s);
+int launch_conv3_zr(const ConvParams& P, int batch, cudaStream_t s) {
+  if (P.n_out > 16 && CO <= 16) return launch_conv3_t<CO, (CO <= 16 ? 4 : 2), DGRAD>(P, batch, s);
+  if (P.n_out > 8) return launch_conv3_t<CO, 2, DGRAD>(P, batch, s);
+  return launch_conv3_t<CO, 1, DGRAD>(P, batch, s);
 }
 
 /* CO = output channels of THIS launch (forward: Co; dgrad: Ci of the layer) */
 template <bool DGRAD>
 int launch_conv3(ConvParams P, int CO, int batch, cudaStream_t s) {
+  int rc = 0;
   switch (CO) {
-    case 4: launch_conv3_zr<4, DGRAD>(P, batch, s); break;
-    case 8: launch_conv3_zr<8, DGRAD>(P, batch, s); break;
-    case 16: launch_conv3_zr<16, DGRAD>(P, batch, s); break;
-    case 32: launch_conv3_zr<32, DGRAD>(P, batch, s); break;
+    case 4: rc = launch_conv3_zr<4, DGRAD>(P, batch, s); break;
+    case 8: rc = launch_conv3_zr<8, DGRAD>(P, batch, s); break;
+    case 16: rc = launch_conv3_zr<16, DGRAD>(P, batch, s); break;
+    case 32: rc = launch_conv3_zr<32, DGRAD>(P, batch, s); break;
     default:
       return fail(SDFR_E_SHAPE, "conv3d: this launch's output channels must be 4, 8, 16 or 32");
   }
-  return check_launch("sdfr_conv3_kernel");
+  return rc ? rc : check_launch("sdfr_conv3_kernel");
 }
 
 #endif /* SDFR_DECODER_CUH_ */

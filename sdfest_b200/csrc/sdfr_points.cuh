@@ -46,7 +46,7 @@ struct PointParams {
   int z_offset;
 };
 
-template <bool BACKWARD, bool WANT_SDF, bool WANT_POSE>
+template <bool BACKWARD, bool WANT_SDF, bool WANT_POSE, bool WITH_LOSS = false>
 __global__ void __launch_bounds__(256)
 sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   __shared__ float red[8][9];
@@ -73,7 +73,7 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   const float half_rm1 = G.Rm1f * 0.5f;
   const float rm2f = (float)G.Rm2;
 
-  float acc[9]; /* forward: [0] = sum |val|;  backward: g_t (3), g_q (4), g_s (1) */
+  float acc[9]; /* forward: [0] = sum |val|;  backward: g_t (3), g_q (4), g_s (1), [8] = sum |val| (WITH_LOSS) */
 #pragma unroll
   for (int i = 0; i < 9; ++i) acc[i] = 0.0f;
 
@@ -103,6 +103,7 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
       acc[0] += fabsf(val);
       continue;
     }
+    if (WITH_LOSS) acc[8] += fabsf(val);
     if (val == 0.0f) continue; /* d|.|/d. = 0 at 0, as torch.abs */
     const float g = val > 0.0f ? up : -up; /* d L / d val */
     if (WANT_SDF) {
@@ -147,8 +148,8 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   }
 
   /* CTA reduction: one value (forward) or eight (backward) */
-  constexpr int NV = BACKWARD ? 8 : 1;
-  if constexpr (!BACKWARD || WANT_POSE) {
+  constexpr int NV = BACKWARD ? (WITH_LOSS ? 9 : 8) : 1;
+  if constexpr (!BACKWARD || WANT_POSE || WITH_LOSS) {
 #pragma unroll
   for (int i = 0; i < NV; ++i) acc[i] = warp_sum(acc[i]);
   if (lane == 0) {
@@ -157,7 +158,7 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float t[8];
+    float t[9];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       float v = 0.0f;
@@ -167,6 +168,7 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
     if (!BACKWARD) {
       if (t[0] != 0.0f) atomicAdd(P.loss_sum + b, t[0]);
     } else {
+      if (WITH_LOSS && t[8] != 0.0f) atomicAdd(P.loss_sum + b, t[8]);
       if (P.flags & SDFR_GRAD_POSITION) {
         if (t[0] != 0.0f) atomicAdd(P.grad_position + 3 * b + 0, t[0]);
         if (t[1] != 0.0f) atomicAdd(P.grad_position + 3 * b + 1, t[1]);
@@ -188,25 +190,25 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   }
 }
 
-template <bool BACKWARD>
+template <bool BACKWARD, bool WITH_LOSS = false>
 int launch_point_loss(PointParams P, int batch, cudaStream_t s) {
   int gx = (P.n_points + 255) / 256;
   gx = gx < 1 ? 1 : (gx > 512 ? 512 : gx);
   const bool want_sdf = (P.flags & SDFR_GRAD_SDF) != 0;
   const bool want_pose =
       (P.flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
-  if (BACKWARD && !want_sdf && !want_pose) return 0;
+  if (BACKWARD && !WITH_LOSS && !want_sdf && !want_pose) return 0;
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid(gx, batch - z0 < 65535 ? batch - z0 : 65535);
-    if (!BACKWARD)
+    if (!BACKWARD || (!want_sdf && !want_pose))
       sdfr_point_loss_kernel<false, false, false><<<grid, 256, 0, s>>>(P);
     else if (want_sdf && want_pose)
-      sdfr_point_loss_kernel<true, true, true><<<grid, 256, 0, s>>>(P);
+      sdfr_point_loss_kernel<true, true, true, WITH_LOSS><<<grid, 256, 0, s>>>(P);
     else if (want_sdf)
-      sdfr_point_loss_kernel<true, true, false><<<grid, 256, 0, s>>>(P);
+      sdfr_point_loss_kernel<true, true, false, WITH_LOSS><<<grid, 256, 0, s>>>(P);
     else
-      sdfr_point_loss_kernel<true, false, true><<<grid, 256, 0, s>>>(P);
+      sdfr_point_loss_kernel<true, false, true, WITH_LOSS><<<grid, 256, 0, s>>>(P);
   }
   return check_launch("sdfr_point_loss_kernel");
 }

@@ -1106,6 +1106,7 @@ BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_
 
 #include "sdfr_points.cuh"
 #include "sdfr_decoder.cuh"
+#include "sdfr_step.cuh"
 
 }  // namespace
 
@@ -1399,6 +1400,78 @@ int sdfr_point_loss_backward(const float* points, long long points_stride, int n
   P.grad_position = gp; P.grad_orientation = gq; P.grad_scale = gscale;
   P.flags = flags;
   return launch_point_loss<true>(P, batch, s);
+}
+
+int sdfr_point_loss_fused(const float* points, long long points_stride, int n_points,
+                          const float* sdf, int R, long long sdf_stride, int layout,
+                          const float* pos, const float* quat, const float* scale, int batch,
+                          const float* upstream, float* loss_sum, float* gs, long long gs_stride,
+                          float* gp, float* gq, float* gscale, unsigned flags, void* stream) {
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, scale, batch, 1, 1)) return rc;
+  if (flags & SDFR_SDF_GRAD_EXACT) return fail(SDFR_E_FLAGS, "the point loss has one weight list");
+  if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gscale)) return rc;
+  if (n_points < 0 || points_stride < 0) return fail(SDFR_E_SHAPE, "negative n_points or stride");
+  if (batch == 0) return 0;
+  if (!loss_sum) return fail(SDFR_E_NULL, "loss_sum is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & SDFR_ZERO_GRADS)
+    if (int rc = zero_async(loss_sum, sizeof(float) * batch, s)) return rc;
+  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gscale, s)) return rc;
+  if (n_points == 0) return 0;
+  if (!points) return fail(SDFR_E_NULL, "points is NULL");
+  PointParams P;
+  memset(&P, 0, sizeof(P));
+  P.points = points; P.points_stride = points_stride; P.n_points = n_points;
+  P.sdf = sdf; P.sdf_stride = sdf_stride; P.grid = make_grid(R, layout);
+  P.position = pos; P.orientation = quat; P.scale = scale;
+  P.upstream = upstream;
+  P.loss_sum = loss_sum;
+  P.grad_sdf = gs; P.grad_sdf_stride = gs_stride;
+  P.grad_position = gp; P.grad_orientation = gq; P.grad_scale = gscale;
+  P.flags = flags;
+  return launch_point_loss<true, true>(P, batch, s);
+}
+
+int sdfr_hypothesis_step(float* position, float* orientation, float* scale, float* latent,
+                         int latent_size, int batch, float* loss_sum, float* n_overlap,
+                         float* gr_position, float* gr_orientation, float* gr_inv_scale,
+                         float depth_weight, float* point_sum, float point_weight,
+                         float* g2_position, float* g2_orientation, float* g2_scale,
+                         float* g_latent, float* exp_avg, float* exp_avg_sq, int* step,
+                         const float* lr, float beta1, float beta2, float eps,
+                         float* unit_orientation, float* inv_scale, float* loss, unsigned flags,
+                         void* stream) {
+  if (flags & ~(SDFR_STEP_CLEAR_INPUTS | SDFR_STEP_NO_UPDATE)) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (batch < 0 || latent_size < 0 || latent_size > kStepMaxLatent)
+    return fail(SDFR_E_SHAPE, "hypothesis step: batch >= 0 and 0 <= latent_size <= 64 expected");
+  if (batch == 0) return 0;
+  if (!position || !orientation || !scale) return fail(SDFR_E_NULL, "hypothesis step: NULL parameter pointer");
+  const bool update = !(flags & SDFR_STEP_NO_UPDATE);
+  if (update && (!exp_avg || !exp_avg_sq || !step || !lr))
+    return fail(SDFR_E_NULL, "hypothesis step: NULL optimiser state or learning rates");
+  if (loss_sum && !n_overlap) return fail(SDFR_E_NULL, "hypothesis step: loss_sum without n_overlap");
+  if ((gr_position || gr_orientation || gr_inv_scale) && !n_overlap)
+    return fail(SDFR_E_NULL, "hypothesis step: raw render gradients without n_overlap");
+  StepParams P;
+  memset(&P, 0, sizeof(P));
+  P.position = position; P.orientation = orientation; P.scale = scale;
+  P.latent = latent_size > 0 ? latent : nullptr;
+  P.latent_size = (latent && g_latent) ? latent_size : 0;
+  P.state_stride = 8 + latent_size;
+  P.batch = batch;
+  P.loss_sum = loss_sum; P.n_overlap = n_overlap;
+  P.gr_position = gr_position; P.gr_orientation = gr_orientation; P.gr_inv_scale = gr_inv_scale;
+  P.depth_weight = depth_weight;
+  P.point_sum = point_sum; P.point_weight = point_weight;
+  P.g2_position = g2_position; P.g2_orientation = g2_orientation; P.g2_scale = g2_scale;
+  P.g_latent = P.latent_size > 0 ? g_latent : nullptr;
+  P.exp_avg = exp_avg; P.exp_avg_sq = exp_avg_sq; P.step = step;
+  if (lr) for (int i = 0; i < 4; ++i) P.lr[i] = lr[i];
+  P.beta1 = beta1; P.beta2 = beta2; P.eps = eps;
+  P.unit_orientation = unit_orientation; P.inv_scale = inv_scale; P.loss = loss;
+  P.flags = flags;
+  sdfr_hypothesis_step_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("sdfr_hypothesis_step_kernel");
 }
 
 int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const float* weight,

@@ -201,6 +201,40 @@ def trunk_stage(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tens
     return _TrunkStage.apply(x.contiguous(), weight, bias, in_size, relu)
 
 
+class _FrozenLinearReLU(torch.autograd.Function):
+    """``relu(x @ W^T + b)`` of a frozen fully-connected layer whose backward splits the long
+    contraction.  The decoder's last fc layer maps 50 -> 8192 features (mug.yaml:2-4), so its data
+    gradient is a (B x 8192) @ (8192 x 50) product: one output tile, 8192 deep -- cuBLAS runs it as a
+    single-CTA-per-tile kernel in 61 us for B = 64 (profiles/r01q_loop_ops_fused_iteration.txt).
+    Cutting the 8192 into ``_SPLIT`` independent slices (one strided-batched GEMM) and adding the
+    partial products takes ~8 us.  Still cuBLAS: the fc stack is not a kernel target."""
+
+    _SPLIT = 32
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        y = torch.relu(torch.addmm(bias, x, weight.t()))
+        ctx.save_for_backward(y, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        y, weight = ctx.saved_tensors
+        g = grad_y * (y > 0)
+        B, K = g.shape
+        S = _FrozenLinearReLU._SPLIT
+        parts = torch.bmm(g.view(B, S, K // S).transpose(0, 1), weight.view(S, K // S, weight.shape[1]))
+        return parts.sum(0), None, None
+
+
+def _fc_relu(layer: nn.Linear, x: torch.Tensor) -> torch.Tensor:
+    if (x.is_cuda and x.requires_grad and layer.bias is not None and not layer.weight.requires_grad
+            and layer.out_features >= 2048 and layer.out_features % _FrozenLinearReLU._SPLIT == 0
+            and layer.weight.is_contiguous()):
+        return _FrozenLinearReLU.apply(x, layer.weight, layer.bias)
+    return torch.relu(layer(x))
+
+
 _CUDA_TRUNK_CHANNELS = (4, 8, 16, 32)
 
 
@@ -279,7 +313,7 @@ class FusedTailDecoder(nn.Module):
         """Everything before the last stage's interpolation: (B,L) -> (B,C,S,S,S)."""
         out = z
         for layer in self._fc:
-            out = torch.relu(layer(out))
+            out = _fc_relu(layer, out)
         c0, s0 = self._conv[0].in_channels, self._info[0][0]
         out = out.view(-1, c0, s0, s0, s0)
         if self.trunk_impl == "cuda" and out.is_cuda:

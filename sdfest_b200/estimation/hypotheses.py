@@ -9,12 +9,16 @@ all_gather of the per-hypothesis losses (the reference has no distributed code a
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Callable, Optional
 
 import torch
 import torch.distributed as dist
 
+from .. import _lib
 from ..differentiable_renderer import Camera, render_and_compare
+from ..differentiable_renderer.sdf_renderer import (_camera_params, _grid_operand, _ptr,
+                                                    _skewed_elems, _stream)
 from . import losses
 from .decoder import FusedTailDecoder
 from .fused import decode_render_compare
@@ -64,15 +68,31 @@ class HypothesisOptimizer:
     Learning rates and loss weights default to the reference's (simple_setup.py:400-405,
     estimation/configs/default.yaml:14-16).  ``decoder`` maps latents (B,L) to grids
     (B,1,R,R,R) (e.g. ``SDFVAE.decode``); without it ``sdf`` holds fixed grids (B|1,R,R,R).
+
+    ``optimizer``: ``"fused"`` runs the whole iteration as direct C-ABI launches -- decoder tail,
+    ``sdfr_compare_fused``, ``sdfr_point_loss_fused``, tail adjoint, and ONE
+    ``sdfr_hypothesis_step`` kernel for the gradient chain rule, Adam on all four groups, the
+    quaternion renormalisation and the loss (autograd only carries the tail's gradient through the
+    decoder trunk); ``"torch"`` composes the package's autograd operators with
+    ``torch.optim.Adam`` (~60 more 1-2 us launches per iteration).  ``"auto"`` (default) picks
+    ``"fused"`` for CUDA tensors with fixed grids or a ``FusedTailDecoder``.
     """
 
     def __init__(self, camera: Camera, threshold: float, depth_obs: torch.Tensor,
                  position: torch.Tensor, orientation: torch.Tensor, scale: torch.Tensor,
                  sdf: Optional[torch.Tensor] = None, latent: Optional[torch.Tensor] = None,
                  decoder: Optional[Callable] = None, depth_weight: float = 1.0,
-                 pc_weight: float = 3.0, max_points: int = 0, group=None):
+                 pc_weight: float = 3.0, max_points: int = 0, group=None, optimizer: str = "auto",
+                 lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
+        if optimizer not in ("auto", "fused", "torch"):
+            raise ValueError("optimizer must be 'auto', 'fused' or 'torch'")
+        can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder))
+        if optimizer == "fused" and not can_fuse:
+            raise ValueError("optimizer='fused' needs CUDA tensors and fixed grids or a FusedTailDecoder")
+        self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
+        self.lrs, self.betas, self.eps = tuple(float(x) for x in lrs), tuple(betas), float(eps)
         self.camera, self.threshold, self.group = camera, float(threshold), group
         self.depth_obs = depth_obs.contiguous()
         self.depth_weight, self.pc_weight = depth_weight, pc_weight
@@ -80,13 +100,17 @@ class HypothesisOptimizer:
         self.orientation = orientation.detach().clone().requires_grad_(True)
         self.scale = scale.detach().clone().requires_grad_(True)
         self.decoder, self.sdf = decoder, sdf
-        groups = [{"params": [self.position], "lr": 1e-3}, {"params": [self.orientation], "lr": 1e-2},
-                  {"params": [self.scale], "lr": 1e-3}]
+        groups = [{"params": [self.position], "lr": self.lrs[0]},
+                  {"params": [self.orientation], "lr": self.lrs[1]},
+                  {"params": [self.scale], "lr": self.lrs[2]}]
         self.latent = None
         if decoder is not None:
             self.latent = latent.detach().clone().requires_grad_(True)
-            groups.append({"params": [self.latent], "lr": 1e-2})
-        self.optimizer = torch.optim.Adam(groups, capturable=self.position.is_cuda)
+            groups.append({"params": [self.latent], "lr": self.lrs[3]})
+        self.optimizer = None
+        if self.optimizer_impl == "torch":
+            self.optimizer = torch.optim.Adam(groups, betas=self.betas, eps=self.eps,
+                                              capturable=self.position.is_cuda)
         # observed points, once (the only host sync), sub-sampled to a fixed size
         pts = losses.depth_to_pointcloud(self.depth_obs, camera)
         if max_points and pts.shape[0] > max_points:
@@ -96,6 +120,126 @@ class HypothesisOptimizer:
         self.points = pts.contiguous()
         self.last_losses = None
         self._graph = None
+        if self.optimizer_impl == "fused":
+            self._init_fused()
+
+    # ------------------------------------------------------------------------------------
+    # optimizer="fused": one iteration = a handful of C-ABI launches, no autograd outside the trunk
+    # ------------------------------------------------------------------------------------
+    def _init_fused(self) -> None:
+        B, dev = self.position.shape[0], self.position.device
+        for t, shape in ((self.position, (B, 3)), (self.orientation, (B, 4))):
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"position (B,3) and orientation (B,4) expected, got {tuple(t.shape)}")
+        if self.scale.numel() != B:
+            raise RuntimeError("scale must have one element per hypothesis")
+        for t in (self.position, self.orientation, self.scale):
+            t.requires_grad_(False)  # updated in place by sdfr_hypothesis_step
+        L = 0 if self.latent is None else int(self.latent.shape[1])
+        self._L = L
+        W, H = int(self.camera.width), int(self.camera.height)
+        if tuple(self.depth_obs.shape) == (H, W):
+            self._obs_stride = 0
+        elif tuple(self.depth_obs.shape) == (B, H, W):
+            self._obs_stride = H * W
+        else:
+            raise RuntimeError(f"depth_obs must have shape ({H},{W}) or ({B},{H},{W})")
+        # every small per-hypothesis buffer in one allocation: consumed AND cleared by the step kernel
+        small = torch.zeros(20 * B, dtype=torch.float32, device=dev)
+        cuts = (("loss_sum", 1), ("n_overlap", 1), ("gr_p", 3), ("gr_q", 4), ("gr_is", 1),
+                ("pl", 1), ("g2_p", 3), ("g2_q", 4), ("g2_s", 1))
+        off, self._buf = 0, {}
+        for name, k in cuts:
+            self._buf[name] = small[off:off + k * B]
+            off += k * B
+        self._small = small
+        self._unit_q = torch.empty((B, 4), dtype=torch.float32, device=dev)
+        self._inv_scale = torch.empty((B,), dtype=torch.float32, device=dev)
+        self._loss = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self._m = torch.zeros((B, 8 + L), dtype=torch.float32, device=dev)
+        self._v = torch.zeros((B, 8 + L), dtype=torch.float32, device=dev)
+        self._t = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self._lr = (ctypes.c_float * 4)(*self.lrs)
+        self._depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        M = int(self.points.shape[0]) if self.pc_weight else 0
+        self._M = M
+        self._up_p = torch.full((B,), (self.pc_weight / M) if M else 0.0, dtype=torch.float32, device=dev)
+        self._up_d = torch.full((B,), float(self.depth_weight), dtype=torch.float32, device=dev)
+        if self.decoder is None:
+            sdf = self.sdf.contiguous()
+            R = int(sdf.shape[-1])
+            stride = 0 if sdf.shape[0] == 1 else R ** 3
+            self._R = R
+            self._grids = _grid_operand(sdf, R, stride, B, W * H)  # (tensor, stride, layout), made once
+            self._g_sdf = self._g_sdf_pc = None
+        else:
+            R = int(self.decoder.volume_size)
+            self._R = R
+            SK = _skewed_elems(R)
+            self._grids = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
+            self._g_sdf = torch.empty((B, R ** 3), dtype=torch.float32, device=dev)
+            self._g_sdf_pc = torch.empty((B, R ** 3), dtype=torch.float32, device=dev) if M else None
+        self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale for the first render
+
+    def _hyp_step(self, flags: int, g_latent: Optional[torch.Tensor] = None) -> None:
+        b, B = self._buf, self.position.shape[0]
+        M = self._M
+        _lib.check(_lib.lib().sdfr_hypothesis_step(
+            self.position.data_ptr(), self.orientation.data_ptr(), self.scale.data_ptr(),
+            _ptr(self.latent), self._L, B, b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(),
+            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), float(self.depth_weight),
+            b["pl"].data_ptr() if M else None, (self.pc_weight / M) if M else 0.0,
+            b["g2_p"].data_ptr() if M else None, b["g2_q"].data_ptr() if M else None,
+            b["g2_s"].data_ptr() if M else None, _ptr(g_latent), self._m.data_ptr(),
+            self._v.data_ptr(), self._t.data_ptr(), self._lr, self.betas[0], self.betas[1], self.eps,
+            self._unit_q.data_ptr(), self._inv_scale.data_ptr(), self._loss.data_ptr(), flags,
+            _stream()), "sdfr_hypothesis_step")
+
+    def _fused_iteration(self) -> torch.Tensor:
+        lib, b, st = _lib.lib(), self._buf, _stream()
+        B, R, M = self.position.shape[0], self._R, self._M
+        W, H, cx, cy, fx, fy = _camera_params(self.camera)
+        grids, gstride, layout = self._grids
+        dec, x = self.decoder, None
+        if dec is not None:
+            x = dec.trunk(self.latent).contiguous()  # autograd graph: latent -> x only
+            w, bias = dec.tail_parameters()
+            C, S = int(x.shape[1]), int(x.shape[2])
+            _lib.check(lib.sdfr_decoder_tail_forward(
+                x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
+                gstride, layout, st), "sdfr_decoder_tail_forward")
+            self._g_sdf.zero_()
+            if self._g_sdf_pc is not None:
+                self._g_sdf_pc.zero_()
+        flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
+        if dec is not None:
+            flags |= _lib.GRAD_SDF
+        _lib.check(lib.sdfr_compare_fused(
+            grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
+            self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
+            self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
+            b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), _ptr(self._g_sdf), R ** 3,
+            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, st),
+            "sdfr_compare_fused")
+        if M:
+            _lib.check(lib.sdfr_point_loss_fused(
+                self.points.data_ptr(), 0, M, grids.data_ptr(), R, gstride, layout,
+                self.position.data_ptr(), self._unit_q.data_ptr(), self.scale.data_ptr(), B,
+                self._up_p.data_ptr(), b["pl"].data_ptr(), _ptr(self._g_sdf_pc), R ** 3,
+                b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(), flags, st),
+                "sdfr_point_loss_fused")
+        g_latent = None
+        if dec is not None:
+            g_x = torch.empty_like(x)
+            _lib.check(lib.sdfr_decoder_tail_backward(
+                self._g_sdf.data_ptr(), R ** 3, b["n_overlap"].data_ptr(), self._up_d.data_ptr(),
+                _ptr(self._g_sdf_pc), R ** 3, w.data_ptr(), C, S, B, R, g_x.data_ptr(), st),
+                "sdfr_decoder_tail_backward")
+            (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
+            g_latent = g_latent.contiguous()
+        self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent)
+        self.last_losses = self._loss
+        return self.last_losses
 
     def _grids(self):
         if self.decoder is None:
@@ -118,7 +262,8 @@ class HypothesisOptimizer:
                 self._eager_step()
         torch.cuda.current_stream().wait_stream(side)
         graph = torch.cuda.CUDAGraph()
-        self.optimizer.zero_grad(set_to_none=True)
+        if self.optimizer is not None:
+            self.optimizer.zero_grad(set_to_none=True)
         with torch.cuda.graph(graph):
             self._static_loss = self._eager_step()
         self._graph = graph
@@ -144,6 +289,8 @@ class HypothesisOptimizer:
         return loss
 
     def _eager_step(self) -> torch.Tensor:
+        if self.optimizer_impl == "fused":
+            return self._fused_iteration()
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda:

@@ -31,6 +31,9 @@ def phase_breakdown(opt: HypothesisOptimizer, iterations: int = 10, warmup: int 
     from ..differentiable_renderer import render_and_compare
     from . import losses
 
+    if opt.optimizer is None:
+        raise ValueError("phase_breakdown times the composed path: build the HypothesisOptimizer with "
+                         "optimizer='torch' (the fused iteration has no phase boundaries to time)")
     acc = dict.fromkeys(PHASES, 0.0)
     for it in range(warmup + iterations):
         opt.optimizer.zero_grad(set_to_none=True)

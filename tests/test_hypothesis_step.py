@@ -1,0 +1,287 @@
+"""sdfr_hypothesis_step (ABI v6) and sdfr_point_loss_fused: the optimiser side of the loop.
+
+CPU: the numpy oracle (oracle/hypothesis_step.py) is pinned against torch autograd through the
+reference's chain (simple_setup.py:411, :431, :447-452) followed by torch.optim.Adam.step() and the
+renormalisation (:462).  GPU: the kernel against that oracle; the fused optimiser against the
+torch-composed one.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hypothesis_step as hs
+
+LRS = (1e-3, 1e-2, 1e-3, 1e-2)
+
+
+def _random_case(B, L, seed, with_points=True):
+    rng = np.random.default_rng(seed)
+    c = dict(
+        position=rng.normal(0, 0.3, (B, 3)), orientation=rng.normal(0, 1, (B, 4)),
+        scale=rng.uniform(0.1, 0.3, B), latent=rng.normal(0, 1, (B, L)) if L else None,
+        loss_sum=rng.uniform(0, 50, B), n_overlap=rng.integers(0, 3, B) * rng.integers(1, 5000, B),
+        gr_p=rng.normal(0, 300, (B, 3)), gr_q=rng.normal(0, 300, (B, 4)), gr_is=rng.normal(0, 30, B),
+        g_latent=rng.normal(0, 1e-3, (B, L)) if L else None)
+    c["orientation"] /= np.linalg.norm(c["orientation"], axis=1, keepdims=True) * rng.uniform(0.9, 1.1, (B, 1))
+    if with_points:
+        c.update(point_sum=rng.uniform(0, 10, B), g2_p=rng.normal(0, 1, (B, 3)),
+                 g2_q=rng.normal(0, 1, (B, 4)), g2_s=rng.normal(0, 1, B))
+    else:
+        c.update(point_sum=None, g2_p=None, g2_q=None, g2_s=None)
+    return {k: (None if v is None else np.asarray(v, np.float64)) for k, v in c.items()}
+
+
+def _torch_reference(case, steps, depth_weight, point_weight):
+    """The reference's own operators: autograd through q = o/|o|, 1/scale and the weighted loss
+    with SURROGATE linear losses that have the given gradients, then torch.optim.Adam."""
+    t = lambda a: None if a is None else torch.tensor(a, dtype=torch.float64)  # noqa: E731
+    pos, ori, scale = (t(case[k]).requires_grad_(True) for k in ("position", "orientation", "scale"))
+    groups = [{"params": [pos], "lr": LRS[0]}, {"params": [ori], "lr": LRS[1]}, {"params": [scale], "lr": LRS[2]}]
+    lat = None
+    if case["latent"] is not None:
+        lat = t(case["latent"]).requires_grad_(True)
+        groups.append({"params": [lat], "lr": LRS[3]})
+    opt = torch.optim.Adam(groups)
+    n = t(case["n_overlap"])
+    coef = torch.where(n > 0, depth_weight / torch.where(n > 0, n, torch.ones_like(n)), torch.zeros_like(n))
+    for _ in range(steps):
+        opt.zero_grad()
+        q = ori / torch.sqrt(torch.sum(ori ** 2, dim=1, keepdim=True))
+        inv = 1 / scale
+        loss = (coef * ((t(case["gr_p"]) * pos).sum(1) + (t(case["gr_q"]) * q).sum(1) + t(case["gr_is"]) * inv)).sum()
+        if case["g2_p"] is not None:
+            loss = loss + ((t(case["g2_p"]) * pos).sum(1) + (t(case["g2_q"]) * q).sum(1) + t(case["g2_s"]) * scale).sum()
+        if lat is not None:
+            loss = loss + (t(case["g_latent"]) * lat).sum()
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            ori /= torch.sqrt(torch.sum(ori ** 2, dim=1, keepdim=True))
+    return [None if x is None else x.detach().numpy() for x in (pos, ori, scale, lat)]
+
+
+def _oracle_run(case, steps, depth_weight, point_weight, L):
+    B = case["position"].shape[0]
+    st = dict(position=case["position"], orientation=case["orientation"], scale=case["scale"],
+              latent=case["latent"], m=np.zeros((B, 8 + L)), v=np.zeros((B, 8 + L)), t=0)
+    out = None
+    for _ in range(steps):
+        out = hs.hypothesis_step(st, case["loss_sum"], case["n_overlap"], case["gr_p"], case["gr_q"],
+                                 case["gr_is"], depth_weight, case["point_sum"], point_weight,
+                                 case["g2_p"], case["g2_q"], case["g2_s"], case["g_latent"], LRS)
+        st = out[0]
+    return out
+
+
+@pytest.mark.parametrize("L,with_points", [(0, True), (8, True), (5, False)])
+def test_oracle_matches_torch_adam(L, with_points):
+    case = _random_case(7, L, seed=L + 3, with_points=with_points)
+    ref = _torch_reference(case, 6, 1.0, 0.01)
+    st, unit, inv, loss = _oracle_run(case, 6, 1.0, 0.01, L)
+    for a, b in zip(ref, (st["position"], st["orientation"], st["scale"], st["latent"])):
+        if a is not None:
+            np.testing.assert_allclose(b, a, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(np.linalg.norm(unit, axis=1), 1.0, atol=1e-14)
+    np.testing.assert_allclose(inv, 1.0 / st["scale"])
+    n = case["n_overlap"]
+    exp = np.where(n > 0, case["loss_sum"] / np.where(n > 0, n, 1), 0.0)
+    if with_points:
+        exp = exp + 0.01 * case["point_sum"]
+    np.testing.assert_allclose(loss, exp)
+
+
+# ------------------------------------------------------------------------------------------
+# GPU
+# ------------------------------------------------------------------------------------------
+def _dev(case, dev):
+    return {k: (None if v is None else torch.tensor(v, dtype=torch.float32, device=dev).contiguous())
+            for k, v in case.items()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,with_points", [(1, 0, True), (64, 8, True), (300, 5, False)])
+def test_step_kernel_matches_oracle(cuda_device, B, L, with_points):
+    from sdfest_b200 import _lib
+
+    lib = _lib.lib()
+    case = _random_case(B, L, seed=11 + B, with_points=with_points)
+    case32 = {k: (None if v is None else v.astype(np.float32).astype(np.float64)) for k, v in case.items()}
+    d = _dev(case, cuda_device)
+    m = torch.zeros((B, 8 + L), device=cuda_device)
+    v = torch.zeros((B, 8 + L), device=cuda_device)
+    t = torch.zeros(B, dtype=torch.int32, device=cuda_device)
+    unit = torch.empty((B, 4), device=cuda_device)
+    inv = torch.empty(B, device=cuda_device)
+    loss = torch.empty(B, device=cuda_device)
+    lr = (ctypes.c_float * 4)(*LRS)
+    p = lambda x: None if x is None else x.data_ptr()  # noqa: E731
+    steps = 5
+    for _ in range(steps):
+        _lib.check(lib.sdfr_hypothesis_step(
+            p(d["position"]), p(d["orientation"]), p(d["scale"]), p(d["latent"]), L, B,
+            p(d["loss_sum"]), p(d["n_overlap"]), p(d["gr_p"]), p(d["gr_q"]), p(d["gr_is"]), 1.0,
+            p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]),
+            p(m), p(v), p(t), lr, 0.9, 0.999, 1e-8, p(unit), p(inv), p(loss), 0, None), "step")
+    torch.cuda.synchronize()
+    st, unit_o, inv_o, loss_o = _oracle_run(case32, steps, 1.0, 0.01, L)
+    assert int(t.min()) == steps and int(t.max()) == steps
+    for name, got in (("position", d["position"]), ("orientation", d["orientation"]),
+                      ("scale", d["scale"]), ("latent", d["latent"])):
+        if got is not None:
+            np.testing.assert_allclose(got.cpu().numpy(), st[name], rtol=2e-5, atol=2e-6, err_msg=name)
+    np.testing.assert_allclose(unit.cpu().numpy(), unit_o, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(inv.cpu().numpy(), inv_o, rtol=2e-5)
+    np.testing.assert_allclose(loss.cpu().numpy(), loss_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(m.cpu().numpy(), st["m"], rtol=1e-4, atol=1e-6)
+
+    # NO_UPDATE leaves parameters and state alone; CLEAR_INPUTS zeroes what was consumed
+    before = [x.clone() for x in (d["position"], d["orientation"], d["scale"], m, v)]
+    _lib.check(lib.sdfr_hypothesis_step(
+        p(d["position"]), p(d["orientation"]), p(d["scale"]), p(d["latent"]), L, B,
+        p(d["loss_sum"]), p(d["n_overlap"]), p(d["gr_p"]), p(d["gr_q"]), p(d["gr_is"]), 1.0,
+        p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]),
+        p(m), p(v), p(t), lr, 0.9, 0.999, 1e-8, p(unit), p(inv), p(loss),
+        _lib.STEP_NO_UPDATE | _lib.STEP_CLEAR_INPUTS, None), "step")
+    torch.cuda.synchronize()
+    for a, b in zip(before, (d["position"], d["orientation"], d["scale"], m, v)):
+        assert torch.equal(a, b)
+    assert int(t.max()) == steps
+    for k in ("loss_sum", "n_overlap", "gr_p", "gr_q", "gr_is", "point_sum", "g2_p", "g2_q", "g2_s"):
+        if d[k] is not None:
+            assert float(d[k].abs().max()) == 0.0, k
+
+
+@pytest.mark.gpu
+def test_step_kernel_argument_errors(cuda_device):
+    from sdfest_b200 import _lib
+
+    lib = _lib.lib()
+    x = torch.zeros(8, device=cuda_device)
+    lr = (ctypes.c_float * 4)(*LRS)
+    a = x.data_ptr()
+    assert lib.sdfr_hypothesis_step(None, a, a, None, 0, 1, None, None, None, None, None, 1.0, None, 0.0,
+                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, 0, None) == -1
+    assert lib.sdfr_hypothesis_step(a, a, a, None, 65, 1, None, None, None, None, None, 1.0, None, 0.0,
+                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, 0, None) == -2
+    assert lib.sdfr_hypothesis_step(a, a, a, None, 0, 1, None, None, None, None, None, 1.0, None, 0.0,
+                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, 0x1, None) == -3
+    assert lib.sdfr_hypothesis_step(a, a, a, None, 0, 0, None, None, None, None, None, 1.0, None, 0.0,
+                                    None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8,
+                                    None, None, None, 0, None) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("layout", ["dense", "skewed"])
+def test_point_loss_fused_matches_forward_and_backward(cuda_device, layout):
+    from sdfest_b200 import _lib, synthetic as syn
+    from sdfest_b200.differentiable_renderer.sdf_renderer import _skewed_elems
+
+    lib, dev = _lib.lib(), cuda_device
+    B, R, M = 5, 32, 4000
+    hyp = syn.make_hypotheses(B, seed=3, device=dev)
+    grids = syn.hypothesis_grids(hyp["shape_param"], R, dev).contiguous()
+    scale = (1.0 / hyp["inv_scale"]).contiguous()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    pts = (torch.randn(M, 3, generator=g) * 0.12).to(dev) + hyp["position"][0]
+    pts = pts.contiguous()
+    up = torch.full((B,), 3.0 / M, device=dev)
+    if layout == "skewed":
+        SK = _skewed_elems(R)
+        src = torch.empty((B, SK), device=dev)
+        _lib.check(lib.sdfr_skew_grids(grids.data_ptr(), R, R ** 3, B, src.data_ptr(), SK, None), "skew")
+        stride, lay = SK, _lib.LAYOUT_SKEWED
+    else:
+        src, stride, lay = grids, R ** 3, _lib.LAYOUT_DENSE
+    flags = _lib.GRAD_ALL | _lib.ZERO_GRADS
+    pose = (hyp["position"].data_ptr(), hyp["orientation"].data_ptr(), scale.data_ptr())
+
+    def bufs():
+        return (torch.empty(B, device=dev), torch.empty((B, R ** 3), device=dev), torch.empty((B, 3), device=dev),
+                torch.empty((B, 4), device=dev), torch.empty(B, device=dev))
+
+    l0, gs0, gp0, gq0, gsc0 = bufs()
+    _lib.check(lib.sdfr_point_loss_forward(pts.data_ptr(), 0, M, src.data_ptr(), R, stride, lay, *pose, B,
+                                           l0.data_ptr(), _lib.ZERO_GRADS, None), "fwd")
+    _lib.check(lib.sdfr_point_loss_backward(pts.data_ptr(), 0, M, src.data_ptr(), R, stride, lay, *pose, B,
+                                            up.data_ptr(), gs0.data_ptr(), R ** 3, gp0.data_ptr(),
+                                            gq0.data_ptr(), gsc0.data_ptr(), flags, None), "bwd")
+    l1, gs1, gp1, gq1, gsc1 = bufs()
+    _lib.check(lib.sdfr_point_loss_fused(pts.data_ptr(), 0, M, src.data_ptr(), R, stride, lay, *pose, B,
+                                         up.data_ptr(), l1.data_ptr(), gs1.data_ptr(), R ** 3,
+                                         gp1.data_ptr(), gq1.data_ptr(), gsc1.data_ptr(), flags, None), "fused")
+    torch.cuda.synchronize()
+    assert float(l0.abs().min()) > 0
+    for a, b in ((l0, l1), (gp0, gp1), (gq0, gq1), (gsc0, gsc1), (gs0, gs1)):
+        torch.testing.assert_close(b, a, rtol=1e-4, atol=1e-6 * float(a.abs().max()))
+    # loss only (no gradient flags): the forward kernel
+    l2 = torch.empty(B, device=dev)
+    _lib.check(lib.sdfr_point_loss_fused(pts.data_ptr(), 0, M, src.data_ptr(), R, stride, lay, *pose, B,
+                                         None, l2.data_ptr(), None, 0, None, None, None, _lib.ZERO_GRADS,
+                                         None), "fused loss only")
+    torch.testing.assert_close(l2, l0, rtol=1e-5, atol=0)
+
+
+def _make_optimizers(dev, B, with_decoder, optimizer):
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, render_depth_batched
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    W, H, thr = 160, 120, 0.005
+    R = 64 if with_decoder else 32  # the mug decoder architecture ends at 64^3
+    cam = Camera(W, H, W / 2, W / 2, W / 2, H / 2, pixel_center=0.5)
+    hyp = syn.make_hypotheses(B, seed=0, device=dev)
+    base = syn.make_hypotheses(1, seed=0, device=dev)
+    obs = render_depth_batched(syn.hypothesis_grids(base["shape_param"], R, dev), base["position"],
+                               base["orientation"], base["inv_scale"], thr, cam)[0].contiguous()
+    torch.manual_seed(0)
+    if with_decoder:
+        dec = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
+        kw = dict(latent=0.1 * torch.randn(B, 8, device=dev), decoder=dec)
+    else:
+        kw = dict(sdf=syn.hypothesis_grids(hyp["shape_param"], R, dev))
+    return HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                               optimizer=optimizer, **kw)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("with_decoder", [False, True])
+def test_fused_optimizer_matches_torch_optimizer(cuda_device, with_decoder):
+    B, steps = 6, 4
+    a = _make_optimizers(cuda_device, B, with_decoder, "torch")
+    b = _make_optimizers(cuda_device, B, with_decoder, "fused")
+    assert a.optimizer_impl == "torch" and b.optimizer_impl == "fused"
+    for _ in range(steps):
+        la = a.step().clone()
+        lb = b.step().clone()
+        torch.testing.assert_close(lb, la, rtol=2e-3, atol=1e-5)
+    # Adam's first steps move every parameter by ~lr regardless of the gradient's size, so
+    # parameters agree to a small fraction of steps * lr unless a gradient is pure noise
+    for name, lr in (("position", 1e-3), ("orientation", 1e-2), ("scale", 1e-3)):
+        pa, pb = getattr(a, name).detach(), getattr(b, name).detach()
+        assert float((pa - pb).abs().max()) < 0.05 * lr * steps, name
+    if with_decoder:
+        moved = float((a.latent.detach() - 0.0).abs().max())
+        assert moved > 0
+        assert float((a.latent.detach() - b.latent.detach()).abs().max()) < 0.05 * 1e-2 * steps
+    torch.testing.assert_close(torch.linalg.norm(b.orientation, dim=1),
+                               torch.ones(B, device=cuda_device), rtol=0, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_fused_optimizer_graph_replay_matches_eager(cuda_device):
+    a = _make_optimizers(cuda_device, 4, True, "fused")
+    b = _make_optimizers(cuda_device, 4, True, "fused")
+    a.step()
+    b.capture(warmup=1)  # one eager iteration, then one recorded (not executed) iteration
+    for _ in range(3):
+        la = a.step().clone()
+        lb = b.step().clone()
+    torch.cuda.synchronize()
+    torch.testing.assert_close(lb, la, rtol=2e-3, atol=1e-5)
+    assert float((a.position - b.position).abs().max()) < 1e-4
+    assert float((a.latent.detach() - b.latent.detach()).abs().max()) < 1e-3

@@ -121,9 +121,14 @@ def test_runtime_breakdown_reports_every_phase(cuda_device):
     base = syn.sdf_mug(R, dev)
     obs = render_depth_batched(base, hyp["position"][:1], hyp["orientation"][:1], hyp["inv_scale"][:1],
                                thr, cam)[0].contiguous()
-    opt = HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
-                              latent=torch.zeros(B, 8, device=dev),
-                              decoder=syn.residual_decoder(R, dev, base))
-    res = runtime_analysis.phase_breakdown(opt, iterations=3, warmup=1)
+    def make(optimizer):
+        return HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                                   latent=torch.zeros(B, 8, device=dev),
+                                   decoder=syn.residual_decoder(R, dev, base), optimizer=optimizer)
+
+    res = runtime_analysis.phase_breakdown(make("torch"), iterations=3, warmup=1)
     assert set(res) == set(runtime_analysis.PHASES) | {"total"} and all(v > 0 for v in res.values())
-    assert runtime_analysis.iteration_ms(opt, iterations=3, warmup=1, graph=True) > 0
+    with pytest.raises(ValueError):
+        runtime_analysis.phase_breakdown(make("fused"), iterations=1, warmup=0)
+    for optimizer in ("torch", "fused"):
+        assert runtime_analysis.iteration_ms(make(optimizer), iterations=3, warmup=1, graph=True) > 0
