@@ -453,10 +453,32 @@ def main():
             final = opt.run(1)  # one more step with the all_gather of the per-hypothesis losses
             assert final.numel() == world * B
         loop = {"hyp_iter_per_s": world * B * n_it / (loop_ms * 1e-3), "ms_per_iteration": loop_ms / n_it,
-                "iterations": n_it, "hypotheses_per_gpu": B,
+                "iterations": n_it, "hypotheses_per_gpu": B, "optimizer": opt.optimizer_impl,
                 "what": "50 Adam steps on position/orientation/scale/latent: decoder trunk + fused tail, "
-                        "fused render-and-compare, point loss, backward, Adam; CUDA-graph replay",
+                        "fused render-and-compare, fused point loss, tail adjoint + trunk backward, one "
+                        "sdfr_hypothesis_step kernel (chain rule + Adam + renormalisation); CUDA-graph replay",
                 "final_mean_loss": float(opt.last_losses.mean())}
+        # fixed grids (BASELINE config 4's per-GPU work: pose/scale hypotheses on given shapes)
+        opt = HypothesisOptimizer(cam, THRESHOLD, obs, pos, quat, 1.0 / inv_s, sdf=grids)
+        opt.capture()
+        for _ in range(5):
+            opt.step()
+        torch.cuda.synchronize()
+        a, b_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n_it):
+            opt.step()
+        b_ev.record()
+        torch.cuda.synchronize()
+        pose_ms = a.elapsed_time(b_ev)
+        if distributed:
+            t = torch.tensor([pose_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pose_ms = float(t.item())
+        loop["pose_only"] = {"hyp_iter_per_s": world * B * n_it / (pose_ms * 1e-3),
+                             "ms_per_iteration": pose_ms / n_it,
+                             "what": "same loop on fixed grids: 3 launches per iteration (fused "
+                                     "render-and-compare, fused point loss, hypothesis step)"}
     except Exception as e:  # the loop demo never blocks the render metric
         loop = {"unavailable": str(e)[:200]}
 

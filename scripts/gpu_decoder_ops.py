@@ -18,8 +18,11 @@ torch.manual_seed(0)
 flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
 
 
-def timeit(fn, n=20):
-    for _ in range(3):
+N = int(os.environ.get("OPS_N", "20"))  # OPS_N=1: one launch per kernel (ncu capture)
+
+
+def timeit(fn, n=N):
+    for _ in range(3 if n > 1 else 0):
         fn()
     ts = []
     for _ in range(n):

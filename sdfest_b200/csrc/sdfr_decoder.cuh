@@ -53,6 +53,7 @@ struct TailParams {
   float* __restrict__ g_x; /* [B, C, S, S, S] */
   int z_offset;
   int xb; /* forward: output x-planes per CTA */
+  int fast4; /* forward: 4-row groups (tail_forward_plan); backward: float4 loads of the gradient planes */
 };
 
 /* ATen area_pixel_compute_source_index, align_corners = false, linear */
@@ -84,12 +85,13 @@ inline void tail_source_host(int o, int S, int R, int& i0, int& i1) {
  */
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
-  extern __shared__ float tail_smem[];
+  extern __shared__ __align__(16) float tail_smem[];
   const int S = P.S, R = P.R, C = P.C;
   int* ti0 = (int*)tail_smem;         /* [R] */
   int* ti1 = ti0 + R;                 /* [R] */
   float* tl1 = (float*)(ti1 + R);     /* [R] */
-  float* src = tl1 + R;               /* [np][S*S] channel-contracted source planes */
+  float* wy = tl1 + R;                /* [R][4] (fast4): weight of source row ti0[4*(oy/4)] + k on output row oy */
+  float* src = wy + (P.fast4 ? 4 * R : 0); /* [np][S*S] channel-contracted source planes */
   const int b = blockIdx.y + P.z_offset;
   const int ox0 = blockIdx.x * P.xb;
   const int nxo = R - ox0 < P.xb ? R - ox0 : P.xb;
@@ -101,6 +103,13 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
     ti0[o] = i0; ti1[o] = i1; tl1[o] = l1;
   }
   __syncthreads();
+  if (P.fast4) {
+    for (int e = threadIdx.x; e < 4 * R; e += blockDim.x) {
+      const int oy = e >> 2, row = ti0[oy & ~3] + (e & 3);
+      const float l1 = tl1[oy];
+      wy[e] = (ti0[oy] == row ? 1.0f - l1 : 0.0f) + (ti1[oy] == row ? l1 : 0.0f);
+    }
+  }
   const int xs_lo = ti0[ox0], np = ti1[ox0 + nxo - 1] - xs_lo + 1;
   float w[kTailMaxChannels];
 #pragma unroll
@@ -119,29 +128,42 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
   __syncthreads();
   const float bias = P.bias ? __ldg(P.bias) : 0.0f;
   float* __restrict__ out = P.out + (size_t)b * P.out_stride;
-  if (R <= 256 && (256 % R) == 0) {
-    /* a thread keeps ONE output column oz (z-interpolation constants in registers) and walks the
-     * rows of every plane of the slab; x / y constants are warp-uniform (broadcast loads) */
-    const int oz = threadIdx.x % R, rows = 256 / R;
+  if (P.fast4) {
+    /* A thread keeps ONE output column oz (z-interpolation constants in registers) and produces FOUR
+     * consecutive output rows per step: the <= 4 source rows they read are blended in x and z once
+     * (16 shared-memory loads) and combined with a 4x4 weight block from wy.  The first version
+     * produced one output per step from 8 loads and ~70 instructions, most of them integer address
+     * arithmetic (profiles/r01s_ncu_decoder.txt); this one needs ~19 per output. */
+    const int oz = threadIdx.x % R, rl = threadIdx.x / R, rows = 256 / R, G = R >> 2;
     const int z0 = ti0[oz], z1 = ti1[oz];
     const float lz1 = tl1[oz], lz0 = 1.0f - lz1;
+    const size_t R2 = (size_t)R * R;
     for (int dx = 0; dx < nxo; ++dx) {
       const int ox = ox0 + dx;
       const float* __restrict__ pa = src + (ti0[ox] - xs_lo) * S2;
       const float* __restrict__ pb = src + (ti1[ox] - xs_lo) * S2;
       const float lx1 = tl1[ox], lx0 = 1.0f - lx1;
-      float* __restrict__ o = out + (size_t)ox * P.px;
-      const float* __restrict__ base = P.base ? P.base + (size_t)ox * R * R : nullptr;
-      for (int oy = threadIdx.x / R; oy < R; oy += rows) {
-        const int r0 = ti0[oy] * S, r1 = ti1[oy] * S;
-        const float ly1 = tl1[oy], ly0 = 1.0f - ly1;
-        const float a0 = lz0 * pa[r0 + z0] + lz1 * pa[r0 + z1];
-        const float a1 = lz0 * pa[r1 + z0] + lz1 * pa[r1 + z1];
-        const float b0 = lz0 * pb[r0 + z0] + lz1 * pb[r0 + z1];
-        const float b1 = lz0 * pb[r1 + z0] + lz1 * pb[r1 + z1];
-        float v = (lx0 * (ly0 * a0 + ly1 * a1) + lx1 * (ly0 * b0 + ly1 * b1)) + bias;
-        if (base) v += __ldg(base + oy * R + oz);
-        o[oy * P.py + oz] = v;
+      float* __restrict__ o = out + (size_t)ox * P.px + oz;
+      const float* __restrict__ base = P.base ? P.base + (size_t)ox * R2 + oz : nullptr;
+      for (int g = rl; g < G; g += rows) {
+        const int yb = ti0[4 * g];
+        float r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = (yb + k < S ? yb + k : S - 1) * S;
+          const float a = lz0 * pa[row + z0] + lz1 * pa[row + z1];
+          const float c = lz0 * pb[row + z0] + lz1 * pb[row + z1];
+          r[k] = lx0 * a + lx1 * c;
+        }
+        const float4* __restrict__ W = reinterpret_cast<const float4*>(wy + 16 * g);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 w4 = W[i];
+          float v = (w4.x * r[0] + w4.y * r[1] + w4.z * r[2] + w4.w * r[3]) + bias;
+          const int oy = 4 * g + i;
+          if (base) v += __ldg(base + oy * R);
+          o[(size_t)oy * P.py] = v;
+        }
       }
     }
     return;
@@ -177,7 +199,7 @@ __host__ __device__ inline int tail_taps(int S, int R) { return 2 * ((R + S - 1)
 /* One CTA per (source x-plane, hypothesis). */
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
-  extern __shared__ float tail_smem[];
+  extern __shared__ __align__(16) float tail_smem[];
   const int S = P.S, R = P.R, C = P.C;
   const int KW = tail_taps(S, R);
   float* Pl = tail_smem;              /* [R][R]  x-collapsed gradient plane */
@@ -226,7 +248,31 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   const float* __restrict__ ge = P.g_extra ? P.g_extra + (size_t)b * P.g_extra_stride : nullptr;
   const int xlo = lo[sx], nx = hi[sx] - xlo + 1;
   const float* __restrict__ wx = Wt + sx * KW;
-  /* 1. collapse x:  Pl[oy][oz] = sum_ox W(ox, sx) g[ox][oy][oz] */
+  /* 1. collapse x:  Pl[oy][oz] = sum_ox W(ox, sx) g[ox][oy][oz]  (float4 when the planes allow it:
+   * the scalar loop below costs 37 instructions per element, half of the kernel) */
+  if (P.fast4) {
+    const int n4 = (int)(R2 >> 2);
+    const float4* __restrict__ ga4 = reinterpret_cast<const float4*>(ga + (size_t)xlo * R2);
+    const float4* __restrict__ ge4 = ge ? reinterpret_cast<const float4*>(ge + (size_t)xlo * R2) : nullptr;
+    const bool use_main = coef != 0.0f;
+    for (int j = threadIdx.x; j < n4; j += blockDim.x) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < nx; ++k) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (use_main) {
+          g = __ldg(ga4 + (size_t)k * n4 + j);
+          g.x *= coef; g.y *= coef; g.z *= coef; g.w *= coef;
+        }
+        if (ge4) {
+          const float4 e = __ldg(ge4 + (size_t)k * n4 + j);
+          g.x += e.x; g.y += e.y; g.z += e.z; g.w += e.w;
+        }
+        const float w = wx[k];
+        acc.x += w * g.x; acc.y += w * g.y; acc.z += w * g.z; acc.w += w * g.w;
+      }
+      reinterpret_cast<float4*>(Pl)[j] = acc;
+    }
+  } else
   for (int j = threadIdx.x; j < (int)R2; j += blockDim.x) {
     float acc = 0.0f;
     for (int k = 0; k < nx; ++k) {
@@ -265,9 +311,19 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
 
 /* Slab thickness (output x-planes per CTA) and the shared memory it needs: aim at ~32 K outputs
  * per CTA, shrink while the staged source planes do not fit. */
-size_t tail_forward_plan(int S, int R, int& xb) {
+size_t tail_forward_plan(int S, int R, int batch, int& xb, int& fast4) {
+  fast4 = (R % 4 == 0 && R <= 256 && 256 % R == 0) ? 1 : 0;
+  for (int g = 0; fast4 && g < R / 4; ++g) { /* every 4-row group must read at most 4 source rows */
+    int a0, a1, b0, b1;
+    tail_source_host(4 * g, S, R, a0, a1);
+    tail_source_host(4 * g + 3, S, R, b0, b1);
+    if (b1 - a0 > 3) fast4 = 0;
+  }
   xb = 32768 / (R * R);
   xb = xb < 1 ? 1 : (xb > R ? R : xb);
+  /* thinner slabs only when the grid would not even fill the SMs twice (measured: 4 instead of 8
+   * planes per CTA at 64 hypotheses re-stages more than the extra CTAs hide, 75 -> 81 us) */
+  while (xb > 2 && (long)((R + xb - 1) / xb) * batch < 296) xb /= 2;
   for (;;) {
     int np = 1;
     for (int ox0 = 0; ox0 < R; ox0 += xb) {
@@ -277,7 +333,7 @@ size_t tail_forward_plan(int S, int R, int& xb) {
       tail_source_host(last, S, R, b0, b1);
       np = b1 - a0 + 1 > np ? b1 - a0 + 1 : np;
     }
-    const size_t bytes = sizeof(float) * ((size_t)np * S * S + 3 * (size_t)R);
+    const size_t bytes = sizeof(float) * ((size_t)np * S * S + (fast4 ? 7 : 3) * (size_t)R);
     if (bytes <= 160 * 1024 || xb == 1) return bytes;
     xb = xb / 2;
   }
@@ -296,7 +352,7 @@ int tail_check(int C, int S, int R, int batch) {
 }
 
 int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
-  const size_t smem = tail_forward_plan(P.S, P.R, P.xb);
+  const size_t smem = tail_forward_plan(P.S, P.R, batch, P.xb, P.fast4);
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_forward_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -312,6 +368,9 @@ int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
 
 int launch_tail_backward(TailParams P, int batch, cudaStream_t s) {
   const size_t smem = tail_backward_smem(P.S, P.R);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(P.g_main) | reinterpret_cast<uintptr_t>(P.g_extra);
+  P.fast4 = ((P.R * P.R) % 4 == 0 && P.R >= 32 && (al & 15) == 0 && P.g_main_stride % 4 == 0 &&
+             (!P.g_extra || P.g_extra_stride % 4 == 0)) ? 1 : 0;
   if (smem > 48 * 1024) {
     const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_backward_kernel,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -353,6 +412,7 @@ struct ConvParams {
   int tiles_y, tiles_z;
   int z_offset;
   int cc; /* channels staged per pass = min(CI, ConvTile::CC) */
+  int co_total; /* output channels of the launch; a CTA computes CO of them starting at blockIdx.z * CO */
 };
 
 /* Shared-memory geometry of one CTA: CC input channels of the (TX+2) x (TY+2) x (TZ+2) input tile,
@@ -383,6 +443,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   float* __restrict__ ws = conv_smem + P.cc * T::CH;  /* [CC][27][CO] */
 
   const int b = blockIdx.y + P.z_offset;
+  const int co0 = blockIdx.z * CO, COT = P.co_total;
   int t = blockIdx.x;
   const int tz = t % P.tiles_z; t /= P.tiles_z;
   const int tyy = t % P.tiles_y;
@@ -451,8 +512,8 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
       const int tap = (e / CO) % 27;
       const int c = e / (CO * 27);
       float v;
-      if (!DGRAD) v = __ldg(P.w + ((size_t)co * CI + ci0 + c) * 27 + tap);
-      else v = __ldg(P.w + ((size_t)(ci0 + c) * CO + co) * 27 + (26 - tap)); /* w[co_orig = in ch][ci_orig = out ch], flipped */
+      if (!DGRAD) v = __ldg(P.w + ((size_t)(co0 + co) * CI + ci0 + c) * 27 + tap);
+      else v = __ldg(P.w + ((size_t)(ci0 + c) * COT + co0 + co) * 27 + (26 - tap)); /* w[co_orig = in ch][ci_orig = out ch], flipped */
       ws[e] = v;
     }
     __syncthreads();
@@ -502,8 +563,8 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   const size_t out_vol = (size_t)n_out * n_out * n_out;
 #pragma unroll
   for (int co = 0; co < CO; ++co) {
-    const float bias = (!DGRAD && P.bias) ? __ldg(P.bias + co) : 0.0f;
-    float* __restrict__ o = P.out + ((size_t)b * CO + co) * out_vol + ((size_t)ox * n_out + oy) * n_out;
+    const float bias = (!DGRAD && P.bias) ? __ldg(P.bias + co0 + co) : 0.0f;
+    float* __restrict__ o = P.out + ((size_t)b * COT + co0 + co) * out_vol + ((size_t)ox * n_out + oy) * n_out;
 #pragma unroll
     for (int i = 0; i < ZR; ++i) {
       const int oz = Z0 + z0 + i;
@@ -531,7 +592,7 @@ int launch_conv3_v(ConvParams P, int batch, cudaStream_t s) {
   }
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
-    const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535);
+    const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535, P.co_total / CO);
     sdfr_conv3_kernel<CO, ZR, DGRAD, VEC><<<grid, 256, smem, s>>>(P);
   }
   return 0;
@@ -561,6 +622,15 @@ int launch_conv3_zr(const ConvParams& P, int batch, cudaStream_t s) {
 template <bool DGRAD>
 int launch_conv3(ConvParams P, int CO, int batch, cudaStream_t s) {
   int rc = 0;
+  P.co_total = CO;
+  if (P.n_out <= 8) {
+    /* the smallest stage (8^3 -> 6^3 in every shipped decoder) has 2 tiles per volume; with few
+     * hypotheses the output channels are split over blockIdx.z to fill the SMs.  (At 64 hypotheses
+     * = 128 CTAs splitting was measured SLOWER, 33 -> 41 us: 4 accumulators per thread starve the FMA
+     * pipe; the stage is latency-bound at 8 warps per SM, not CTA-count-bound.) */
+    const long tiles = (long)((P.n_out + 3) / 4) * batch;
+    while (CO > 8 && tiles * (P.co_total / CO) < 74) CO /= 2;
+  }
   switch (CO) {
     case 4: rc = launch_conv3_zr<4, DGRAD>(P, batch, s); break;
     case 8: rc = launch_conv3_zr<8, DGRAD>(P, batch, s); break;

@@ -83,7 +83,8 @@ class HypothesisOptimizer:
                  sdf: Optional[torch.Tensor] = None, latent: Optional[torch.Tensor] = None,
                  decoder: Optional[Callable] = None, depth_weight: float = 1.0,
                  pc_weight: float = 3.0, max_points: int = 0, group=None, optimizer: str = "auto",
-                 lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8):
+                 lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8,
+                 overlap: bool = True):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
@@ -92,6 +93,7 @@ class HypothesisOptimizer:
         if optimizer == "fused" and not can_fuse:
             raise ValueError("optimizer='fused' needs CUDA tensors and fixed grids or a FusedTailDecoder")
         self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
+        self.overlap = bool(overlap)
         self.lrs, self.betas, self.eps = tuple(float(x) for x in lrs), tuple(betas), float(eps)
         self.camera, self.threshold, self.group = camera, float(threshold), group
         self.depth_obs = depth_obs.contiguous()
@@ -179,6 +181,9 @@ class HypothesisOptimizer:
             self._grids = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
             self._g_sdf = torch.empty((B, R ** 3), dtype=torch.float32, device=dev)
             self._g_sdf_pc = torch.empty((B, R ** 3), dtype=torch.float32, device=dev) if M else None
+        # second stream: the point loss runs beside the render (both only read the grids), the
+        # gradient-grid clears beside the decoder trunk; forks and joins are captured by capture()
+        self._side = torch.cuda.Stream(dev) if self.overlap else None
         self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale for the first render
 
     def _hyp_step(self, flags: int, g_latent: Optional[torch.Tensor] = None) -> None:
@@ -196,44 +201,66 @@ class HypothesisOptimizer:
             _stream()), "sdfr_hypothesis_step")
 
     def _fused_iteration(self) -> torch.Tensor:
-        lib, b, st = _lib.lib(), self._buf, _stream()
+        lib, b = _lib.lib(), self._buf
         B, R, M = self.position.shape[0], self._R, self._M
         W, H, cx, cy, fx, fy = _camera_params(self.camera)
         grids, gstride, layout = self._grids
         dec, x = self.decoder, None
+        main, side = torch.cuda.current_stream(), self._side
+
+        def on_side(fn):
+            """Run fn on the second stream after everything enqueued so far (or inline)."""
+            if side is None:
+                fn()
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn()
+
+        def clear_grids():
+            self._g_sdf.zero_()
+            if self._g_sdf_pc is not None:
+                self._g_sdf_pc.zero_()
+
         if dec is not None:
+            on_side(clear_grids)
             x = dec.trunk(self.latent).contiguous()  # autograd graph: latent -> x only
             w, bias = dec.tail_parameters()
             C, S = int(x.shape[1]), int(x.shape[2])
             _lib.check(lib.sdfr_decoder_tail_forward(
                 x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
-                gstride, layout, st), "sdfr_decoder_tail_forward")
-            self._g_sdf.zero_()
-            if self._g_sdf_pc is not None:
-                self._g_sdf_pc.zero_()
+                gstride, layout, _stream()), "sdfr_decoder_tail_forward")
+            if side is not None:
+                main.wait_stream(side)
         flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
         if dec is not None:
             flags |= _lib.GRAD_SDF
+
+        def point_loss():
+            _lib.check(lib.sdfr_point_loss_fused(
+                self.points.data_ptr(), 0, M, grids.data_ptr(), R, gstride, layout,
+                self.position.data_ptr(), self._unit_q.data_ptr(), self.scale.data_ptr(), B,
+                self._up_p.data_ptr(), b["pl"].data_ptr(), _ptr(self._g_sdf_pc), R ** 3,
+                b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(), flags, _stream()),
+                "sdfr_point_loss_fused")
+
+        if M:
+            on_side(point_loss)
         _lib.check(lib.sdfr_compare_fused(
             grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
             self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
             self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
             b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), _ptr(self._g_sdf), R ** 3,
-            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, st),
+            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
             "sdfr_compare_fused")
-        if M:
-            _lib.check(lib.sdfr_point_loss_fused(
-                self.points.data_ptr(), 0, M, grids.data_ptr(), R, gstride, layout,
-                self.position.data_ptr(), self._unit_q.data_ptr(), self.scale.data_ptr(), B,
-                self._up_p.data_ptr(), b["pl"].data_ptr(), _ptr(self._g_sdf_pc), R ** 3,
-                b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(), flags, st),
-                "sdfr_point_loss_fused")
+        if M and side is not None:
+            main.wait_stream(side)
         g_latent = None
         if dec is not None:
             g_x = torch.empty_like(x)
             _lib.check(lib.sdfr_decoder_tail_backward(
                 self._g_sdf.data_ptr(), R ** 3, b["n_overlap"].data_ptr(), self._up_d.data_ptr(),
-                _ptr(self._g_sdf_pc), R ** 3, w.data_ptr(), C, S, B, R, g_x.data_ptr(), st),
+                _ptr(self._g_sdf_pc), R ** 3, w.data_ptr(), C, S, B, R, g_x.data_ptr(), _stream()),
                 "sdfr_decoder_tail_backward")
             (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
             g_latent = g_latent.contiguous()
