@@ -16,17 +16,32 @@ from util import (default_camera, golden_names, load_golden, mug_sdf, sdf_box, s
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "host_emul", "emul.cpp")
 SO = os.path.join(HERE, "host_emul", "libemul.so")
+SO_REF = os.path.join(HERE, "host_emul", "libemul_ref.so")
 CORE = os.path.join(os.path.dirname(HERE), "sdfest_b200", "csrc", "sdfr_core.cuh")
 f32 = np.float32
 
 
+def _build(so, *defines):
+    if (not os.path.isfile(so)
+            or os.path.getmtime(so) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
+        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        subprocess.check_call([gxx, "-O2", "-ffp-contract=off", *defines, "-fPIC", "-shared", SRC, "-o", so])
+    return ctypes.CDLL(so)
+
+
 @pytest.fixture(scope="module")
 def emul():
-    if (not os.path.isfile(SO)
-            or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(CORE))):
-        gxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-        subprocess.check_call([gxx, "-O2", "-ffp-contract=off", "-fPIC", "-shared", SRC, "-o", SO])
-    return ctypes.CDLL(SO)
+    """The per-ray functions in the REFERENCE'S operation order (-DSDFR_REFERENCE_ROUNDING):
+    bit-identical to the fp32 oracle."""
+    return _build(SO_REF, "-DSDFR_REFERENCE_ROUNDING")
+
+
+@pytest.fixture(scope="module")
+def emul_product():
+    """The per-ray functions as the shipped library compiles them: the march evaluates the cell
+    coordinate with one fma per axis and fma lerps (sdfr_core.cuh march<>), a few ulp away from the
+    reference's expression."""
+    return _build(SO)
 
 
 def P(a):
@@ -61,6 +76,32 @@ def test_device_math_matches_oracle_on_golden(emul, name):
     hit = z["depth"] > 0
     assert ((depth > 0) == hit).all()
     assert (np.abs(depth - z["depth"])[hit] / z["depth"][hit]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_product_march_is_within_rounding_of_the_oracle(emul_product, name):
+    """Default build (fma march): same hit mask; depth within 2e-6 relative of the fp32 oracle for
+    every pixel whose step count agrees (a termination test decided within an ulp may flip and move
+    that pixel by up to `threshold` relative: at most 0.1 % of the hit pixels); within 1e-5 of the
+    reference's float64 renderer like the reference-order build."""
+    z = load_golden(name)
+    thr = float(z["threshold"])
+    depth, steps, _ = run_forward(emul_product, z["sdf"], z["position"], z["orientation"],
+                                  float(z["inv_scale"]), z["W"], z["H"], z["cam"], thr)
+    d_or, st_or, _ = oracle.render(z["sdf"], z["position"], z["orientation"], z["inv_scale"],
+                                   z["W"], z["H"], threshold=thr, extras=True, **z["cam"])
+    hit = d_or > 0
+    assert ((depth > 0) == hit).mean() > 0.999
+    both = hit & (depth > 0)
+    rel = np.abs(depth - d_or)[both] / d_or[both]
+    same = (steps == st_or)[both]
+    assert same.mean() > 0.999
+    assert rel[same].max() < 2e-6
+    assert rel.max() < 1.5 * thr
+    ref_hit = z["depth"] > 0
+    ok = ref_hit & (depth > 0)
+    rel64 = np.abs(depth - z["depth"])[ok] / z["depth"][ok]
+    assert (rel64 < 1e-5).mean() > 0.999 and rel64.max() < 1.5 * thr
 
 
 @pytest.mark.parametrize("name", golden_names())
