@@ -83,10 +83,11 @@ inline void tail_source_host(int o, int S, int R, int& i0, int& i1) {
  * barrier-separated phases each, 60 M warp instructions for the 64^3 tail and bound by CTA turnover,
  * not bandwidth: profiles/r01j_ncu_decoder.txt.)
  */
+template <int ST, int RT> /* compile-time sizes for the shipped decoders' resizes, 0 = run time */
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
   extern __shared__ __align__(16) float tail_smem[];
-  const int S = P.S, R = P.R, C = P.C;
+  const int S = ST ? ST : P.S, R = RT ? RT : P.R, C = P.C;
   int* ti0 = (int*)tail_smem;         /* [R] */
   int* ti1 = ti0 + R;                 /* [R] */
   float* tl1 = (float*)(ti1 + R);     /* [R] */
@@ -194,13 +195,14 @@ __device__ __forceinline__ float tail_weight(const int* ti0, const int* ti1, con
 }
 
 /* upper bound on the number of output indices that read one source index along an axis */
-__host__ __device__ inline int tail_taps(int S, int R) { return 2 * ((R + S - 1) / S) + 2; }
+__host__ __device__ constexpr int tail_taps(int S, int R) { return 2 * ((R + S - 1) / S) + 2; }
 
 /* One CTA per (source x-plane, hypothesis). */
+template <int ST, int RT>
 __global__ void __launch_bounds__(256)
 sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
   extern __shared__ __align__(16) float tail_smem[];
-  const int S = P.S, R = P.R, C = P.C;
+  const int S = ST ? ST : P.S, R = RT ? RT : P.R, C = P.C;
   const int KW = tail_taps(S, R);
   float* Pl = tail_smem;              /* [R][R]  x-collapsed gradient plane */
   float* Q = Pl + R * R;              /* [R][S]  ... z-collapsed */
@@ -218,16 +220,19 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
     tail_source(o, ratio, S, i0, i1, l1);
     ti0[o] = i0; ti1[o] = i1; tl1[o] = l1;
   }
-  __syncthreads();
   for (int s = threadIdx.x; s < S; s += blockDim.x) {
-    int l = R, h = -1;
-    for (int o = 0; o < R; ++o)
-      if (ti0[o] == s || ti1[o] == s) {
-        l = o < l ? o : l;
-        h = o;
-      }
-    lo[s] = l;
-    hi[s] = h;
+    lo[s] = R;
+    hi[s] = -1;
+  }
+  __syncthreads();
+  /* first / last output index reading each source index: one shared-memory atomic pair per output
+   * (the first version scanned all R outputs serially per source index -- 30 threads busy for
+   * 64 iterations while the other 226 waited at the barrier, in each of 1920 CTAs) */
+  for (int o = threadIdx.x; o < R; o += blockDim.x) {
+    atomicMin(&lo[ti0[o]], o);
+    atomicMax(&hi[ti0[o]], o);
+    atomicMin(&lo[ti1[o]], o);
+    atomicMax(&hi[ti1[o]], o);
   }
   __syncthreads();
   for (int e = threadIdx.x; e < S * KW; e += blockDim.x) {
@@ -255,8 +260,10 @@ sdfr_decoder_tail_backward_kernel(const __grid_constant__ TailParams P) {
     const float4* __restrict__ ga4 = reinterpret_cast<const float4*>(ga + (size_t)xlo * R2);
     const float4* __restrict__ ge4 = ge ? reinterpret_cast<const float4*>(ge + (size_t)xlo * R2) : nullptr;
     const bool use_main = coef != 0.0f;
+    constexpr int KU = ST ? tail_taps(ST ? ST : 1, RT ? RT : 1) : 1; /* all taps' loads in flight at once */
     for (int j = threadIdx.x; j < n4; j += blockDim.x) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll KU
       for (int k = 0; k < nx; ++k) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
         if (use_main) {
@@ -351,19 +358,44 @@ int tail_check(int C, int S, int R, int batch) {
   return 0;
 }
 
-int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
-  const size_t smem = tail_forward_plan(P.S, P.R, batch, P.xb, P.fast4);
+template <int ST, int RT>
+int launch_tail_forward_t(TailParams P, int batch, size_t smem, cudaStream_t s) {
   if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_forward_kernel,
+    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_forward_kernel<ST, RT>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "decoder tail forward: shared memory opt-in failed");
   }
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid((P.R + P.xb - 1) / P.xb, batch - z0 < 65535 ? batch - z0 : 65535);
-    sdfr_decoder_tail_forward_kernel<<<grid, 256, smem, s>>>(P);
+    sdfr_decoder_tail_forward_kernel<ST, RT><<<grid, 256, smem, s>>>(P);
   }
   return check_launch("sdfr_decoder_tail_forward_kernel");
+}
+
+/* the resizes of every decoder the reference ships (mug.yaml and siblings: 8 -> 6 -> 16, 14 -> 32,
+ * 30 -> 64) get compile-time sizes: most of the generic kernels' instructions are index arithmetic */
+int launch_tail_forward(TailParams P, int batch, cudaStream_t s) {
+  const size_t smem = tail_forward_plan(P.S, P.R, batch, P.xb, P.fast4);
+  if (P.S == 30 && P.R == 64) return launch_tail_forward_t<30, 64>(P, batch, smem, s);
+  if (P.S == 14 && P.R == 32) return launch_tail_forward_t<14, 32>(P, batch, smem, s);
+  if (P.S == 6 && P.R == 16) return launch_tail_forward_t<6, 16>(P, batch, smem, s);
+  return launch_tail_forward_t<0, 0>(P, batch, smem, s);
+}
+
+template <int ST, int RT>
+int launch_tail_backward_t(TailParams P, int batch, size_t smem, cudaStream_t s) {
+  if (smem > 48 * 1024) {
+    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_backward_kernel<ST, RT>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail((int)e, "decoder tail backward: shared memory opt-in failed");
+  }
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    P.z_offset = z0;
+    const dim3 grid(P.S, batch - z0 < 65535 ? batch - z0 : 65535);
+    sdfr_decoder_tail_backward_kernel<ST, RT><<<grid, 256, smem, s>>>(P);
+  }
+  return check_launch("sdfr_decoder_tail_backward_kernel");
 }
 
 int launch_tail_backward(TailParams P, int batch, cudaStream_t s) {
@@ -371,17 +403,10 @@ int launch_tail_backward(TailParams P, int batch, cudaStream_t s) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(P.g_main) | reinterpret_cast<uintptr_t>(P.g_extra);
   P.fast4 = ((P.R * P.R) % 4 == 0 && P.R >= 32 && (al & 15) == 0 && P.g_main_stride % 4 == 0 &&
              (!P.g_extra || P.g_extra_stride % 4 == 0)) ? 1 : 0;
-  if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(sdfr_decoder_tail_backward_kernel,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail((int)e, "decoder tail backward: shared memory opt-in failed");
-  }
-  for (int z0 = 0; z0 < batch; z0 += 65535) {
-    P.z_offset = z0;
-    const dim3 grid(P.S, batch - z0 < 65535 ? batch - z0 : 65535);
-    sdfr_decoder_tail_backward_kernel<<<grid, 256, smem, s>>>(P);
-  }
-  return check_launch("sdfr_decoder_tail_backward_kernel");
+  if (P.S == 30 && P.R == 64) return launch_tail_backward_t<30, 64>(P, batch, smem, s);
+  if (P.S == 14 && P.R == 32) return launch_tail_backward_t<14, 32>(P, batch, smem, s);
+  if (P.S == 6 && P.R == 16) return launch_tail_backward_t<6, 16>(P, batch, smem, s);
+  return launch_tail_backward_t<0, 0>(P, batch, smem, s);
 }
 
 
