@@ -442,9 +442,17 @@ struct ConvParams {
 
 /* Shared-memory geometry of one CTA: CC input channels of the (TX+2) x (TY+2) x (TZ+2) input tile,
  * z-pitch PZ a multiple of 4 floats so that staging and the inner loop use 128 / 64-bit accesses. */
-template <int CO, int ZR>
+#ifndef SDFR_CONV_CC_ZR4
+#define SDFR_CONV_CC_ZR4 8 /* input channels staged per pass by the 32-deep tiles (tuning knob) */
+#endif
+#ifndef SDFR_CONV_YR2_MAX_ACC
+#define SDFR_CONV_YR2_MAX_ACC 0 /* CO*ZR up to which a thread computes two output rows (tuning knob, off) */
+#endif
+template <int CO, int ZR, int YR = 1>
 struct ConvTile {
-  static constexpr int K = 3, TX = 4, TY = 8, TZ = 8 * ZR, CC = 8;
+  static constexpr int K = 3, TX = 4, TY = 8 * YR, TZ = 8 * ZR;
+  /* channels staged per pass: the tile must leave room for >= 3 CTAs per SM */
+  static constexpr int CC = YR == 2 ? 4 : (ZR == 4 ? SDFR_CONV_CC_ZR4 : 8);
   static constexpr int IX = TX + K - 1, IY = TY + K - 1, IZ = TZ + K - 1;
   static constexpr int PZ = ((IZ + 3) / 4) * 4;
   static constexpr int CH = IX * IY * PZ; /* floats per staged channel */
@@ -457,10 +465,22 @@ struct ConvTile {
  * so there is no separate clearing pass.  First version: per-element staging with 2 slots per
  * thread and plane -- ~29 instructions per element, 43 % of all instructions executed
  * (profiles/r01j_ncu_decoder.txt: 127 M warp instructions for 56 M warp-FFMAs). */
-template <int CO, int ZR, bool DGRAD, int VEC>
-__global__ void __launch_bounds__(256, (CO * ZR <= 16 ? 4 : (CO * ZR <= 32 ? 3 : (CO * ZR <= 64 ? 2 : 1))))
+/* KS > 1: a thread-block cluster of KS CTAs (cluster dims (1,1,KS)) splits the INPUT channels of one
+ * tile; the partial sums meet in the leader's shared memory over DSMEM.  For the smallest stage
+ * (8^3 -> 6^3: 2 tiles per volume, 128 CTAs of 9 k instructions per thread at 64 hypotheses --
+ * one CTA per SM, latency-bound at 8 warps) this quadruples the resident warps without shrinking
+ * the per-thread accumulator block (splitting the OUTPUT channels instead was measured slower). */
+/* YR = 2: a thread computes two adjacent output rows (y), sharing the 4 input rows they read and
+ * every weight vector: shared-memory wavefronts per FFMA drop from 0.19 to 0.115 (the 32-deep tile is
+ * co-limited by the LDS pipe at 69 % with the FMA pipe at 58 %, profiles/r01s_ncu_decoder.txt).
+ * Measured (-DSDFR_CONV_YR2_MAX_ACC=16 / 32): no gain at 64 hypotheses -- 108 us either way for the
+ * 8 -> 4 channel stage, 151 instead of 133 us for its data gradient with 64 accumulators; half as many,
+ * twice as long CTAs quantise worse into waves of 3 CTAs per SM.  Left as a knob, off by default. */
+template <int CO, int ZR, bool DGRAD, int VEC, int KS = 1, int YR = 1>
+__global__ void __launch_bounds__(256, (CO * ZR * YR <= 16 ? 4 : (CO * ZR * YR <= 32 ? 3 : (CO * ZR * YR <= 64 ? 2 : 1))))
 sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
-  using T = ConvTile<CO, ZR>;
+  using T = ConvTile<CO, ZR, YR>;
+  constexpr int NZ = YR * ZR; /* accumulators per output channel: [row r][z i] at r * ZR + i */
   constexpr int K = 3, TX = T::TX, TY = T::TY, TZ = T::TZ, CC = T::CC;
   constexpr int IX = T::IX, IY = T::IY, PZ = T::PZ;
   extern __shared__ __align__(16) float conv_smem[];
@@ -468,7 +488,8 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   float* __restrict__ ws = conv_smem + P.cc * T::CH;  /* [CC][27][CO] */
 
   const int b = blockIdx.y + P.z_offset;
-  const int co0 = blockIdx.z * CO, COT = P.co_total;
+  const int kr = KS > 1 ? (int)(blockIdx.z % KS) : 0; /* rank in the cluster = input-channel slice */
+  const int co0 = (int)(blockIdx.z / KS) * CO, COT = P.co_total;
   int t = blockIdx.x;
   const int tz = t % P.tiles_z; t /= P.tiles_z;
   const int tyy = t % P.tiles_y;
@@ -480,14 +501,15 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   const size_t in_vol = (size_t)n_in * n_in * n_in;
   constexpr int shift = DGRAD ? K - 1 : 0; /* input coordinate = output coordinate + tap - shift */
 
-  float acc[CO][ZR];
+  float acc[CO][NZ];
 #pragma unroll
   for (int co = 0; co < CO; ++co)
 #pragma unroll
-    for (int i = 0; i < ZR; ++i) acc[co][i] = 0.0f;
+    for (int i = 0; i < NZ; ++i) acc[co][i] = 0.0f;
 
-  for (int ci0 = 0; ci0 < CI; ci0 += CC) {
-    const int nc = CI - ci0 < CC ? CI - ci0 : CC;
+  const int ci_begin = kr * (CI / KS), ci_end = ci_begin + CI / KS; /* CI % KS == 0 (launcher) */
+  for (int ci0 = ci_begin; ci0 < ci_end; ci0 += CC) {
+    const int nc = ci_end - ci0 < CC ? ci_end - ci0 : CC;
     /* stage the input tile */
     constexpr int SL = PZ / VEC; /* slots per row */
     const int n_slots = nc * IX * IY * SL;
@@ -545,22 +567,25 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
     for (int c = 0; c < nc; ++c) {
 #pragma unroll
       for (int dx = 0; dx < K; ++dx) {
+        float v[YR + K - 1][ZR + K - 1]; /* the input rows this thread's YR output rows read */
 #pragma unroll
-        for (int dy = 0; dy < K; ++dy) {
-          float v[ZR + K - 1];
-          const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly + dy) * PZ + z0;
+        for (int ry = 0; ry < YR + K - 1; ++ry) {
+          const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly * YR + ry) * PZ + z0;
           if constexpr (ZR == 4) {
             const float4 a = *reinterpret_cast<const float4*>(row);
             const float2 e2 = *reinterpret_cast<const float2*>(row + 4);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e2.x; v[5] = e2.y;
+            v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = a.z; v[ry][3] = a.w; v[ry][4] = e2.x; v[ry][5] = e2.y;
           } else if constexpr (ZR == 2) {
             const float2 a = *reinterpret_cast<const float2*>(row);
             const float2 e2 = *reinterpret_cast<const float2*>(row + 2);
-            v[0] = a.x; v[1] = a.y; v[2] = e2.x; v[3] = e2.y;
+            v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = e2.x; v[ry][3] = e2.y;
           } else {
 #pragma unroll
-            for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
+            for (int i = 0; i < ZR + K - 1; ++i) v[ry][i] = row[i];
           }
+        }
+#pragma unroll
+        for (int dy = 0; dy < K; ++dy) {
 #pragma unroll
           for (int dz = 0; dz < K; ++dz) {
             const float4* __restrict__ wp =
@@ -569,56 +594,111 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
             for (int c4 = 0; c4 < CO / 4; ++c4) {
               const float4 w4 = wp[c4];
 #pragma unroll
-              for (int i = 0; i < ZR; ++i) {
-                acc[4 * c4 + 0][i] = fmaf(w4.x, v[i + dz], acc[4 * c4 + 0][i]);
-                acc[4 * c4 + 1][i] = fmaf(w4.y, v[i + dz], acc[4 * c4 + 1][i]);
-                acc[4 * c4 + 2][i] = fmaf(w4.z, v[i + dz], acc[4 * c4 + 2][i]);
-                acc[4 * c4 + 3][i] = fmaf(w4.w, v[i + dz], acc[4 * c4 + 3][i]);
+              for (int r = 0; r < YR; ++r) {
+#pragma unroll
+                for (int i = 0; i < ZR; ++i) {
+                  const float x = v[r + dy][i + dz];
+                  acc[4 * c4 + 0][r * ZR + i] = fmaf(w4.x, x, acc[4 * c4 + 0][r * ZR + i]);
+                  acc[4 * c4 + 1][r * ZR + i] = fmaf(w4.y, x, acc[4 * c4 + 1][r * ZR + i]);
+                  acc[4 * c4 + 2][r * ZR + i] = fmaf(w4.z, x, acc[4 * c4 + 2][r * ZR + i]);
+                  acc[4 * c4 + 3][r * ZR + i] = fmaf(w4.w, x, acc[4 * c4 + 3][r * ZR + i]);
+                }
               }
             }
           }
         }
       }
     }
-    if (ci0 + CC < CI) __syncthreads();
+    if (ci0 + CC < ci_end) __syncthreads();
   }
 
-  const int ox = X0 + lx, oy = Y0 + ly;
-  if (ox >= n_out || oy >= n_out) return;
+  if constexpr (KS > 1) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __syncthreads(); /* everyone is done with the tile: its memory becomes the exchange buffer */
+    float* red = conv_smem; /* [CO * NZ][256] */
+    if (kr != 0) {
+#pragma unroll
+      for (int co = 0; co < CO; ++co)
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) red[(co * NZ + i) * 256 + threadIdx.x] = acc[co][i];
+    }
+    cluster.sync();
+    if (kr == 0) {
+      for (int r = 1; r < KS; ++r) {
+        const float* __restrict__ peer = cluster.map_shared_rank(red, r);
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+#pragma unroll
+          for (int i = 0; i < NZ; ++i) acc[co][i] += peer[(co * NZ + i) * 256 + threadIdx.x];
+      }
+    }
+    cluster.sync(); /* peers keep their shared memory alive until the leader has read it */
+    if (kr != 0) return;
+  }
+
+  const int ox = X0 + lx;
+  if (ox >= n_out) return;
   const size_t out_vol = (size_t)n_out * n_out * n_out;
 #pragma unroll
-  for (int co = 0; co < CO; ++co) {
-    const float bias = (!DGRAD && P.bias) ? __ldg(P.bias + co0 + co) : 0.0f;
-    float* __restrict__ o = P.out + ((size_t)b * COT + co0 + co) * out_vol + ((size_t)ox * n_out + oy) * n_out;
+  for (int r = 0; r < YR; ++r) {
+    const int oy = Y0 + ly * YR + r;
+    if (oy >= n_out) continue;
 #pragma unroll
-    for (int i = 0; i < ZR; ++i) {
-      const int oz = Z0 + z0 + i;
-      if (oz < n_out) {
-        float v = acc[co][i] + bias;
-        if (!DGRAD && P.relu) v = v > 0.0f ? v : 0.0f;
-        o[oz] = v;
+    for (int co = 0; co < CO; ++co) {
+      const float bias = (!DGRAD && P.bias) ? __ldg(P.bias + co0 + co) : 0.0f;
+      float* __restrict__ o = P.out + ((size_t)b * COT + co0 + co) * out_vol + ((size_t)ox * n_out + oy) * n_out;
+#pragma unroll
+      for (int i = 0; i < ZR; ++i) {
+        const int oz = Z0 + z0 + i;
+        if (oz < n_out) {
+          float v = acc[co][r * ZR + i] + bias;
+          if (!DGRAD && P.relu) v = v > 0.0f ? v : 0.0f;
+          o[oz] = v;
+        }
       }
     }
   }
 }
 
-template <int CO, int ZR, bool DGRAD, int VEC>
+template <int CO, int ZR, bool DGRAD, int VEC, int KS = 1, int YR = 1>
 int launch_conv3_v(ConvParams P, int batch, cudaStream_t s) {
-  using T = ConvTile<CO, ZR>;
+  using T = ConvTile<CO, ZR, YR>;
   const int tiles_x = (P.n_out + T::TX - 1) / T::TX;
   P.tiles_y = (P.n_out + T::TY - 1) / T::TY;
   P.tiles_z = (P.n_out + T::TZ - 1) / T::TZ;
-  P.cc = P.CI < T::CC ? P.CI : T::CC;
-  const size_t smem = T::bytes(P.cc);
+  const int per_cta = P.CI / KS;
+  P.cc = per_cta < T::CC ? per_cta : T::CC;
+  size_t smem = T::bytes(P.cc);
+  if (KS > 1 && smem < sizeof(float) * CO * ZR * YR * 256) smem = sizeof(float) * CO * ZR * YR * 256;
+  auto kernel = sdfr_conv3_kernel<CO, ZR, DGRAD, VEC, KS, YR>;
   if (smem > 48 * 1024) {
-    const cudaError_t e = cudaFuncSetAttribute(sdfr_conv3_kernel<CO, ZR, DGRAD, VEC>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail((int)e, "conv3d: shared memory opt-in failed");
   }
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
-    const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535, P.co_total / CO);
-    sdfr_conv3_kernel<CO, ZR, DGRAD, VEC><<<grid, 256, smem, s>>>(P);
+    const dim3 grid(tiles_x * P.tiles_y * P.tiles_z, batch - z0 < 65535 ? batch - z0 : 65535,
+                    (P.co_total / CO) * KS);
+    if (KS == 1) {
+      kernel<<<grid, 256, smem, s>>>(P);
+    } else {
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = grid;
+      cfg.blockDim = dim3(256);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = s;
+      cudaLaunchAttribute attr;
+      attr.id = cudaLaunchAttributeClusterDimension;
+      attr.val.clusterDim.x = 1;
+      attr.val.clusterDim.y = 1;
+      attr.val.clusterDim.z = KS;
+      cfg.attrs = &attr;
+      cfg.numAttrs = 1;
+      const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, P);
+      if (e != cudaSuccess) return fail((int)e, "conv3d: cluster launch failed");
+    }
   }
   return 0;
 }
@@ -628,10 +708,20 @@ int launch_conv3_v(ConvParams P, int batch, cudaStream_t s) {
 template <int CO, int ZR, bool DGRAD>
 int launch_conv3_t(const ConvParams& P, int batch, cudaStream_t s) {
   const uintptr_t a = reinterpret_cast<uintptr_t>(P.in) | reinterpret_cast<uintptr_t>(P.mask);
+  if constexpr (ZR == 1 && CO <= 16) {
+    /* smallest stage, too few tiles to fill the SMs: 4-CTA clusters over the input channels */
+    const long ctas = (long)((P.n_out + 3) / 4) * ((P.n_out + 7) / 8) * ((P.n_out + 7) / 8) * batch *
+                      (P.co_total / CO);
+    if (P.CI % 16 == 0 && ctas < 296) {
+      if (!DGRAD && P.n_in % 4 == 0 && (a & 15) == 0) return launch_conv3_v<CO, ZR, DGRAD, DGRAD ? 2 : 4, 4>(P, batch, s);
+      if (P.n_in % 2 == 0 && (a & 7) == 0) return launch_conv3_v<CO, ZR, DGRAD, 2, 4>(P, batch, s);
+    }
+  }
+  constexpr int YR = (ZR >= 2 && CO * ZR <= SDFR_CONV_YR2_MAX_ACC) ? 2 : 1;
   if constexpr (!DGRAD)
-    if (P.n_in % 4 == 0 && (a & 15) == 0) return launch_conv3_v<CO, ZR, DGRAD, 4>(P, batch, s);
-  if (P.n_in % 2 == 0 && (a & 7) == 0) return launch_conv3_v<CO, ZR, DGRAD, 2>(P, batch, s);
-  return launch_conv3_v<CO, ZR, DGRAD, 1>(P, batch, s);
+    if (P.n_in % 4 == 0 && (a & 15) == 0) return launch_conv3_v<CO, ZR, DGRAD, 4, 1, YR>(P, batch, s);
+  if (P.n_in % 2 == 0 && (a & 7) == 0) return launch_conv3_v<CO, ZR, DGRAD, 2, 1, YR>(P, batch, s);
+  return launch_conv3_v<CO, ZR, DGRAD, 1, 1, YR>(P, batch, s);
 }
 
 /* z-extent of the CTA tile (8 * ZR) follows the volume: 32 for n_out > 16, 16 for > 8, else 8 --

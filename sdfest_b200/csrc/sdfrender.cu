@@ -25,6 +25,7 @@
  *
  * No tensor cores: the path is a dependent gather chain, not a contraction.
  */
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
