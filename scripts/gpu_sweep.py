@@ -8,7 +8,7 @@ each, per-iteration all_gather of the per-hypothesis losses over NCCL, global ar
 
 Every rank owns a contiguous shard (estimation.shard_range); within the shard the hypotheses of one
 category share ONE grid (sdf_stride = 0), so a rank runs three fused optimisers (3 launches per
-iteration each, replayed from CUDA graphs).  Prints one JSON line on rank 0 and writes
+iteration each), the rank's whole iteration replayed as one CUDA graph.  Prints one JSON line on rank 0 and writes
 gpurun_out/<tag>_sweep_n<G>.json.  Time = CUDA events around the ITER iterations, max over ranks.
 """
 import json
@@ -52,20 +52,39 @@ for c, name in enumerate(syn.CATEGORIES):
     grid = syn.category_grid(name, R, dev)[None].contiguous()
     opt = HypothesisOptimizer(cam, THR, obs, hyp["position"][sel], hyp["orientation"][sel],
                               1.0 / hyp["inv_scale"][sel], sdf=grid, max_points=20000)
-    opt.capture()
     opts.append(opt)
     index.append(sel)
 index = torch.cat(index)
 local_losses = torch.empty(hi - lo, device=dev)
 
 
-def iteration():
+def local_iteration():
     off = 0
     for opt in opts:
         l = opt.step()
         local_losses[off:off + l.numel()] = l
         off += l.numel()
-    return gather_losses(local_losses)  # the path's only exchange: (hi - lo) floats per rank
+
+
+# the rank's whole iteration (three categories x three launches + the loss concatenation) as ONE graph
+side = torch.cuda.Stream(dev)
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(2):
+        local_iteration()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    local_iteration()
+
+
+SIZES = [h - l for l, h in (shard_range(N_TOTAL, r, world) for r in range(world))]
+
+
+def iteration():
+    graph.replay()
+    return gather_losses(local_losses, sizes=SIZES)  # the path's only exchange: (hi - lo) floats per rank
 
 
 for _ in range(3):

@@ -76,6 +76,15 @@ def _worker(rank, world, port, n_total, q):
             losses[0] = float("nan")  # a hypothesis without overlap must never win
             losses[-1] = 0.25         # the global best lives on rank 1
         full = gather_losses(losses)
+        # shard sizes known up front (shard_range): same result, no size exchange per call
+        known = [h - l for l, h in (shard_range(n_total, r, world) for r in range(world))]
+        again = gather_losses(losses, sizes=known)
+        assert torch.equal(torch.nan_to_num(full), torch.nan_to_num(again))
+        try:
+            gather_losses(losses, sizes=[1] * world if known != [1] * world else [2] * world)
+            raise AssertionError("wrong shard sizes must be rejected")
+        except ValueError:
+            pass
         idx, val = global_best(losses, lo)
         q.put((rank, full.tolist(), idx, val))
     finally:
