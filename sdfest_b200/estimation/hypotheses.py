@@ -185,13 +185,13 @@ class HypothesisOptimizer:
             R = int(sdf.shape[-1])
             stride = 0 if sdf.shape[0] == 1 else R ** 3
             self._R = R
-            self._grids = _grid_operand(sdf, R, stride, B, W * H)  # (tensor, stride, layout), made once
+            self._grid_op = _grid_operand(sdf, R, stride, B, W * H)  # (tensor, stride, layout), made once
             self._g_sdf = self._g_sdf_pc = None
         else:
             R = int(self.decoder.volume_size)
             self._R = R
             SK = _skewed_elems(R)
-            self._grids = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
+            self._grid_op = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
             self._g_sdf = torch.empty((B, R ** 3), dtype=torch.float32, device=dev)
             self._g_sdf_pc = torch.empty((B, R ** 3), dtype=torch.float32, device=dev) if M else None
         # second stream: the point loss runs beside the render (both only read the grids), the
@@ -217,7 +217,7 @@ class HypothesisOptimizer:
         lib, b = _lib.lib(), self._buf
         B, R, M = self.position.shape[0], self._R, self._M
         W, H, cx, cy, fx, fy = _camera_params(self.camera)
-        grids, gstride, layout = self._grids
+        grids, gstride, layout = self._grid_op
         dec, x = self.decoder, None
         main, side = torch.cuda.current_stream(), self._side
 
