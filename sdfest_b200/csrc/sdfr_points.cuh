@@ -66,6 +66,9 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
   const float tx = __ldg(P.position + 3 * b + 0), ty = __ldg(P.position + 3 * b + 1);
   const float tz = __ldg(P.position + 3 * b + 2);
   const float s = __ldg(P.scale + b);
+  /* one reciprocal per hypothesis instead of nine IEEE divisions per point (1 ulp per quotient;
+   * the reference evaluates obj / scale and offsets / grid_size in torch, losses.py:81, 104) */
+  const float rs = 1.0f / s, rh = 1.0f / G.h;
   const float up = BACKWARD ? (P.upstream ? __ldg(P.upstream + b) : 1.0f) : 0.0f;
   const float* __restrict__ pts = P.points + (size_t)b * P.points_stride;
   const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
@@ -91,16 +94,16 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
     if (m < P.n_points) {
       const float dx = __ldg(pts + 3 * m + 0) - tx, dy = __ldg(pts + 3 * m + 1) - ty;
       const float dz = __ldg(pts + 3 * m + 2) - tz;
-      const float x0 = (r00 * dx + r01 * dy + r02 * dz) / s;
-      const float x1 = (r10 * dx + r11 * dy + r12 * dz) / s;
-      const float x2 = (r20 * dx + r21 * dy + r22 * dz) / s;
+      const float x0 = (r00 * dx + r01 * dy + r02 * dz) * rs;
+      const float x1 = (r10 * dx + r11 * dy + r12 * dz) * rs;
+      const float x2 = (r20 * dx + r21 * dy + r22 * dz) * rs;
       const float f0 = floorf((x0 + 1.0f) * half_rm1), f1 = floorf((x1 + 1.0f) * half_rm1);
       const float f2 = floorf((x2 + 1.0f) * half_rm1);
       const bool outside = fminf(f0, fminf(f1, f2)) < 0.0f || fmaxf(f0, fmaxf(f1, f2)) > rm2f;
       if (!(outside || !(f0 == f0) || !(f1 == f1) || !(f2 == f2))) { /* else contributes 0 */
         const int ix = (int)f0, iy = (int)f1, iz = (int)f2;
-        const float u0 = (x0 - (f0 * G.h - 1.0f)) / G.h, u1 = (x1 - (f1 * G.h - 1.0f)) / G.h;
-        const float u2 = (x2 - (f2 * G.h - 1.0f)) / G.h;
+        const float u0 = (x0 - (f0 * G.h - 1.0f)) * rh, u1 = (x1 - (f1 * G.h - 1.0f)) * rh;
+        const float u2 = (x2 - (f2 * G.h - 1.0f)) * rh;
         const Corners k = gather<0>(grid, G, ix, iy, iz);
         /* losses.py:107-131: x first, then y, then z */
         const float a0 = k.c000 * (1 - u0) + k.c100 * u0; /* y0 z0 */
@@ -134,15 +137,15 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
             const float dv1 = (a2 - a0) * (1 - u2) + (a3 - a1) * u2;
             const float dv2 = b1 - b0;
             /* dL/dx = g * s * dv/du / h ;  x = Rm d / s */
-            const float c0 = g * s / G.h;
+            const float c0 = g * s * rh;
             const float gx0 = c0 * dv0, gx1 = c0 * dv1, gx2 = c0 * dv2;
-            const float gy0 = gx0 / s, gy1 = gx1 / s, gy2 = gx2 / s; /* dL/d(Rm d) */
+            const float gy0 = gx0 * rs, gy1 = gx1 * rs, gy2 = gx2 * rs; /* dL/d(Rm d) */
             /* position: d = p - t */
             acc[0] -= r00 * gy0 + r10 * gy1 + r20 * gy2;
             acc[1] -= r01 * gy0 + r11 * gy1 + r21 * gy2;
             acc[2] -= r02 * gy0 + r12 * gy1 + r22 * gy2;
             /* scale: val = v s, dx/ds = -x/s */
-            acc[7] += g * v - (gx0 * x0 + gx1 * x1 + gx2 * x2) / s;
+            acc[7] += g * v - (gx0 * x0 + gx1 * x1 + gx2 * x2) * rs;
             /* unit quaternion: dL/dq_k = gy . (dRm/dq_k d) */
             acc[3] += gy0 * (2 * qy * dy + 2 * qz * dz) + gy1 * (2 * qy * dx - 4 * qx * dy + 2 * qw * dz) +
                       gy2 * (2 * qz * dx - 2 * qw * dy - 4 * qx * dz);
@@ -204,7 +207,10 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
 
 template <bool BACKWARD, bool WITH_LOSS = false>
 int launch_point_loss(PointParams P, int batch, cudaStream_t s) {
-  int gx = (P.n_points + 255) / 256;
+  /* ~4 points per thread: the per-thread prologue (rotation matrix, reciprocals) and the CTA
+   * reduction of the eight pose gradients cost about half as much as one point */
+  int gx = (P.n_points + 1023) / 1024;
+  if ((long)gx * batch < 592) gx = (P.n_points + 255) / 256; /* few hypotheses: keep the SMs busy */
   gx = gx < 1 ? 1 : (gx > 512 ? 512 : gx);
   const bool want_sdf = (P.flags & SDFR_GRAD_SDF) != 0;
   const bool want_pose =

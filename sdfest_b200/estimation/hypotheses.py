@@ -192,8 +192,10 @@ class HypothesisOptimizer:
             self._R = R
             SK = _skewed_elems(R)
             self._grid_op = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
-            self._g_sdf = torch.empty((B, R ** 3), dtype=torch.float32, device=dev)
-            self._g_sdf_pc = torch.empty((B, R ** 3), dtype=torch.float32, device=dev) if M else None
+            # both gradient grids in one allocation: one clear per iteration
+            self._g_both = torch.empty((2 if M else 1, B, R ** 3), dtype=torch.float32, device=dev)
+            self._g_sdf = self._g_both[0]
+            self._g_sdf_pc = self._g_both[1] if M else None
         # second stream: the point loss runs beside the render (both only read the grids), the
         # gradient-grid clears beside the decoder trunk; forks and joins are captured by capture()
         self._side = torch.cuda.Stream(dev) if self.overlap else None
@@ -231,9 +233,7 @@ class HypothesisOptimizer:
                 fn()
 
         def clear_grids():
-            self._g_sdf.zero_()
-            if self._g_sdf_pc is not None:
-                self._g_sdf_pc.zero_()
+            self._g_both.zero_()
 
         if dec is not None:
             on_side(clear_grids)
