@@ -42,7 +42,7 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=5)
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--hypotheses", type=int, default=64, help="hypotheses per GPU (weak scaling)")
-    p.add_argument("--cpu-sample", type=int, default=4,
+    p.add_argument("--cpu-sample", type=int, default=32,
                    help="hypotheses per step rendered by the CPU reference arm / cpu_baseline")
     p.add_argument("--e2e-chunk", type=int, default=8, help="hypotheses per pipelined chunk (e2e)")
     p.add_argument("--no-ref-ext", action="store_true",
@@ -181,9 +181,9 @@ def time_cpu(sample, steps, warmup):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
+    steps = max(1, min(args.steps, 50))
     warmup = max(1, min(args.warmup, 3))
-    sample = args.cpu_sample
+    sample = min(args.cpu_sample, args.hypotheses)
     mpix, ms, cores = time_cpu(sample, steps, warmup)
     desc = (f"{sample} of the {args.hypotheses} hypotheses of one step per timed step "
             f"(forward + masked L1 + backward through oracle/liboracle.so, OpenMP over image rows)")
@@ -544,10 +544,10 @@ def main():
 
     if not args.no_cpu_baseline:
         try:
-            mpix, ms, cores = time_cpu(args.cpu_sample, 3, 1)
+            mpix, ms, cores = time_cpu(min(args.cpu_sample, args.hypotheses), 40, 1)
             line["cpu_baseline"] = {
                 "value": mpix, "unit": UNIT, "cores": cores, "kind": "port",
-                "sample": f"{args.cpu_sample} hypotheses x {W}x{H} fwd+L1+bwd per step, 3 steps (oracle/liboracle.so, OpenMP)"}
+                "sample": f"{args.cpu_sample} hypotheses x {W}x{H} fwd+L1+bwd per step, 40 steps (oracle/liboracle.so, OpenMP)"}
         except Exception as e:  # the oracle is a checker, never required by the product path
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port",
                                     "sample": f"unavailable: {e}"}
