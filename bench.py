@@ -542,7 +542,7 @@ def main():
         "lib": lib.sdfr_build_info().decode(),
     }
 
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported at N = 1 only
         try:
             mpix, ms, cores = time_cpu(min(args.cpu_sample, args.hypotheses), 40, 1)
             line["cpu_baseline"] = {
