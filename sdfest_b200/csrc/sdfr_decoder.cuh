@@ -564,44 +564,87 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
       ws[e] = v;
     }
     __syncthreads();
-    for (int c = 0; c < nc; ++c) {
+    if constexpr (YR == 1) {
+      /* one row per (dx, dy) at a time: loading the three rows of a dx up front (as the YR = 2 path
+       * below must) costs the 8 -> 4 channel stage 12 us -- more live registers, later first FFMA */
+      for (int c = 0; c < nc; ++c) {
 #pragma unroll
-      for (int dx = 0; dx < K; ++dx) {
-        float v[YR + K - 1][ZR + K - 1]; /* the input rows this thread's YR output rows read */
+        for (int dx = 0; dx < K; ++dx) {
 #pragma unroll
-        for (int ry = 0; ry < YR + K - 1; ++ry) {
-          const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly * YR + ry) * PZ + z0;
-          if constexpr (ZR == 4) {
-            const float4 a = *reinterpret_cast<const float4*>(row);
-            const float2 e2 = *reinterpret_cast<const float2*>(row + 4);
-            v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = a.z; v[ry][3] = a.w; v[ry][4] = e2.x; v[ry][5] = e2.y;
-          } else if constexpr (ZR == 2) {
-            const float2 a = *reinterpret_cast<const float2*>(row);
-            const float2 e2 = *reinterpret_cast<const float2*>(row + 2);
-            v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = e2.x; v[ry][3] = e2.y;
-          } else {
+          for (int dy = 0; dy < K; ++dy) {
+            float v[ZR + K - 1];
+            const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly + dy) * PZ + z0;
+            if constexpr (ZR == 4) {
+              const float4 a = *reinterpret_cast<const float4*>(row);
+              const float2 e2 = *reinterpret_cast<const float2*>(row + 4);
+              v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = e2.x; v[5] = e2.y;
+            } else if constexpr (ZR == 2) {
+              const float2 a = *reinterpret_cast<const float2*>(row);
+              const float2 e2 = *reinterpret_cast<const float2*>(row + 2);
+              v[0] = a.x; v[1] = a.y; v[2] = e2.x; v[3] = e2.y;
+            } else {
 #pragma unroll
-            for (int i = 0; i < ZR + K - 1; ++i) v[ry][i] = row[i];
-          }
-        }
+              for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
+            }
 #pragma unroll
-        for (int dy = 0; dy < K; ++dy) {
+            for (int dz = 0; dz < K; ++dz) {
+              const float4* __restrict__ wp =
+                  reinterpret_cast<const float4*>(ws + (c * 27 + (dx * K + dy) * K + dz) * CO);
 #pragma unroll
-          for (int dz = 0; dz < K; ++dz) {
-            const float4* __restrict__ wp =
-                reinterpret_cast<const float4*>(ws + (c * 27 + (dx * K + dy) * K + dz) * CO);
-#pragma unroll
-            for (int c4 = 0; c4 < CO / 4; ++c4) {
-              const float4 w4 = wp[c4];
-#pragma unroll
-              for (int r = 0; r < YR; ++r) {
+              for (int c4 = 0; c4 < CO / 4; ++c4) {
+                const float4 w4 = wp[c4];
 #pragma unroll
                 for (int i = 0; i < ZR; ++i) {
-                  const float x = v[r + dy][i + dz];
-                  acc[4 * c4 + 0][r * ZR + i] = fmaf(w4.x, x, acc[4 * c4 + 0][r * ZR + i]);
-                  acc[4 * c4 + 1][r * ZR + i] = fmaf(w4.y, x, acc[4 * c4 + 1][r * ZR + i]);
-                  acc[4 * c4 + 2][r * ZR + i] = fmaf(w4.z, x, acc[4 * c4 + 2][r * ZR + i]);
-                  acc[4 * c4 + 3][r * ZR + i] = fmaf(w4.w, x, acc[4 * c4 + 3][r * ZR + i]);
+                  acc[4 * c4 + 0][i] = fmaf(w4.x, v[i + dz], acc[4 * c4 + 0][i]);
+                  acc[4 * c4 + 1][i] = fmaf(w4.y, v[i + dz], acc[4 * c4 + 1][i]);
+                  acc[4 * c4 + 2][i] = fmaf(w4.z, v[i + dz], acc[4 * c4 + 2][i]);
+                  acc[4 * c4 + 3][i] = fmaf(w4.w, v[i + dz], acc[4 * c4 + 3][i]);
+                }
+              }
+            }
+          }
+        }
+      }
+    } else {
+      for (int c = 0; c < nc; ++c) {
+#pragma unroll
+        for (int dx = 0; dx < K; ++dx) {
+          float v[YR + K - 1][ZR + K - 1]; /* the input rows this thread's YR output rows read */
+#pragma unroll
+          for (int ry = 0; ry < YR + K - 1; ++ry) {
+            const float* __restrict__ row = tile + ((c * IX + lx + dx) * IY + ly * YR + ry) * PZ + z0;
+            if constexpr (ZR == 4) {
+              const float4 a = *reinterpret_cast<const float4*>(row);
+              const float2 e2 = *reinterpret_cast<const float2*>(row + 4);
+              v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = a.z; v[ry][3] = a.w; v[ry][4] = e2.x; v[ry][5] = e2.y;
+            } else if constexpr (ZR == 2) {
+              const float2 a = *reinterpret_cast<const float2*>(row);
+              const float2 e2 = *reinterpret_cast<const float2*>(row + 2);
+              v[ry][0] = a.x; v[ry][1] = a.y; v[ry][2] = e2.x; v[ry][3] = e2.y;
+            } else {
+#pragma unroll
+              for (int i = 0; i < ZR + K - 1; ++i) v[ry][i] = row[i];
+            }
+          }
+#pragma unroll
+          for (int dy = 0; dy < K; ++dy) {
+#pragma unroll
+            for (int dz = 0; dz < K; ++dz) {
+              const float4* __restrict__ wp =
+                  reinterpret_cast<const float4*>(ws + (c * 27 + (dx * K + dy) * K + dz) * CO);
+#pragma unroll
+              for (int c4 = 0; c4 < CO / 4; ++c4) {
+                const float4 w4 = wp[c4];
+#pragma unroll
+                for (int r = 0; r < YR; ++r) {
+#pragma unroll
+                  for (int i = 0; i < ZR; ++i) {
+                    const float x = v[r + dy][i + dz];
+                    acc[4 * c4 + 0][r * ZR + i] = fmaf(w4.x, x, acc[4 * c4 + 0][r * ZR + i]);
+                    acc[4 * c4 + 1][r * ZR + i] = fmaf(w4.y, x, acc[4 * c4 + 1][r * ZR + i]);
+                    acc[4 * c4 + 2][r * ZR + i] = fmaf(w4.z, x, acc[4 * c4 + 2][r * ZR + i]);
+                    acc[4 * c4 + 3][r * ZR + i] = fmaf(w4.w, x, acc[4 * c4 + 3][r * ZR + i]);
+                  }
                 }
               }
             }
