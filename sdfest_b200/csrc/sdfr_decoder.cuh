@@ -149,12 +149,27 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
       for (int g = rl; g < G; g += rows) {
         const int yb = ti0[4 * g];
         float r[4];
+        if (yb + 3 < S) {
+          /* the four source rows are consecutive: with compile-time S the 16 loads share four base
+           * addresses and differ by immediates (the clamped form below computes 16 addresses) */
+          const float* __restrict__ a0 = pa + yb * S + z0;
+          const float* __restrict__ a1 = pa + yb * S + z1;
+          const float* __restrict__ c0 = pb + yb * S + z0;
+          const float* __restrict__ c1 = pb + yb * S + z1;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = (yb + k < S ? yb + k : S - 1) * S;
-          const float a = lz0 * pa[row + z0] + lz1 * pa[row + z1];
-          const float c = lz0 * pb[row + z0] + lz1 * pb[row + z1];
-          r[k] = lx0 * a + lx1 * c;
+          for (int k = 0; k < 4; ++k) {
+            const float a = lz0 * a0[k * S] + lz1 * a1[k * S];
+            const float c = lz0 * c0[k * S] + lz1 * c1[k * S];
+            r[k] = lx0 * a + lx1 * c;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = (yb + k < S ? yb + k : S - 1) * S;
+            const float a = lz0 * pa[row + z0] + lz1 * pa[row + z1];
+            const float c = lz0 * pb[row + z0] + lz1 * pb[row + z1];
+            r[k] = lx0 * a + lx1 * c;
+          }
         }
         const float4* __restrict__ W = reinterpret_cast<const float4*>(wy + 16 * g);
 #pragma unroll
