@@ -102,3 +102,44 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libsdfrender.so"))
     with pytest.raises(RuntimeError, match="no CPU or PyTorch fallback"):
         _lib.lib()
+
+
+def _header_prototypes():
+    """{name: [C parameter declarations]} for every function the header declares."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(sdfr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",")]
+        protos[m.group(1)] = [] if params == ["void"] else params
+    return protos
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Same number of parameters and the same kind of parameter (pointer / int / long long / unsigned /
+    float) at every position: a silently shifted argument would corrupt a launch, not fail it."""
+    from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
+
+    protos = _header_prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, params in protos.items():
+        _, argtypes = _lib.SIGNATURES[name]
+        assert len(params) == len(argtypes), f"{name}: header has {len(params)} parameters, binding {len(argtypes)}"
+        for i, (decl, ct) in enumerate(zip(params, argtypes)):
+            if "*" in decl:
+                want = "pointer"
+            elif decl.startswith("long long"):
+                want = c_longlong
+            elif decl.startswith("unsigned"):
+                want = c_uint
+            elif decl.startswith("float"):
+                want = c_float
+            elif decl.startswith("int"):
+                want = c_int
+            else:
+                raise AssertionError(f"{name}: cannot classify parameter {decl!r}")
+            if want == "pointer":
+                ok = ct is c_void_p or (isinstance(ct, type) and issubclass(ct, ctypes._Pointer))
+            else:
+                ok = ct is want
+            assert ok, f"{name}: parameter {i} is {decl!r} in the header but {ct} in the binding"
