@@ -902,7 +902,10 @@ int sm_count() {
 
 int ctas_per_hypothesis(int batch, int W, int H) {
   const long long n_tiles = (long long)((W + kTileW - 1) / kTileW) * ((H + kTileH - 1) / kTileH);
-  long long target = (long long)sm_count() * 32;
+  /* 16 CTAs per SM in total for larger batches (measured at 64 hypotheses, profiles/r01zp_micro.json
+   * c2_cta_sweep: 2368 CTAs beat 4736 by 2 % forward / fused and 6 % backward); small batches keep 32
+   * so that a single large frame still gets one CTA per tile */
+  long long target = (long long)sm_count() * (batch >= 16 ? 16 : 32);
   if (const char* env = getenv("SDFR_TARGET_CTAS")) { /* tuning knob, see scripts/gpu_micro.py */
     const long long v = atoll(env);
     if (v > 0) target = v;
