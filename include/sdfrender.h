@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 6
+#define SDFR_ABI_VERSION 7
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -68,6 +68,10 @@ extern "C" {
  * (simple_renderer.py:399-408). */
 #define SDFR_SDF_GRAD_EXACT 0x10u
 #define SDFR_ZERO_GRADS 0x20u /* clear the requested gradient buffers before accumulating */
+/* sdfr_point_loss_fused only: loss_sum[b] += upstream[b] * sum_m |.| instead of the raw sum, so that
+ * hypotheses of different object instances (clouds of different sizes, padded to n_points with points
+ * outside the volume) carry their own pc_weight / n_points_b into the loss as well as the gradients */
+#define SDFR_LOSS_WEIGHTED 0x40u
 
 /* flags of sdfr_hypothesis_step */
 #define SDFR_STEP_CLEAR_INPUTS 0x100u /* zero the sums / gradient inputs after consuming them */
@@ -229,8 +233,9 @@ int sdfr_point_loss_backward(const float* points, long long points_stride, int n
 /*
  * sdfr_point_loss_forward and _backward in ONE traversal: valid whenever `upstream` does not depend
  * on this call's loss_sum -- in the loop it is the constant pc_weight / n_points
- * (estimation/simple_setup.py:447-452).  loss_sum as in _forward, gradients as in _backward;
- * SDFR_ZERO_GRADS clears loss_sum and the requested gradient buffers first.
+ * (estimation/simple_setup.py:447-452).  loss_sum as in _forward (times upstream[b] with
+ * SDFR_LOSS_WEIGHTED), gradients as in _backward; SDFR_ZERO_GRADS clears loss_sum and the requested
+ * gradient buffers first.
  */
 int sdfr_point_loss_fused(const float* points, long long points_stride, int n_points,
                           const float* sdf, int resolution, long long sdf_stride, int sdf_layout,

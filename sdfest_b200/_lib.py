@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -22,6 +22,7 @@ GRAD_INV_SCALE = 0x08
 GRAD_ALL = 0x0F
 SDF_GRAD_EXACT = 0x10
 ZERO_GRADS = 0x20
+LOSS_WEIGHTED = 0x40  # sdfr_point_loss_fused: loss_sum += upstream[b] * sum
 STEP_CLEAR_INPUTS = 0x100
 STEP_NO_UPDATE = 0x200
 LAYOUT_DENSE = 0

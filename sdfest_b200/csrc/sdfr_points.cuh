@@ -183,7 +183,8 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
     if (!BACKWARD) {
       if (t[0] != 0.0f) atomicAdd(P.loss_sum + b, t[0]);
     } else {
-      if (WITH_LOSS && t[8] != 0.0f) atomicAdd(P.loss_sum + b, t[8]);
+      if (WITH_LOSS && t[8] != 0.0f)
+        atomicAdd(P.loss_sum + b, (P.flags & SDFR_LOSS_WEIGHTED) ? up * t[8] : t[8]);
       if (P.flags & SDFR_GRAD_POSITION) {
         if (t[0] != 0.0f) atomicAdd(P.grad_position + 3 * b + 0, t[0]);
         if (t[1] != 0.0f) atomicAdd(P.grad_position + 3 * b + 1, t[1]);

@@ -1413,7 +1413,7 @@ int sdfr_point_loss_fused(const float* points, long long points_stride, int n_po
                           float* gp, float* gq, float* gscale, unsigned flags, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, scale, batch, 1, 1)) return rc;
   if (flags & SDFR_SDF_GRAD_EXACT) return fail(SDFR_E_FLAGS, "the point loss has one weight list");
-  if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gscale)) return rc;
+  if (int rc = check_backward_outputs(flags & ~SDFR_LOSS_WEIGHTED, gs, gs_stride, gp, gq, gscale)) return rc;
   if (n_points < 0 || points_stride < 0) return fail(SDFR_E_SHAPE, "negative n_points or stride");
   if (batch == 0) return 0;
   if (!loss_sum) return fail(SDFR_E_NULL, "loss_sum is NULL");

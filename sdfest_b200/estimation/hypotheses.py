@@ -81,6 +81,11 @@ class HypothesisOptimizer:
     estimation/configs/default.yaml:14-16).  ``decoder`` maps latents (B,L) to grids
     (B,1,R,R,R) (e.g. ``SDFVAE.decode``); without it ``sdf`` holds fixed grids (B|1,R,R,R).
 
+    Object instances: ``depth_obs`` (H,W) is one observation shared by all hypotheses; (K,H,W) with
+    ``instance`` (B,) compares hypothesis b with the depth map *and the observed points* of instance
+    ``instance[b]`` (default ``arange(B)``: one map per hypothesis), each instance's point loss
+    averaged over its own points -- the reference's loop run for K objects x B/K hypotheses at once.
+
     ``optimizer``: ``"fused"`` runs the whole iteration as direct C-ABI launches -- decoder tail,
     ``sdfr_compare_fused``, ``sdfr_point_loss_fused``, tail adjoint, and ONE
     ``sdfr_hypothesis_step`` kernel for the gradient chain rule, Adam on all four groups, the
@@ -96,7 +101,7 @@ class HypothesisOptimizer:
                  decoder: Optional[Callable] = None, depth_weight: float = 1.0,
                  pc_weight: float = 3.0, max_points: int = 0, group=None, optimizer: str = "auto",
                  lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8,
-                 overlap: bool = True):
+                 overlap: bool = True, instance: Optional[torch.Tensor] = None):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
@@ -125,13 +130,29 @@ class HypothesisOptimizer:
         if self.optimizer_impl == "torch":
             self.optimizer = torch.optim.Adam(groups, betas=self.betas, eps=self.eps,
                                               capturable=self.position.is_cuda)
-        # observed points, once (the only host sync), sub-sampled to a fixed size
-        pts = losses.depth_to_pointcloud(self.depth_obs, camera)
-        if max_points and pts.shape[0] > max_points:
-            sel = torch.randperm(pts.shape[0], device=pts.device,
-                                 generator=torch.Generator(pts.device).manual_seed(0))[:max_points]
-            pts = pts[sel]
-        self.points = pts.contiguous()
+        # observed points, once (the only host syncs), sub-sampled to a fixed size
+        B = self.position.shape[0]
+        self.point_counts = None  # (B,) points hypothesis b owns, when the clouds differ
+        if self.depth_obs.dim() == 2:
+            if instance is not None:
+                raise ValueError("`instance` needs one observed depth map per object instance (K,H,W)")
+            self.points = losses.subsample_points(losses.depth_to_pointcloud(self.depth_obs, camera),
+                                                  max_points)
+        else:
+            # object instances: hypothesis b is compared with the depth map and the points of instance
+            # instance[b] (default: one map per hypothesis)
+            if instance is None:
+                instance = torch.arange(B, device=self.depth_obs.device)
+            instance = instance.to(device=self.depth_obs.device, dtype=torch.int64)
+            if instance.shape != (B,) or self.depth_obs.dim() != 3:
+                raise ValueError("depth_obs (K,H,W) and instance (B,) expected")
+            if int(instance.min()) < 0 or int(instance.max()) >= self.depth_obs.shape[0]:
+                raise ValueError("instance index out of range")
+            clouds, counts = losses.depth_to_pointclouds(self.depth_obs, camera, max_points)
+            self.points = clouds.index_select(0, instance).contiguous()
+            self.point_counts = counts.index_select(0, instance)
+            self.depth_obs = self.depth_obs.index_select(0, instance).contiguous()
+        self.instance = instance
         self.last_losses = None
         self._graph = None
         self._shard_sizes = None  # exchanged on the first gather of run()
@@ -176,9 +197,19 @@ class HypothesisOptimizer:
         self._t = torch.zeros((B,), dtype=torch.int32, device=dev)
         self._lr = (ctypes.c_float * 4)(*self.lrs)
         self._depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
-        M = int(self.points.shape[0]) if self.pc_weight else 0
+        M = int(self.points.shape[-2]) if self.pc_weight else 0
         self._M = M
-        self._up_p = torch.full((B,), (self.pc_weight / M) if M else 0.0, dtype=torch.float32, device=dev)
+        if self.point_counts is None:
+            self._points_stride, self._point_flags = 0, 0
+            self._point_weight = (self.pc_weight / M) if M else 0.0
+            self._up_p = torch.full((B,), self._point_weight, dtype=torch.float32, device=dev)
+        else:
+            # per-instance clouds: hypothesis b weighs its own points with pc_weight / counts[b], in
+            # the gradients (upstream) and -- SDFR_LOSS_WEIGHTED -- in the loss sum itself
+            self._points_stride, self._point_flags = 3 * M, _lib.LOSS_WEIGHTED
+            self._point_weight = 1.0
+            n = self.point_counts.to(torch.float32)
+            self._up_p = torch.where(n > 0, self.pc_weight / n.clamp(min=1.0), torch.zeros_like(n)).contiguous()
         self._up_d = torch.full((B,), float(self.depth_weight), dtype=torch.float32, device=dev)
         if self.decoder is None:
             sdf = self.sdf.contiguous()
@@ -208,7 +239,7 @@ class HypothesisOptimizer:
             self.position.data_ptr(), self.orientation.data_ptr(), self.scale.data_ptr(),
             _ptr(self.latent), self._L, B, b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(),
             b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), float(self.depth_weight),
-            b["pl"].data_ptr() if M else None, (self.pc_weight / M) if M else 0.0,
+            b["pl"].data_ptr() if M else None, self._point_weight,
             b["g2_p"].data_ptr() if M else None, b["g2_q"].data_ptr() if M else None,
             b["g2_s"].data_ptr() if M else None, _ptr(g_latent), self._m.data_ptr(),
             self._v.data_ptr(), self._t.data_ptr(), self._lr, self.betas[0], self.betas[1], self.eps,
@@ -251,11 +282,11 @@ class HypothesisOptimizer:
 
         def point_loss():
             _lib.check(lib.sdfr_point_loss_fused(
-                self.points.data_ptr(), 0, M, grids.data_ptr(), R, gstride, layout,
+                self.points.data_ptr(), self._points_stride, M, grids.data_ptr(), R, gstride, layout,
                 self.position.data_ptr(), self._unit_q.data_ptr(), self.scale.data_ptr(), B,
                 self._up_p.data_ptr(), b["pl"].data_ptr(), _ptr(self._g_sdf_pc), R ** 3,
-                b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(), flags, _stream()),
-                "sdfr_point_loss_fused")
+                b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(),
+                flags | self._point_flags, _stream()), "sdfr_point_loss_fused")
 
         if M:
             on_side(point_loss)
@@ -333,7 +364,8 @@ class HypothesisOptimizer:
             return self._fused_iteration()
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
-        if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda:
+        if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda \
+                and self.point_counts is None:  # the chained operator takes one shared cloud
             loss = self._fused_loss(q)
             loss.sum().backward()
             self.optimizer.step()
@@ -346,12 +378,16 @@ class HypothesisOptimizer:
                                               (1.0 / self.scale).contiguous(), self.depth_obs,
                                               self.threshold, self.camera)
         loss = self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
-        if self.pc_weight and self.points.shape[0] > 0:
+        if self.pc_weight and self.points.shape[-2] > 0:
             # NB: the reference passes the un-normalised quaternion and lets pc_loss normalise it
             # (simple_setup.py:436-443, losses.py:56); q is already unit here, same value
-            loss = loss + self.pc_weight * losses.point_loss(
-                self.points, self.position, q, self.scale,
-                grids if grids.dim() == 4 else grids[None])
+            loss_pc = losses.point_loss(self.points, self.position, q, self.scale,
+                                        grids if grids.dim() == 4 else grids[None])
+            if self.point_counts is not None:  # mean over the instance's own points, not the padding
+                n = self.point_counts.to(loss_pc.dtype)
+                loss_pc = loss_pc * torch.where(n > 0, self.points.shape[1] / n.clamp(min=1.0),
+                                                torch.zeros_like(n))
+            loss = loss + self.pc_weight * loss_pc
         loss.sum().backward()
         self.optimizer.step()
         with torch.no_grad():

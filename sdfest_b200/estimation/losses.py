@@ -23,6 +23,38 @@ def depth_to_pointcloud(depth_image: torch.Tensor, camera, mask=None) -> torch.T
     return torch.stack([(cols.float() - cx) * z / fx, -(rows.float() - cy) * z / fy, -z], dim=1)
 
 
+def subsample_points(points: torch.Tensor, max_points: int) -> torch.Tensor:
+    """At most ``max_points`` of the (N,3) points, a fixed random subset (seed 0); 0 = keep all."""
+    if max_points and points.shape[0] > max_points:
+        sel = torch.randperm(points.shape[0], device=points.device,
+                             generator=torch.Generator(points.device).manual_seed(0))[:max_points]
+        points = points[sel]
+    return points.contiguous()
+
+
+PAD_COORDINATE = 1.0e6  # metres: outside every SDF volume, contributes exactly 0 (losses.py:84-101)
+
+
+def depth_to_pointclouds(depth_images: torch.Tensor, camera, max_points: int = 0):
+    """Observed depth maps (K,H,W) of K object instances -> (points (K,M,3), counts (K,)).
+
+    Instance k owns the first counts[k] points of row k (``depth_to_pointcloud`` + ``subsample_points``
+    of its own map); the rest of the row is padding far outside any SDF volume, where the reference's
+    ``pc_loss`` is exactly 0 (estimation/losses.py:84-101), so a mean over the instance's own points is
+    ``sum / counts[k]``.  M = the largest count (at least 1).  One host sync per instance, once per
+    observation, outside the loop.
+    """
+    if depth_images.dim() != 3:
+        raise RuntimeError(f"depth_images must be (K,H,W), got {tuple(depth_images.shape)}")
+    clouds = [subsample_points(depth_to_pointcloud(d, camera), max_points) for d in depth_images]
+    counts = torch.tensor([c.shape[0] for c in clouds], dtype=torch.int64)
+    M = max(int(counts.max()) if len(clouds) else 0, 1)
+    out = torch.full((len(clouds), M, 3), PAD_COORDINATE, dtype=torch.float32, device=depth_images.device)
+    for k, c in enumerate(clouds):
+        out[k, : c.shape[0]] = c
+    return out, counts.to(depth_images.device)
+
+
 def rotation_matrices(q: torch.Tensor) -> torch.Tensor:
     """(B,4) unit quaternions (x,y,z,w) -> (B,3,3) matrices of the INVERSE rotation, i.e. camera
     -> object, laid out as in losses.py:61-75."""

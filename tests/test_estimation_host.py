@@ -10,7 +10,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from sdfest_b200.differentiable_renderer import Camera
-from sdfest_b200.estimation import depth_to_pointcloud, gather_losses, global_best, pc_loss, shard_range
+from sdfest_b200.estimation import (depth_to_pointcloud, depth_to_pointclouds, gather_losses, global_best,
+                                    pc_loss, point_loss, shard_range, subsample_points)
 from util import GOLDEN_DIR
 
 
@@ -51,6 +52,39 @@ def test_depth_to_pointcloud_opengl_convention():
     # row-major order of nonzero(): (0,0) first
     assert torch.allclose(pts[0], torch.tensor([(0 - 1.5) * 1.0 / 2, -(0 - 1.0) * 1.0 / 2, -1.0]))
     assert torch.allclose(pts[1], torch.tensor([(3 - 1.5) * 2.0 / 2, -(1 - 1.0) * 2.0 / 2, -2.0]))
+
+
+def test_padded_instance_clouds_keep_every_instance_mean():
+    """K instances with clouds of different sizes: rows are the instance's own cloud followed by padding
+    that pc_loss maps to exactly 0, so sum / count is the reference's mean over the instance's points."""
+    z = np.load(os.path.join(GOLDEN_DIR, "pcloss_torus16.npz"))
+    t = lambda k: torch.tensor(z[k], dtype=torch.float32)  # noqa: E731
+    cam = Camera(16, 12, 14.0, 14.0, 8.0, 6.0, pixel_center=0.5)
+    g = torch.Generator().manual_seed(3)
+    depth = torch.zeros(3, 12, 16)
+    depth[0, 2:9, 3:12] = 0.9 + 0.05 * torch.rand(7, 9, generator=g)
+    depth[1, 5:7, 5:8] = 1.0  # instance 2 has no valid pixel at all
+    clouds, counts = depth_to_pointclouds(depth, cam)
+    assert counts.tolist() == [63, 6, 0] and clouds.shape == (3, 63, 3)
+    for k in range(3):
+        own = depth_to_pointcloud(depth[k], cam)
+        assert torch.equal(clouds[k, : counts[k]], own)
+        assert bool((clouds[k, counts[k]:] > 1e5).all())
+    capped, n_capped = depth_to_pointclouds(depth, cam, max_points=10)
+    assert n_capped.tolist() == [10, 6, 0] and capped.shape == (3, 10, 3)
+    assert torch.equal(capped[0], subsample_points(depth_to_pointcloud(depth[0], cam), 10))
+    # the padding contributes exactly 0 to the point loss of any pose
+    pos = torch.tensor([[0.0, 0.0, -0.95]]).repeat(3, 1)
+    quat = t("orientation")[None].repeat(3, 1)
+    scale = torch.full((3,), 0.4)
+    padded = point_loss(clouds, pos, quat, scale, t("sdf")[None])  # sum / M over the padded rows
+    for k in range(2):
+        own = point_loss(clouds[k, : counts[k]], pos[k:k + 1], quat[k:k + 1], scale[k:k + 1], t("sdf")[None])
+        assert float(own) > 0
+        assert torch.allclose(padded[k] * clouds.shape[1] / counts[k], own[0], rtol=1e-6)
+    assert float(padded[2]) == 0.0
+    with pytest.raises(RuntimeError):
+        depth_to_pointclouds(depth[0], cam)
 
 
 def test_shard_range_partitions_exactly():

@@ -1,4 +1,4 @@
-"""sdfr_hypothesis_step (ABI v6) and sdfr_point_loss_fused: the optimiser side of the loop.
+"""sdfr_hypothesis_step (ABI v7) and sdfr_point_loss_fused: the optimiser side of the loop.
 
 CPU: the numpy oracle (oracle/hypothesis_step.py) is pinned against torch autograd through the
 reference's chain (simple_setup.py:411, :431, :447-452) followed by torch.optim.Adam.step() and the
@@ -324,3 +324,79 @@ def test_fused_optimizer_at_full_c2_size(cuda_device):
     torch.testing.assert_close(torch.linalg.norm(b.orientation, dim=1), torch.ones(B, device=dev),
                                rtol=0, atol=1e-6)
     assert float(b.latent.detach().abs().max()) > 0
+
+
+def _instance_scene(dev, K, per):
+    """K object instances (different poses and apparent sizes -> clouds of different sizes, one of them
+    cropped to a few rows), `per` hypotheses each."""
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, render_depth_batched
+
+    W, H, R, thr = 160, 120, 32, 0.005
+    cam = Camera(W, H, W / 2, W / 2, W / 2, H / 2, pixel_center=0.5)
+    truth = syn.make_hypotheses(K, seed=5, device=dev)
+    truth["position"][:, 2] -= 0.08 * torch.arange(K, device=dev)  # farther away = fewer pixels
+    grid = syn.sdf_mug(R, dev)[None].contiguous()
+    obs = render_depth_batched(grid, truth["position"], truth["orientation"], truth["inv_scale"], thr,
+                               cam).contiguous()
+    obs[K - 1, : H // 2] = 0.0
+    hyp = syn.make_hypotheses(K * per, seed=1, device=dev)
+    instance = torch.arange(K * per, device=dev) // per
+    hyp["position"] = (hyp["position"] - hyp["position"].mean(0)) + truth["position"][instance]
+    return cam, thr, grid, obs, hyp, instance
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("max_points", [0, 500])
+def test_instance_batched_optimizer_equals_one_optimizer_per_instance(cuda_device, max_points):
+    """Object instances in one batch (depth map + observed points per instance, SDFR_LOSS_WEIGHTED):
+    the same numbers as running the shared-observation optimiser once per instance."""
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    K, per, steps = 3, 4, 5
+    cam, thr, grid, obs, hyp, instance = _instance_scene(cuda_device, K, per)
+    kw = dict(sdf=grid, optimizer="fused", max_points=max_points)
+    joint = HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                                instance=instance, **kw)
+    counts = joint.point_counts.view(K, per)[:, 0].tolist()
+    assert len(set(counts)) == K or max_points  # the clouds really differ in size
+    singles = [HypothesisOptimizer(cam, thr, obs[k], hyp["position"][k * per:(k + 1) * per],
+                                   hyp["orientation"][k * per:(k + 1) * per],
+                                   1.0 / hyp["inv_scale"][k * per:(k + 1) * per], **kw) for k in range(K)]
+    for _ in range(steps):
+        lj = joint.step().clone()
+        ls = torch.cat([s.step().clone() for s in singles])
+        torch.testing.assert_close(lj, ls, rtol=1e-4, atol=1e-6)
+    for name, lr in (("position", 1e-3), ("orientation", 1e-2), ("scale", 1e-3)):
+        pj = getattr(joint, name).detach()
+        ps = torch.cat([getattr(s, name).detach() for s in singles])
+        assert float((pj - ps).abs().max()) < 0.05 * lr * steps, name
+    assert float(lj.min()) > 0
+
+
+@pytest.mark.gpu
+def test_instance_batched_fused_matches_torch_composition(cuda_device):
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    K, per, steps = 3, 2, 4
+    cam, thr, grid, obs, hyp, instance = _instance_scene(cuda_device, K, per)
+
+    def make(optimizer):
+        return HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                                   sdf=grid, optimizer=optimizer, instance=instance)
+
+    a, b = make("torch"), make("fused")
+    la = a.step().clone()
+    b.capture(warmup=1)  # one eager iteration, then graph replay
+    torch.testing.assert_close(b.last_losses, la, rtol=2e-3, atol=1e-5)
+    for _ in range(steps):
+        la, lb = a.step().clone(), b.step().clone()
+        torch.testing.assert_close(lb, la, rtol=2e-3, atol=1e-5)
+    for name, lr in (("position", 1e-3), ("orientation", 1e-2), ("scale", 1e-3)):
+        assert float((getattr(a, name).detach() - getattr(b, name).detach()).abs().max()) < 0.05 * lr * (steps + 1)
+    with pytest.raises(ValueError):
+        HypothesisOptimizer(cam, thr, obs[0], hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                            sdf=grid, instance=instance)
+    with pytest.raises(ValueError):
+        HypothesisOptimizer(cam, thr, obs, hyp["position"], hyp["orientation"], 1.0 / hyp["inv_scale"],
+                            sdf=grid, instance=instance + 1)
