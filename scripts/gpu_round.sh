@@ -13,6 +13,7 @@ echo "== bench reference arm"; timeout 600 python bench.py --impl reference --st
 fi
 echo "== bench ours"; timeout 900 python bench.py --steps 50 --warmup 5 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "exit $?"; cat gpurun_out/${TAG}_bench.json; tail -5 gpurun_out/${TAG}_bench.err
 echo "== micro"; timeout 900 python scripts/gpu_micro.py ${TAG} > gpurun_out/${TAG}_micro.log 2>&1; echo "exit $?"; tail -100 gpurun_out/${TAG}_micro.log
+echo "== configs 3 and 5"; timeout 300 python scripts/gpu_configs.py ${TAG} > gpurun_out/${TAG}_configs.log 2>&1; echo "exit $?"; tail -5 gpurun_out/${TAG}_configs.log
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"sdfr_|emset" -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
    python bench.py --steps 2 --warmup 1 --no-ref-ext --no-cpu-baseline > gpurun_out/${TAG}_ncu_launch_bench.log 2>&1; echo "exit $?"

@@ -145,3 +145,36 @@ def test_two_rank_gloo_gather_and_argmin(n_total):
         for i, (a, b) in enumerate(zip(full, expect)):
             assert (np.isnan(a) and i == lo1) or a == b
         assert idx == n_total - 1 and val == 0.25
+
+
+def test_hypothesis_optimizer_instance_bookkeeping_on_cpu():
+    """Host side of object-instance batching (no kernels run): hypothesis b gets the depth map, the
+    cloud and the point count of instance[b]; malformed instance arguments are rejected."""
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    cam = Camera(16, 12, 14.0, 14.0, 8.0, 6.0, pixel_center=0.5)
+    depth = torch.zeros(2, 12, 16)
+    depth[0, 2:6, 3:9] = 1.0
+    depth[1, 5:7, 5:8] = 1.2
+    B = 5
+    instance = torch.tensor([0, 0, 1, 1, 0])
+    pos, quat, scale = torch.zeros(B, 3), torch.tensor([[0.0, 0, 0, 1]]).repeat(B, 1), torch.ones(B)
+    sdf = torch.zeros(1, 8, 8, 8)
+    opt = HypothesisOptimizer(cam, 0.005, depth, pos, quat, scale, sdf=sdf, instance=instance)
+    assert opt.optimizer_impl == "torch"
+    assert opt.point_counts.tolist() == [24, 24, 6, 6, 24]
+    assert opt.points.shape == (B, 24, 3) and opt.depth_obs.shape == (B, 12, 16)
+    assert torch.equal(opt.depth_obs[2], depth[1]) and torch.equal(opt.depth_obs[4], depth[0])
+    assert torch.equal(opt.points[3, :6], depth_to_pointcloud(depth[1], cam))
+    # default: one observation per hypothesis
+    one_each = HypothesisOptimizer(cam, 0.005, depth, pos[:2], quat[:2], scale[:2], sdf=sdf)
+    assert one_each.point_counts.tolist() == [24, 6]
+    # a single shared observation keeps the (M,3) cloud and has no per-hypothesis counts
+    shared = HypothesisOptimizer(cam, 0.005, depth[0], pos, quat, scale, sdf=sdf)
+    assert shared.point_counts is None and shared.points.shape == (24, 3)
+    for bad in (dict(depth_obs=depth[0], instance=instance),            # instance without (K,H,W)
+                dict(depth_obs=depth, instance=instance[:3]),             # wrong length
+                dict(depth_obs=depth, instance=instance + 1),             # out of range
+                dict(depth_obs=depth, instance=-instance)):
+        with pytest.raises(ValueError):
+            HypothesisOptimizer(cam, 0.005, bad["depth_obs"], pos, quat, scale, sdf=sdf, instance=bad["instance"])
