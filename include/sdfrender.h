@@ -280,6 +280,33 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
                          void* stream);
 
 /*
+ * Result selection of the loop, batched and without the reference's host synchronisation
+ * (estimation/simple_setup.py:177-211, called every iteration at :463).
+ * sdfr_inlier_count:  n_inlier[b] += #{pixels: |obs - est| / obs < rel_threshold}  (IEEE division: a
+ *   pixel with obs == 0 gives inf or nan and is never an inlier, as in the torch expression :183-184),
+ *   n_valid[b] += #{obs != 0} (:186).  depth [batch, height*width] = the estimate (e.g. the image
+ *   sdfr_compare_fused wrote); hypothesis b is compared with depth_obs + b*obs_stride (0 = one shared
+ *   observation).  SDFR_ZERO_GRADS clears both counters first.
+ * sdfr_track_best:  ratio[b] = n_inlier[b] / n_valid[b] (:187; 0/0 = nan); where best_iteration[b] < 0
+ *   (nothing kept yet, the reference's `is None`) or ratio[b] > best_ratio[b] (:205), best_ratio,
+ *   best_iteration (= step[b], the counter sdfr_hypothesis_step maintains; 0 if NULL) and the snapshots
+ *   best_position / best_orientation / best_scale / best_latent are overwritten with the current
+ *   parameters.  NOTE: the reference stores REFERENCES to the live parameter tensors (:207-210), which
+ *   the in-place optimiser keeps mutating, so its "best" estimate always equals the last iterate; this
+ *   entry point keeps the copy the code evidently intends.  ratio / latent / best_latent may be NULL.
+ *   SDFR_STEP_CLEAR_INPUTS zeroes n_inlier / n_valid after reading them.
+ */
+int sdfr_inlier_count(const float* depth, const float* depth_obs, long long obs_stride, int batch,
+                      int width, int height, float rel_threshold, float* n_inlier, float* n_valid,
+                      unsigned flags, void* stream);
+
+int sdfr_track_best(float* n_inlier, float* n_valid, const float* position, const float* orientation,
+                    const float* scale, const float* latent, int latent_size, int batch,
+                    const int* step, float* ratio, float* best_ratio, int* best_iteration,
+                    float* best_position, float* best_orientation, float* best_scale,
+                    float* best_latent, unsigned flags, void* stream);
+
+/*
  * Decoder tail: the last two operators of the reference SDF decoder,
  *   interpolate(x -> (R,R,R), mode="trilinear", align_corners=False)   sdfest/vae/sdf_vae.py:235-244
  *   Conv3d(channels -> 1, kernel_size=1), no ReLU                       sdfest/vae/sdf_vae.py:245-247

@@ -76,3 +76,31 @@ def hypothesis_step(state, loss_sum, n_overlap, gr_p, gr_q, gr_is, depth_weight,
     new = dict(position=pos, orientation=ori, scale=sc, latent=lat, m=m, v=v, t=t)
     unit = ori / np.linalg.norm(ori, axis=1, keepdims=True)
     return new, unit, 1.0 / sc, loss
+
+
+def inlier_counts(depth_obs, depth_est, rel_threshold):
+    """(n_inlier, n_valid) of simple_setup.py:177-188 for one image pair, in the float32 arithmetic
+    the reference runs in:  rel = |obs - est| / obs;  inliers = count(rel < threshold);  valid =
+    count(obs != 0).  A pixel with obs == 0 divides to inf or nan and never counts."""
+    obs = np.asarray(depth_obs, np.float32)
+    est = np.asarray(depth_est, np.float32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.abs(obs - est) / obs
+        n_inlier = int(np.count_nonzero(rel < np.float32(rel_threshold)))
+    return n_inlier, int(np.count_nonzero(obs))
+
+
+class BestEstimate:
+    """simple_setup.py:190-211 as the code intends it (copies, not the references to the live tensors
+    the reference stores at :207-210): keep the parameters with the highest inlier ratio so far."""
+
+    def __init__(self):
+        self.ratio, self.iteration, self.params = None, -1, None
+
+    def update(self, n_inlier, n_valid, iteration, params):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            ratio = np.float32(n_inlier) / np.float32(n_valid)
+        if self.ratio is None or ratio > self.ratio:  # :205
+            self.ratio, self.iteration = ratio, iteration
+            self.params = tuple(None if p is None else np.array(p, copy=True) for p in params)
+        return ratio

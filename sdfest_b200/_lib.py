@@ -66,6 +66,10 @@ SIGNATURES = {
     "sdfr_hypothesis_step": (
         c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, _P, c_float, _P, _P, _P, _P,
                 _P, _P, _P, ctypes.POINTER(c_float), c_float, c_float, c_float, _P, _P, _P, c_uint, _P]),
+    "sdfr_inlier_count": (
+        c_int, [_P, _P, c_longlong, c_int, c_int, c_int, c_float, _P, _P, c_uint, _P]),
+    "sdfr_track_best": (
+        c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_uint, _P]),
     "sdfr_decoder_tail_forward": (
         c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_longlong, c_int, _P]),
     "sdfr_decoder_tail_backward": (

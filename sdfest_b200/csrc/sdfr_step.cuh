@@ -230,4 +230,114 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
   }
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Result selection of the loop (estimation/simple_setup.py):
+ *   :177-188  _compute_inlier_ratio: rel = |depth_input - depth_estimate| / depth_input;
+ *             inliers = count(rel < relative_inlier_threshold); ratio = inliers / count(depth_input != 0)
+ *   :190-211  _update_best_estimate: keep the estimate with the highest ratio so far
+ *   :463      called every iteration, after optimizer.step(), with the depth rendered before the step
+ * The reference needs ~8 torch kernels and, through `inlier_ratio > self._best_inlier_ratio`, a host
+ * synchronisation per iteration.  Here: one streaming pass over the estimate the fused traversal wrote
+ * anyway (sdfr_inlier_count_kernel, two counters per hypothesis) and one thread per hypothesis for the
+ * bookkeeping (sdfr_track_best_kernel).  The division is IEEE (obs == 0 gives inf or nan: never an
+ * inlier, exactly as the torch expression).
+ * ---------------------------------------------------------------------------------------- */
+struct InlierParams {
+  const float* __restrict__ depth; /* [B, pixels] */
+  const float* __restrict__ obs;   /* + b * obs_stride */
+  long long obs_stride;
+  int pixels;
+  float threshold;
+  float* __restrict__ n_inlier; /* [B] += */
+  float* __restrict__ n_valid;  /* [B] += */
+  int z_offset;
+};
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+sdfr_inlier_count_kernel(const __grid_constant__ InlierParams P) {
+  __shared__ float red[8][2];
+  const int b = blockIdx.y + P.z_offset;
+  const float* __restrict__ est = P.depth + (size_t)b * P.pixels;
+  const float* __restrict__ obs = P.obs + (size_t)b * P.obs_stride;
+  const float thr = P.threshold;
+  float inl = 0.0f, val = 0.0f;
+  if (VEC) {
+    const int n4 = P.pixels >> 2;
+    const float4* __restrict__ e4 = reinterpret_cast<const float4*>(est);
+    const float4* __restrict__ o4 = reinterpret_cast<const float4*>(obs);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+      const float4 e = __ldg(e4 + i), o = __ldg(o4 + i);
+      val += (o.x != 0.0f) + (o.y != 0.0f) + (o.z != 0.0f) + (o.w != 0.0f);
+      inl += (__fdiv_rn(fabsf(o.x - e.x), o.x) < thr) + (__fdiv_rn(fabsf(o.y - e.y), o.y) < thr) +
+             (__fdiv_rn(fabsf(o.z - e.z), o.z) < thr) + (__fdiv_rn(fabsf(o.w - e.w), o.w) < thr);
+    }
+  } else {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < P.pixels; i += gridDim.x * 256) {
+      const float e = __ldg(est + i), o = __ldg(obs + i);
+      val += (o != 0.0f);
+      inl += (__fdiv_rn(fabsf(o - e), o) < thr);
+    }
+  }
+  inl = warp_sum(inl);
+  val = warp_sum(val);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[warp][0] = inl;
+    red[warp][1] = val;
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    /* counts are integers < 2^24: the float sums are exact in any order */
+    if (t != 0.0f) atomicAdd((threadIdx.x == 0 ? P.n_inlier : P.n_valid) + b, t);
+  }
+}
+
+struct TrackParams {
+  float* __restrict__ n_inlier; /* [B] */
+  float* __restrict__ n_valid;  /* [B] */
+  const float* __restrict__ position;
+  const float* __restrict__ orientation;
+  const float* __restrict__ scale;
+  const float* __restrict__ latent; /* [B,L] or NULL */
+  int latent_size, batch;
+  const int* __restrict__ step;     /* [B] iteration counter of sdfr_hypothesis_step, or NULL */
+  float* __restrict__ ratio;        /* [B] out or NULL */
+  float* __restrict__ best_ratio;   /* [B] */
+  int* __restrict__ best_iteration; /* [B], < 0 = nothing kept yet */
+  float* __restrict__ best_position;
+  float* __restrict__ best_orientation;
+  float* __restrict__ best_scale;
+  float* __restrict__ best_latent;
+  unsigned flags;
+};
+
+__global__ void __launch_bounds__(128)
+sdfr_track_best_kernel(const __grid_constant__ TrackParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.batch) return;
+  const float r = __fdiv_rn(P.n_inlier[b], P.n_valid[b]); /* 0/0 = nan, like the torch expression */
+  const int it = P.step ? P.step[b] : 0;
+  const bool first = P.best_iteration[b] < 0;
+  const bool better = first || r > P.best_ratio[b]; /* simple_setup.py:205 */
+  if (P.ratio) P.ratio[b] = r;
+  if (P.flags & SDFR_STEP_CLEAR_INPUTS) {
+    P.n_inlier[b] = 0.0f;
+    P.n_valid[b] = 0.0f;
+  }
+  if (!better) return;
+  P.best_ratio[b] = r;
+  P.best_iteration[b] = it;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) P.best_position[3 * b + i] = P.position[3 * b + i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) P.best_orientation[4 * b + i] = P.orientation[4 * b + i];
+  P.best_scale[b] = P.scale[b];
+  if (P.latent && P.best_latent)
+    for (int i = 0; i < P.latent_size; ++i)
+      P.best_latent[(size_t)b * P.latent_size + i] = P.latent[(size_t)b * P.latent_size + i];
+}
+
 #endif /* SDFR_STEP_CUH_ */

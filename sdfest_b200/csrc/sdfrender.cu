@@ -1478,6 +1478,62 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
   return check_launch("sdfr_hypothesis_step_kernel");
 }
 
+int sdfr_inlier_count(const float* depth, const float* depth_obs, long long obs_stride, int batch,
+                      int width, int height, float rel_threshold, float* n_inlier, float* n_valid,
+                      unsigned flags, void* stream) {
+  if (flags & ~SDFR_ZERO_GRADS) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (batch < 0 || width < 1 || height < 1 || obs_stride < 0 || (long long)width * height > (1ll << 30))
+    return fail(SDFR_E_SHAPE, "inlier count: batch >= 0, a non-empty image and obs_stride >= 0 expected");
+  if (batch == 0) return 0;
+  if (!depth || !depth_obs || !n_inlier || !n_valid) return fail(SDFR_E_NULL, "inlier count: NULL pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (flags & SDFR_ZERO_GRADS) {
+    if (int rc = zero_async(n_inlier, sizeof(float) * batch, s)) return rc;
+    if (int rc = zero_async(n_valid, sizeof(float) * batch, s)) return rc;
+  }
+  InlierParams P;
+  memset(&P, 0, sizeof(P));
+  P.depth = depth; P.obs = depth_obs; P.obs_stride = obs_stride;
+  P.pixels = width * height; P.threshold = rel_threshold;
+  P.n_inlier = n_inlier; P.n_valid = n_valid;
+  const bool vec = (P.pixels % 4 == 0) && (obs_stride % 4 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(depth) | reinterpret_cast<uintptr_t>(depth_obs)) & 15) == 0;
+  int gx = ((vec ? P.pixels / 4 : P.pixels) + 1023) / 1024; /* ~4 loads per thread */
+  gx = gx < 1 ? 1 : (gx > 256 ? 256 : gx);
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    P.z_offset = z0;
+    const dim3 grid(gx, batch - z0 < 65535 ? batch - z0 : 65535);
+    if (vec) sdfr_inlier_count_kernel<true><<<grid, 256, 0, s>>>(P);
+    else sdfr_inlier_count_kernel<false><<<grid, 256, 0, s>>>(P);
+  }
+  return check_launch("sdfr_inlier_count_kernel");
+}
+
+int sdfr_track_best(float* n_inlier, float* n_valid, const float* position, const float* orientation,
+                    const float* scale, const float* latent, int latent_size, int batch,
+                    const int* step, float* ratio, float* best_ratio, int* best_iteration,
+                    float* best_position, float* best_orientation, float* best_scale,
+                    float* best_latent, unsigned flags, void* stream) {
+  if (flags & ~SDFR_STEP_CLEAR_INPUTS) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (batch < 0 || latent_size < 0) return fail(SDFR_E_SHAPE, "track best: batch >= 0 and latent_size >= 0 expected");
+  if (batch == 0) return 0;
+  if (!n_inlier || !n_valid || !position || !orientation || !scale || !best_ratio || !best_iteration ||
+      !best_position || !best_orientation || !best_scale)
+    return fail(SDFR_E_NULL, "track best: NULL pointer");
+  TrackParams P;
+  memset(&P, 0, sizeof(P));
+  P.n_inlier = n_inlier; P.n_valid = n_valid;
+  P.position = position; P.orientation = orientation; P.scale = scale;
+  P.latent = latent_size > 0 ? latent : nullptr;
+  P.latent_size = latent_size; P.batch = batch; P.step = step; P.ratio = ratio;
+  P.best_ratio = best_ratio; P.best_iteration = best_iteration;
+  P.best_position = best_position; P.best_orientation = best_orientation; P.best_scale = best_scale;
+  P.best_latent = best_latent;
+  P.flags = flags;
+  sdfr_track_best_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("sdfr_track_best_kernel");
+}
+
 int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const float* weight,
                               const float* bias, const float* base, int batch, int R, float* sdf,
                               long long sdf_stride, int layout, void* stream) {

@@ -86,6 +86,14 @@ class HypothesisOptimizer:
     ``instance[b]`` (default ``arange(B)``: one map per hypothesis), each instance's point loss
     averaged over its own points -- the reference's loop run for K objects x B/K hypotheses at once.
 
+    Result selection: with ``inlier_threshold`` (the reference's ``relative_inlier_threshold``, 0.03)
+    every iteration also evaluates the inlier ratio of simple_setup.py:177-188 -- on the depth rendered
+    before the update, as :463 does -- into ``inlier_ratio`` (B,) and keeps the parameters after the
+    update with the best ratio so far in ``best_position / best_orientation / best_scale /
+    best_latent`` (``best_inlier_ratio``, ``best_iteration``): ``result("best_inlier_ratio")``.
+    The reference keeps references to the live tensors there (:207-210), so what it returns is always
+    the last iterate (``result("last_iteration")``); the copies are what the code evidently intends.
+
     ``optimizer``: ``"fused"`` runs the whole iteration as direct C-ABI launches -- decoder tail,
     ``sdfr_compare_fused``, ``sdfr_point_loss_fused``, tail adjoint, and ONE
     ``sdfr_hypothesis_step`` kernel for the gradient chain rule, Adam on all four groups, the
@@ -101,7 +109,8 @@ class HypothesisOptimizer:
                  decoder: Optional[Callable] = None, depth_weight: float = 1.0,
                  pc_weight: float = 3.0, max_points: int = 0, group=None, optimizer: str = "auto",
                  lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8,
-                 overlap: bool = True, instance: Optional[torch.Tensor] = None):
+                 overlap: bool = True, instance: Optional[torch.Tensor] = None,
+                 inlier_threshold: Optional[float] = None):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
@@ -154,6 +163,18 @@ class HypothesisOptimizer:
             self.depth_obs = self.depth_obs.index_select(0, instance).contiguous()
         self.instance = instance
         self.last_losses = None
+        self.inlier_threshold = None if inlier_threshold is None else float(inlier_threshold)
+        if self.inlier_threshold is not None:
+            dev0 = self.position.device
+            self._inl = torch.zeros(2, B, dtype=torch.float32, device=dev0)  # n_inlier, n_valid
+            self.inlier_ratio = torch.zeros(B, dtype=torch.float32, device=dev0)
+            self.best_inlier_ratio = torch.full((B,), -1.0, dtype=torch.float32, device=dev0)
+            self.best_iteration = torch.full((B,), -1, dtype=torch.int32, device=dev0)
+            self.best_position = self.position.detach().clone()
+            self.best_orientation = self.orientation.detach().clone()
+            self.best_scale = self.scale.detach().clone()
+            self.best_latent = None if self.latent is None else self.latent.detach().clone()
+            self._iteration = torch.zeros(B, dtype=torch.int32, device=dev0)  # optimizer="torch" (device-side: survives graph replay)
         self._graph = None
         self._shard_sizes = None  # exchanged on the first gather of run()
         if self.optimizer_impl == "fused":
@@ -299,6 +320,14 @@ class HypothesisOptimizer:
             "sdfr_compare_fused")
         if M and side is not None:
             main.wait_stream(side)
+        if self.inlier_threshold is not None:
+            # one streaming pass over the estimate, beside the decoder's backward
+            def count_inliers():
+                _lib.check(lib.sdfr_inlier_count(
+                    self._depth.data_ptr(), self.depth_obs.data_ptr(), self._obs_stride, B, W, H,
+                    self.inlier_threshold, self._inl[0].data_ptr(), self._inl[1].data_ptr(), 0,
+                    _stream()), "sdfr_inlier_count")
+            on_side(count_inliers)
         g_latent = None
         if dec is not None:
             g_x = torch.empty_like(x)
@@ -309,8 +338,50 @@ class HypothesisOptimizer:
             (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
             g_latent = g_latent.contiguous()
         self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent)
+        if self.inlier_threshold is not None:
+            if side is not None:
+                main.wait_stream(side)
+            _lib.check(lib.sdfr_track_best(
+                self._inl[0].data_ptr(), self._inl[1].data_ptr(), self.position.data_ptr(),
+                self.orientation.data_ptr(), self.scale.data_ptr(), _ptr(self.latent), self._L, B,
+                self._t.data_ptr(), self.inlier_ratio.data_ptr(), self.best_inlier_ratio.data_ptr(),
+                self.best_iteration.data_ptr(), self.best_position.data_ptr(),
+                self.best_orientation.data_ptr(), self.best_scale.data_ptr(), _ptr(self.best_latent),
+                _lib.STEP_CLEAR_INPUTS, _stream()), "sdfr_track_best")
         self.last_losses = self._loss
         return self.last_losses
+
+    def _track_best_torch(self, depth: torch.Tensor) -> None:
+        """simple_setup.py:177-211 with torch operators (optimizer="torch"; also the CPU statement
+        the kernels are tested against): ratio of the depth rendered before the update, snapshot of the
+        parameters after it."""
+        with torch.no_grad():
+            obs = self.depth_obs if self.depth_obs.dim() == 3 else self.depth_obs[None]
+            rel = (obs - depth.detach()).abs() / obs
+            n_inlier = (rel < self.inlier_threshold).flatten(1).sum(1).to(torch.float32)
+            n_valid = (obs != 0).flatten(1).sum(1).to(torch.float32).expand_as(n_inlier)
+            ratio = n_inlier / n_valid
+            self._iteration += 1
+            better = (self.best_iteration < 0) | (ratio > self.best_inlier_ratio)
+            self.inlier_ratio.copy_(ratio)
+            self.best_inlier_ratio.copy_(torch.where(better, ratio, self.best_inlier_ratio))
+            self.best_iteration.copy_(torch.where(better, self._iteration, self.best_iteration))
+            for best, cur in ((self.best_position, self.position), (self.best_orientation, self.orientation),
+                              (self.best_scale, self.scale), (self.best_latent, self.latent)):
+                if best is not None:
+                    best.copy_(torch.where(better.view(-1, *[1] * (cur.dim() - 1)), cur.detach(), best))
+
+    def result(self, strategy: str = "last_iteration"):
+        """(position, orientation, scale, latent) per hypothesis as SDFPipeline.__call__ returns them
+        (simple_setup.py:583-592): ``"last_iteration"`` or ``"best_inlier_ratio"``."""
+        if strategy == "last_iteration":
+            return (self.position.detach(), self.orientation.detach(), self.scale.detach(),
+                    None if self.latent is None else self.latent.detach())
+        if strategy == "best_inlier_ratio":
+            if self.inlier_threshold is None:
+                raise ValueError("best_inlier_ratio needs inlier_threshold (the reference's default is 0.03)")
+            return self.best_position, self.best_orientation, self.best_scale, self.best_latent
+        raise ValueError(f"Result selection strategy {strategy} is not supported.")
 
     def _grids(self):
         if self.decoder is None:
@@ -347,17 +418,17 @@ class HypothesisOptimizer:
             return self.last_losses
         return self._eager_step()
 
-    def _fused_loss(self, q: torch.Tensor) -> torch.Tensor:
+    def _fused_loss(self, q: torch.Tensor):
         """Decoder tail, render-and-compare and point loss chained through the C ABI
         (estimation/fused.py): no dense grid, no separate layout / scaling / add passes."""
         dec = self.decoder
         w, b = dec.tail_parameters()
-        loss, _, _, _ = decode_render_compare(
+        loss, depth, _, _ = decode_render_compare(
             dec.trunk(self.latent), w, b, self.position, q.contiguous(), self.scale,
             self.depth_obs, self.points if self.pc_weight and self.points.shape[0] > 0 else None,
             dec.volume_size, self.threshold, self.camera, base=dec.base,
             depth_weight=self.depth_weight, pc_weight=self.pc_weight)
-        return loss
+        return loss, depth
 
     def _eager_step(self) -> torch.Tensor:
         if self.optimizer_impl == "fused":
@@ -366,15 +437,17 @@ class HypothesisOptimizer:
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda \
                 and self.point_counts is None:  # the chained operator takes one shared cloud
-            loss = self._fused_loss(q)
+            loss, depth = self._fused_loss(q)
             loss.sum().backward()
             self.optimizer.step()
             with torch.no_grad():
                 self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+            if self.inlier_threshold is not None:
+                self._track_best_torch(depth)
             self.last_losses = loss.detach()
             return self.last_losses
         grids = self._grids()
-        loss_depth, _, _ = render_and_compare(grids, self.position, q.contiguous(),
+        loss_depth, depth, _ = render_and_compare(grids, self.position, q.contiguous(),
                                               (1.0 / self.scale).contiguous(), self.depth_obs,
                                               self.threshold, self.camera)
         loss = self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
@@ -392,6 +465,8 @@ class HypothesisOptimizer:
         self.optimizer.step()
         with torch.no_grad():
             self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+        if self.inlier_threshold is not None:
+            self._track_best_torch(depth)
         self.last_losses = loss.detach()
         return self.last_losses
 
