@@ -229,7 +229,7 @@ def config5():
     init_ms = timed(initialise, 5, warm=2)
     latent, position, scale, orientation = initialise()
     opt = HypothesisOptimizer(cam, THR, obs, position, orientation, scale, latent=latent, decoder=dec,
-                              optimizer="fused")  # all observed points, as the reference
+                              optimizer="fused", inlier_threshold=0.03)  # all observed points, as the reference
     first = opt.step().clone()
     opt.capture(warmup=2)
     sizes = [K] * world
@@ -263,6 +263,8 @@ def config5():
             "instances_per_s_end_to_end": TOTAL / ((init_ms + loop_ms) * 1e-3),
             "points_per_instance": [int(opt.point_counts.min()), int(opt.point_counts.max())],
             "mean_loss_first": float(first.mean()), "mean_loss_last": float(torch.nan_to_num(allv).mean()),
+            "mean_inlier_ratio_last": float(torch.nan_to_num(opt.inlier_ratio).mean()),
+            "mean_best_inlier_ratio": float(torch.nan_to_num(opt.best_inlier_ratio).mean()),
             "init": "position = cloud centroid + 0.02 tanh(net) (-0.05 m in z), scale = 0.15 exp(0.2 tanh(net)), "
                     "latent = 0.1 tanh(net), orientation = the network's unit quaternion"}
 
