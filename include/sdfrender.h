@@ -76,6 +76,9 @@ extern "C" {
 /* flags of sdfr_hypothesis_step */
 #define SDFR_STEP_CLEAR_INPUTS 0x100u /* zero the sums / gradient inputs after consuming them */
 #define SDFR_STEP_NO_UPDATE 0x200u    /* only derive unit_orientation / inv_scale / loss */
+/* sdfr_track_best with SDFR_STEP_CLEAR_INPUTS: zero n_inlier only (n_valid depends on the observation
+ * alone and was counted once) */
+#define SDFR_TRACK_KEEP_VALID 0x400u
 
 int sdfr_abi_version(void);
 const char* sdfr_last_error(void);
@@ -294,11 +297,29 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
  *   parameters.  NOTE: the reference stores REFERENCES to the live parameter tensors (:207-210), which
  *   the in-place optimiser keeps mutating, so its "best" estimate always equals the last iterate; this
  *   entry point keeps the copy the code evidently intends.  ratio / latent / best_latent may be NULL.
- *   SDFR_STEP_CLEAR_INPUTS zeroes n_inlier / n_valid after reading them.
+ *   SDFR_STEP_CLEAR_INPUTS zeroes n_inlier / n_valid after reading them (n_inlier only with
+ *   SDFR_TRACK_KEEP_VALID).
+ * sdfr_compare_fused_inliers:  sdfr_compare_fused that also counts the inliers in the same traversal
+ *   (no extra pass over the images): n_inlier[b] += #{overlap pixels (est > 0, obs > 0):
+ *   |obs - est| / obs < rel_threshold}.  Equal to sdfr_inlier_count's n_inlier whenever the observed
+ *   depth is non-negative and rel_threshold <= 1 (a pixel the estimate misses has relative error
+ *   exactly 1 and a pixel without observation is never an inlier; larger thresholds are rejected with
+ *   SDFR_E_SHAPE).  n_valid = #{obs != 0} depends on the observation only: count it once with
+ *   sdfr_inlier_count.  SDFR_ZERO_GRADS also clears n_inlier.
  */
 int sdfr_inlier_count(const float* depth, const float* depth_obs, long long obs_stride, int batch,
                       int width, int height, float rel_threshold, float* n_inlier, float* n_valid,
                       unsigned flags, void* stream);
+
+int sdfr_compare_fused_inliers(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
+                               const float* position, const float* orientation,
+                               const float* inv_scale, int batch, int width, int height, float cx,
+                               float cy, float fx, float fy, float threshold, const float* depth_obs,
+                               long long obs_stride, float* depth, float* loss_sum, float* n_overlap,
+                               float rel_threshold, float* n_inlier, float* grad_sdf,
+                               long long grad_sdf_stride, float* grad_position,
+                               float* grad_orientation, float* grad_inv_scale, unsigned flags,
+                               void* stream);
 
 int sdfr_track_best(float* n_inlier, float* n_valid, const float* position, const float* orientation,
                     const float* scale, const float* latent, int latent_size, int batch,

@@ -25,6 +25,7 @@ ZERO_GRADS = 0x20
 LOSS_WEIGHTED = 0x40  # sdfr_point_loss_fused: loss_sum += upstream[b] * sum
 STEP_CLEAR_INPUTS = 0x100
 STEP_NO_UPDATE = 0x200
+TRACK_KEEP_VALID = 0x400  # sdfr_track_best: CLEAR_INPUTS zeroes n_inlier only
 LAYOUT_DENSE = 0
 LAYOUT_SKEWED = 1
 
@@ -52,6 +53,9 @@ SIGNATURES = {
     "sdfr_compare_fused": (
         c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
                 *_GRADS, c_uint, _P]),
+    "sdfr_compare_fused_inliers": (
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
+                c_float, _P, *_GRADS, c_uint, _P]),
     "sdfr_skewed_pitches": (c_int, [c_int, _P, _P, _P]),
     "sdfr_skew_grids": (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P]),
     "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P]),

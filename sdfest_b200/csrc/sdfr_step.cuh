@@ -325,7 +325,7 @@ sdfr_track_best_kernel(const __grid_constant__ TrackParams P) {
   if (P.ratio) P.ratio[b] = r;
   if (P.flags & SDFR_STEP_CLEAR_INPUTS) {
     P.n_inlier[b] = 0.0f;
-    P.n_valid[b] = 0.0f;
+    if (!(P.flags & SDFR_TRACK_KEEP_VALID)) P.n_valid[b] = 0.0f;
   }
   if (!better) return;
   P.best_ratio[b] = r;

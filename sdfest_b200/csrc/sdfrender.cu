@@ -83,6 +83,8 @@ struct FwdParams {
   long long obs_stride;
   float* __restrict__ loss_sum;
   float* __restrict__ n_overlap;
+  float* __restrict__ n_inlier;  // optional: overlap pixels with |obs - est| / obs < inlier_threshold
+  float inlier_threshold;
   // stats
   unsigned long long* __restrict__ stats;
   // fused compare + backward (unnormalised gradients)
@@ -410,7 +412,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   float acc[8]; /* MODE 2: pose gradients */
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
-  float err_acc = 0.0f, cnt_acc = 0.0f;
+  float err_acc = 0.0f, cnt_acc = 0.0f, inl_acc = 0.0f;
   unsigned st_steps = 0, st_entered = 0, st_hit = 0, st_capped = 0;
   const int n_rect = T.rtw * T.rth;
   const int n_cand = n_rect > g ? ((n_rect - g + G - 1) / G) * kWarps : 0;
@@ -488,6 +490,9 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
           if (obs > 0.0f) {
             err_acc += fabsf(z - obs);
             cnt_acc += 1.0f;
+            /* result selection (estimation/simple_setup.py:183-185): relative error below the
+             * threshold; IEEE division, the same expression the reference evaluates in torch */
+            if (P.n_inlier) inl_acc += __fdiv_rn(fabsf(obs - z), obs) < P.inlier_threshold ? 1.0f : 0.0f;
             if (MODE == 2 && z != obs) sgn = z > obs ? 1.0f : -1.0f;
           }
         }
@@ -530,6 +535,10 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
     if (lane == 0) {
       if (err_acc != 0.0f) atomicAdd(P.loss_sum + b, err_acc);
       if (cnt_acc != 0.0f) atomicAdd(P.n_overlap + b, cnt_acc);
+    }
+    if (P.n_inlier) {
+      inl_acc = warp_sum(inl_acc);
+      if (lane == 0 && inl_acc != 0.0f) atomicAdd(P.n_inlier + b, inl_acc);
     }
   }
   if (MODE == 2 && WANT_POSE)
@@ -1221,12 +1230,13 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   return launch_backward<1>(P, batch, (flags & SDFR_ZERO_GRADS) != 0, s);
 }
 
-int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
-                       const float* quat, const float* inv_scale, int batch, int W, int H,
-                       float cx, float cy, float fx, float fy, float threshold,
-                       const float* depth_obs, long long obs_stride, float* depth,
-                       float* loss_sum, float* n_overlap, float* gs, long long gs_stride,
-                       float* gp, float* gq, float* gi, unsigned flags, void* stream) {
+static int compare_fused_impl(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
+                              const float* quat, const float* inv_scale, int batch, int W, int H,
+                              float cx, float cy, float fx, float fy, float threshold,
+                              const float* depth_obs, long long obs_stride, float* depth,
+                              float* loss_sum, float* n_overlap, float rel_threshold, float* n_inlier,
+                              float* gs, long long gs_stride, float* gp, float* gq, float* gi,
+                              unsigned flags, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
@@ -1240,6 +1250,8 @@ int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout
   if (flags & SDFR_ZERO_GRADS) {
     if (int rc = zero_async(loss_sum, sizeof(float) * batch, s)) return rc;
     if (int rc = zero_async(n_overlap, sizeof(float) * batch, s)) return rc;
+    if (n_inlier)
+      if (int rc = zero_async(n_inlier, sizeof(float) * batch, s)) return rc;
   }
   if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
   if (W == 0 || H == 0) return 0;
@@ -1250,6 +1262,8 @@ int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout
   P.obs_stride = obs_stride;
   P.loss_sum = loss_sum;
   P.n_overlap = n_overlap;
+  P.n_inlier = n_inlier;
+  P.inlier_threshold = rel_threshold;
   P.grad_sdf = gs;
   P.grad_sdf_stride = gs_stride;
   P.grad_position = gp;
@@ -1257,6 +1271,33 @@ int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout
   P.grad_inv_scale = gi;
   P.flags = flags;
   return launch_forward<2, false>(P, batch, s);
+}
+
+int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
+                       const float* quat, const float* inv_scale, int batch, int W, int H,
+                       float cx, float cy, float fx, float fy, float threshold,
+                       const float* depth_obs, long long obs_stride, float* depth,
+                       float* loss_sum, float* n_overlap, float* gs, long long gs_stride,
+                       float* gp, float* gq, float* gi, unsigned flags, void* stream) {
+  return compare_fused_impl(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, cx, cy, fx, fy,
+                            threshold, depth_obs, obs_stride, depth, loss_sum, n_overlap, 0.0f, nullptr,
+                            gs, gs_stride, gp, gq, gi, flags, stream);
+}
+
+int sdfr_compare_fused_inliers(const float* sdf, int R, long long sdf_stride, int layout,
+                               const float* pos, const float* quat, const float* inv_scale, int batch,
+                               int W, int H, float cx, float cy, float fx, float fy, float threshold,
+                               const float* depth_obs, long long obs_stride, float* depth,
+                               float* loss_sum, float* n_overlap, float rel_threshold, float* n_inlier,
+                               float* gs, long long gs_stride, float* gp, float* gq, float* gi,
+                               unsigned flags, void* stream) {
+  if (batch > 0 && !n_inlier) return fail(SDFR_E_NULL, "n_inlier is NULL");
+  if (!(rel_threshold <= 1.0f))
+    return fail(SDFR_E_SHAPE, "fused inlier count: rel_threshold <= 1 expected (a missed pixel has "
+                              "relative error 1; use sdfr_inlier_count for larger thresholds)");
+  return compare_fused_impl(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, cx, cy, fx, fy,
+                            threshold, depth_obs, obs_stride, depth, loss_sum, n_overlap, rel_threshold,
+                            n_inlier, gs, gs_stride, gp, gq, gi, flags, stream);
 }
 
 int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int batch, float* gs,
@@ -1514,7 +1555,7 @@ int sdfr_track_best(float* n_inlier, float* n_valid, const float* position, cons
                     const int* step, float* ratio, float* best_ratio, int* best_iteration,
                     float* best_position, float* best_orientation, float* best_scale,
                     float* best_latent, unsigned flags, void* stream) {
-  if (flags & ~SDFR_STEP_CLEAR_INPUTS) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (flags & ~(SDFR_STEP_CLEAR_INPUTS | SDFR_TRACK_KEEP_VALID)) return fail(SDFR_E_FLAGS, "unknown flag bits");
   if (batch < 0 || latent_size < 0) return fail(SDFR_E_SHAPE, "track best: batch >= 0 and latent_size >= 0 expected");
   if (batch == 0) return 0;
   if (!n_inlier || !n_valid || !position || !orientation || !scale || !best_ratio || !best_iteration ||

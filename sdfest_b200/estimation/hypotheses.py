@@ -175,6 +175,10 @@ class HypothesisOptimizer:
             self.best_scale = self.scale.detach().clone()
             self.best_latent = None if self.latent is None else self.latent.detach().clone()
             self._iteration = torch.zeros(B, dtype=torch.int32, device=dev0)  # optimizer="torch" (device-side: survives graph replay)
+            # valid pixels depend on the observation alone (simple_setup.py:186): counted once
+            if self.inlier_threshold <= 1.0:  # larger thresholds: sdfr_inlier_count recounts both
+                n_valid = (self.depth_obs != 0).flatten(-2).sum(-1).to(torch.float32)
+                self._inl[1].copy_(n_valid.expand(B) if n_valid.dim() == 0 else n_valid)
         self._graph = None
         self._shard_sizes = None  # exchanged on the first gather of run()
         if self.optimizer_impl == "fused":
@@ -311,16 +315,29 @@ class HypothesisOptimizer:
 
         if M:
             on_side(point_loss)
-        _lib.check(lib.sdfr_compare_fused(
-            grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
-            self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
-            self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
-            b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), _ptr(self._g_sdf), R ** 3,
-            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
-            "sdfr_compare_fused")
+        # inliers of the result selection: counted in the same traversal (thresholds <= 1: a missed
+        # pixel has relative error exactly 1), else by a separate pass over the written estimate
+        inl_fused = self.inlier_threshold is not None and self.inlier_threshold <= 1.0
+        if inl_fused:
+            _lib.check(lib.sdfr_compare_fused_inliers(
+                grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
+                self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
+                self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
+                b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), self.inlier_threshold,
+                self._inl[0].data_ptr(), _ptr(self._g_sdf), R ** 3,
+                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
+                "sdfr_compare_fused_inliers")
+        else:
+            _lib.check(lib.sdfr_compare_fused(
+                grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
+                self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
+                self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
+                b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), _ptr(self._g_sdf), R ** 3,
+                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
+                "sdfr_compare_fused")
         if M and side is not None:
             main.wait_stream(side)
-        if self.inlier_threshold is not None:
+        if self.inlier_threshold is not None and not inl_fused:
             # one streaming pass over the estimate, beside the decoder's backward
             def count_inliers():
                 _lib.check(lib.sdfr_inlier_count(
@@ -339,7 +356,7 @@ class HypothesisOptimizer:
             g_latent = g_latent.contiguous()
         self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent)
         if self.inlier_threshold is not None:
-            if side is not None:
+            if side is not None and not inl_fused:
                 main.wait_stream(side)
             _lib.check(lib.sdfr_track_best(
                 self._inl[0].data_ptr(), self._inl[1].data_ptr(), self.position.data_ptr(),
@@ -347,7 +364,8 @@ class HypothesisOptimizer:
                 self._t.data_ptr(), self.inlier_ratio.data_ptr(), self.best_inlier_ratio.data_ptr(),
                 self.best_iteration.data_ptr(), self.best_position.data_ptr(),
                 self.best_orientation.data_ptr(), self.best_scale.data_ptr(), _ptr(self.best_latent),
-                _lib.STEP_CLEAR_INPUTS, _stream()), "sdfr_track_best")
+                _lib.STEP_CLEAR_INPUTS | (_lib.TRACK_KEEP_VALID if inl_fused else 0), _stream()),
+                "sdfr_track_best")
         self.last_losses = self._loss
         return self.last_losses
 

@@ -557,3 +557,75 @@ def test_fused_result_selection_matches_torch_composition(cuda_device, with_deco
     moved = b.best_iteration < 6
     if bool(moved.any()):
         assert float((b.best_position[moved] - b.position[moved]).abs().max()) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("per_hypothesis_obs", [False, True])
+def test_compare_fused_inliers_counts_in_the_same_traversal(cuda_device, per_hypothesis_obs):
+    """sdfr_compare_fused_inliers = sdfr_compare_fused + the inlier count of sdfr_inlier_count on the
+    depth it wrote (exactly), without a second pass."""
+    from oracle import hypothesis_step as hs
+    from sdfest_b200 import _lib
+
+    lib, B, thr = _lib.lib(), 6, 0.03
+    opt = _make_optimizers(cuda_device, B, False, "fused")
+    cam, R = opt.camera, opt._R
+    W, H = int(cam.width), int(cam.height)
+    obs = opt.depth_obs
+    if per_hypothesis_obs:
+        obs = torch.stack([torch.roll(obs, k, 1) for k in range(B)]).contiguous()
+        obs[1] = 0.0  # an observation without a valid pixel: ratio 0/0
+    grids, gstride, layout = opt._grid_op
+    dev = cuda_device
+    outs = {}
+    for name in ("plain", "inliers"):
+        depth = torch.empty(B, H, W, device=dev)
+        sums = torch.zeros(3, B, device=dev)
+        gp, gq, gi = torch.zeros(B, 3, device=dev), torch.zeros(B, 4, device=dev), torch.zeros(B, device=dev)
+        flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE | _lib.ZERO_GRADS
+        head = (grids.data_ptr(), R, gstride, layout, opt.position.data_ptr(), opt._unit_q.data_ptr(),
+                opt._inv_scale.data_ptr(), B, W, H, W / 2, H / 2, W / 2, W / 2, opt.threshold, obs.data_ptr(),
+                H * W if per_hypothesis_obs else 0, depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr())
+        tail = (None, 0, gp.data_ptr(), gq.data_ptr(), gi.data_ptr(), flags, None)
+        if name == "plain":
+            _lib.check(lib.sdfr_compare_fused(*head, *tail), name)
+        else:
+            sums[2] = 7.0  # ZERO_GRADS clears the inlier counter too
+            _lib.check(lib.sdfr_compare_fused_inliers(*head, thr, sums[2].data_ptr(), *tail), name)
+        torch.cuda.synchronize()
+        outs[name] = (depth, sums, gp, gq, gi)
+    assert torch.equal(outs["plain"][0], outs["inliers"][0])
+    torch.testing.assert_close(outs["plain"][1][:2], outs["inliers"][1][:2], rtol=1e-5, atol=0)
+    for k in (2, 3, 4):
+        torch.testing.assert_close(outs["plain"][k], outs["inliers"][k], rtol=1e-4, atol=1e-6)
+    depth, sums = outs["inliers"][0], outs["inliers"][1]
+    counts = torch.zeros(2, B, device=dev)
+    _lib.check(lib.sdfr_inlier_count(depth.data_ptr(), obs.data_ptr(), H * W if per_hypothesis_obs else 0, B, W, H,
+                                     thr, counts[0].data_ptr(), counts[1].data_ptr(), 0, None), "count")
+    assert torch.equal(sums[2], counts[0])
+    d, o = depth.cpu().numpy(), obs.cpu().numpy()
+    want = [hs.inlier_counts(o[b] if per_hypothesis_obs else o, d[b], thr)[0] for b in range(B)]
+    assert sums[2].tolist() == want and max(want) > 50
+    # thresholds above 1 would have to count missed pixels: rejected
+    assert lib.sdfr_compare_fused_inliers(*head, 1.5, sums[2].data_ptr(), *tail) == -2
+    assert lib.sdfr_compare_fused_inliers(*head, thr, None, *tail) == -1
+
+
+@pytest.mark.gpu
+def test_result_selection_with_a_threshold_above_one_uses_the_separate_pass(cuda_device):
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    o = _make_optimizers(cuda_device, 4, False, "fused")
+
+    def make(optimizer):
+        return HypothesisOptimizer(o.camera, o.threshold, o.depth_obs, o.position.detach(), o.orientation.detach(),
+                                   o.scale.detach(), sdf=o.sdf, optimizer=optimizer, inlier_threshold=1.5)
+
+    a, b = make("torch"), make("fused")
+    for _ in range(3):
+        a.step()
+        b.step()
+    torch.cuda.synchronize()
+    # every valid pixel is an inlier: missed ones have relative error 1 < 1.5
+    torch.testing.assert_close(b.inlier_ratio, a.inlier_ratio, rtol=0, atol=1e-2)
+    assert float(b.inlier_ratio.min()) > 0.9
