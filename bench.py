@@ -457,7 +457,7 @@ def main():
                 "iterations": n_it, "hypotheses_per_gpu": B, "optimizer": opt.optimizer_impl,
                 "what": "50 Adam steps on position/orientation/scale/latent: decoder trunk + fused tail, "
                         "fused render-and-compare, fused point loss, tail adjoint + trunk backward, one "
-                        "sdfr_hypothesis_step kernel (chain rule + Adam + renormalisation), inlier ratio + best estimate (sdfr_inlier_count, sdfr_track_best); CUDA-graph replay",
+                        "sdfr_hypothesis_step kernel (chain rule + Adam + renormalisation), inlier ratio + best estimate (counted inside the render traversal, sdfr_track_best); CUDA-graph replay",
                 "final_mean_loss": float(opt.last_losses.mean()),
                 "final_mean_inlier_ratio": float(torch.nan_to_num(opt.inlier_ratio).mean())}
         # fixed grids (BASELINE config 4's per-GPU work: pose/scale hypotheses on given shapes)
@@ -479,9 +479,9 @@ def main():
             pose_ms = float(t.item())
         loop["pose_only"] = {"hyp_iter_per_s": world * B * n_it / (pose_ms * 1e-3),
                              "ms_per_iteration": pose_ms / n_it,
-                             "what": "same loop on fixed grids: 5 launches per iteration (fused "
-                                     "render-and-compare, fused point loss, hypothesis step, inlier "
-                                     "count, best-estimate bookkeeping)"}
+                             "what": "same loop on fixed grids: 4 launches per iteration (fused "
+                                     "render-and-compare with inlier count, fused point loss, "
+                                     "hypothesis step, best-estimate bookkeeping)"}
     except Exception as e:  # the loop demo never blocks the render metric
         loop = {"unavailable": str(e)[:200]}
 
