@@ -100,3 +100,43 @@ def test_composite_and_l1_helpers():
     assert n == 2 and loss == pytest.approx(0.25)
     assert np.array_equal(grad, [[-0.5, 0.0], [0.0, 0.0]])
     assert oracle.l1_depth_loss(np.zeros((2, 2)), obs)[2] == 0
+
+
+def test_result_selection_oracle_matches_the_reference_methods():
+    """tests/golden/selection.npz was produced by the reference's own _compute_inlier_ratio /
+    _update_best_estimate (simple_setup.py:177-211, source executed unchanged by
+    tests/golden/make_golden_selection.py): the numpy oracle and the package's torch statement
+    reproduce its ratios and its running best exactly; the reference's RETURNED estimate is the last
+    iterate (it keeps references to the live tensors), ours the copy of the best iteration."""
+    import os
+
+    import torch
+
+    from oracle import hypothesis_step as hs
+    from sdfest_b200.differentiable_renderer import Camera
+    from util import GOLDEN_DIR
+    from sdfest_b200.estimation import HypothesisOptimizer
+
+    z = np.load(os.path.join(GOLDEN_DIR, "selection.npz"))
+    obs, est, thr = z["obs"], z["est"], float(z["threshold"])
+    n, (H, W) = est.shape[0], obs.shape
+    best = hs.BestEstimate()
+    cam = Camera(W, H, 30.0, 30.0, W / 2, H / 2, pixel_center=0.5)
+    opt = HypothesisOptimizer(cam, 0.005, torch.tensor(obs), torch.zeros(1, 3), torch.tensor([[0.0, 0, 0, 1]]),
+                              torch.ones(1), sdf=torch.zeros(1, 8, 8, 8), inlier_threshold=thr)
+    for it in range(n):
+        ni, nv = hs.inlier_counts(obs, est[it], thr)
+        r = best.update(ni, nv, it + 1, (z["positions"][it],))
+        assert np.float32(r) == z["ratios"][it]
+        assert np.float32(best.ratio) == z["best_so_far"][it]
+        with torch.no_grad():
+            opt.position.copy_(torch.tensor(z["positions"][it])[None])
+        opt._track_best_torch(torch.tensor(est[it])[None])
+        assert float(opt.inlier_ratio[0]) == float(z["ratios"][it])
+        assert float(opt.best_inlier_ratio[0]) == float(z["best_so_far"][it])
+    assert best.iteration == 4 and int(opt.best_iteration[0]) == 4
+    np.testing.assert_array_equal(best.params[0], z["positions"][3])
+    np.testing.assert_array_equal(opt.result("best_inlier_ratio")[0][0].numpy(), z["positions"][3])
+    # what the reference hands back for "best_inlier_ratio" is the last iterate
+    np.testing.assert_array_equal(z["returned_position"], z["last_position"])
+    np.testing.assert_allclose(opt.result("last_iteration")[0][0].numpy(), z["last_position"], rtol=1e-6)
