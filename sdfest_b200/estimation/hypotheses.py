@@ -86,6 +86,13 @@ class HypothesisOptimizer:
     ``instance[b]`` (default ``arange(B)``: one map per hypothesis), each instance's point loss
     averaged over its own points -- the reference's loop run for K objects x B/K hypotheses at once.
 
+    Views: with ``camera_positions`` (V,3) and ``camera_orientations`` (V,4) (camera-to-world, as
+    SDFPipeline.__call__ takes them) ``depth_obs`` is (V,H,W), one image per view of the SAME object;
+    the pose is optimised in the world frame, moved into every camera frame (``estimation/views.py``,
+    simple_setup.py:423-431) and the per-view losses are summed (:432-446).  This mode composes the
+    package's autograd operators (``optimizer="torch"``); the inlier ratio is evaluated on the last
+    view, as the reference's loop variables leave it (:463).
+
     Result selection: with ``inlier_threshold`` (the reference's ``relative_inlier_threshold``, 0.03)
     every iteration also evaluates the inlier ratio of simple_setup.py:177-188 -- on the depth rendered
     before the update, as :463 does -- into ``inlier_ratio`` (B,) and keeps the parameters after the
@@ -110,14 +117,21 @@ class HypothesisOptimizer:
                  pc_weight: float = 3.0, max_points: int = 0, group=None, optimizer: str = "auto",
                  lrs=(1e-3, 1e-2, 1e-3, 1e-2), betas=(0.9, 0.999), eps: float = 1e-8,
                  overlap: bool = True, instance: Optional[torch.Tensor] = None,
-                 inlier_threshold: Optional[float] = None):
+                 inlier_threshold: Optional[float] = None,
+                 camera_positions: Optional[torch.Tensor] = None,
+                 camera_orientations: Optional[torch.Tensor] = None):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
             raise ValueError("optimizer must be 'auto', 'fused' or 'torch'")
-        can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder))
+        if (camera_positions is None) != (camera_orientations is None):
+            raise ValueError("give camera_positions and camera_orientations together")
+        multiview = camera_positions is not None
+        can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder)) \
+            and not multiview
         if optimizer == "fused" and not can_fuse:
-            raise ValueError("optimizer='fused' needs CUDA tensors and fixed grids or a FusedTailDecoder")
+            raise ValueError("optimizer='fused' needs CUDA tensors, fixed grids or a FusedTailDecoder, and "
+                             "a single view")
         self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
         self.overlap = bool(overlap)
         self.lrs, self.betas, self.eps = tuple(float(x) for x in lrs), tuple(betas), float(eps)
@@ -142,7 +156,21 @@ class HypothesisOptimizer:
         # observed points, once (the only host syncs), sub-sampled to a fixed size
         B = self.position.shape[0]
         self.point_counts = None  # (B,) points hypothesis b owns, when the clouds differ
-        if self.depth_obs.dim() == 2:
+        self._views = None
+        if multiview:
+            V = int(camera_positions.shape[0])
+            if instance is not None:
+                raise ValueError("views and object instances cannot be combined")
+            if tuple(camera_positions.shape) != (V, 3) or tuple(camera_orientations.shape) != (V, 4) \
+                    or self.depth_obs.dim() != 3 or self.depth_obs.shape[0] != V:
+                raise ValueError("camera_positions (V,3), camera_orientations (V,4) and depth_obs (V,H,W) expected")
+            dev_o = self.depth_obs.device
+            self._views = (camera_positions.detach().to(dev_o, torch.float32).contiguous(),
+                           camera_orientations.detach().to(dev_o, torch.float32).contiguous())
+            self._view_points = [losses.subsample_points(losses.depth_to_pointcloud(d, camera), max_points)
+                                 for d in self.depth_obs]
+            self.points = self._view_points[0]
+        elif self.depth_obs.dim() == 2:
             if instance is not None:
                 raise ValueError("`instance` needs one observed depth map per object instance (K,H,W)")
             self.points = losses.subsample_points(losses.depth_to_pointcloud(self.depth_obs, camera),
@@ -176,7 +204,7 @@ class HypothesisOptimizer:
             self.best_latent = None if self.latent is None else self.latent.detach().clone()
             self._iteration = torch.zeros(B, dtype=torch.int32, device=dev0)  # optimizer="torch" (device-side: survives graph replay)
             # valid pixels depend on the observation alone (simple_setup.py:186): counted once
-            if self.inlier_threshold <= 1.0:  # larger thresholds: sdfr_inlier_count recounts both
+            if self.optimizer_impl == "fused" and self.inlier_threshold <= 1.0:  # larger: sdfr_inlier_count recounts both
                 n_valid = (self.depth_obs != 0).flatten(-2).sum(-1).to(torch.float32)
                 self._inl[1].copy_(n_valid.expand(B) if n_valid.dim() == 0 else n_valid)
         self._graph = None
@@ -369,12 +397,44 @@ class HypothesisOptimizer:
         self.last_losses = self._loss
         return self.last_losses
 
-    def _track_best_torch(self, depth: torch.Tensor) -> None:
+    def _multiview_step(self) -> torch.Tensor:
+        """One iteration over V views of the same object (simple_setup.py:420-462): the pose is moved
+        into every camera frame, every view is rendered, compared and scored against its own observed
+        points, the losses are summed; autograd carries the gradients back through the rigid maps."""
+        from . import views
+
+        self.optimizer.zero_grad(set_to_none=True)
+        q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+        grids = self._grids()
+        grids4 = grids if grids.dim() == 4 else grids[None]
+        position_c, orientation_c = views.to_camera_frames(self.position, q, *self._views)
+        inv_scale = (1.0 / self.scale).contiguous()
+        loss, depth = 0.0, None
+        for v in range(self.depth_obs.shape[0]):
+            p_v, q_v = position_c[v].contiguous(), orientation_c[v].contiguous()
+            loss_depth, depth, _ = render_and_compare(grids, p_v, q_v, inv_scale, self.depth_obs[v],
+                                                      self.threshold, self.camera)
+            loss = loss + self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
+            if self.pc_weight and self._view_points[v].shape[0] > 0:
+                loss = loss + self.pc_weight * losses.point_loss(self._view_points[v], p_v, q_v,
+                                                                 self.scale, grids4)
+        loss.sum().backward()
+        self.optimizer.step()
+        with torch.no_grad():
+            self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
+        if self.inlier_threshold is not None:
+            self._track_best_torch(depth, self.depth_obs[-1])
+        self.last_losses = loss.detach()
+        return self.last_losses
+
+    def _track_best_torch(self, depth: torch.Tensor, obs: Optional[torch.Tensor] = None) -> None:
         """simple_setup.py:177-211 with torch operators (optimizer="torch"; also the CPU statement
         the kernels are tested against): ratio of the depth rendered before the update, snapshot of the
         parameters after it."""
         with torch.no_grad():
-            obs = self.depth_obs if self.depth_obs.dim() == 3 else self.depth_obs[None]
+            if obs is None:
+                obs = self.depth_obs
+            obs = obs if obs.dim() == 3 else obs[None]
             rel = (obs - depth.detach()).abs() / obs
             n_inlier = (rel < self.inlier_threshold).flatten(1).sum(1).to(torch.float32)
             n_valid = (obs != 0).flatten(1).sum(1).to(torch.float32).expand_as(n_inlier)
@@ -451,6 +511,8 @@ class HypothesisOptimizer:
     def _eager_step(self) -> torch.Tensor:
         if self.optimizer_impl == "fused":
             return self._fused_iteration()
+        if self._views is not None:
+            return self._multiview_step()
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda \
