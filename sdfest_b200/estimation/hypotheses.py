@@ -93,6 +93,10 @@ class HypothesisOptimizer:
     package's autograd operators (``optimizer="torch"``); the inlier ratio is evaluated on the last
     view, as the reference's loop variables leave it (:463).
 
+    ``point_constraint`` = (source (3,), target (3,), weight) adds ``weight * |R(orientation) source -
+    target|`` on the un-normalised orientation (simple_setup.py:164-175, losses.py:138-153); like the
+    views it runs on the autograd-composed path.
+
     Result selection: with ``inlier_threshold`` (the reference's ``relative_inlier_threshold``, 0.03)
     every iteration also evaluates the inlier ratio of simple_setup.py:177-188 -- on the depth rendered
     before the update, as :463 does -- into ``inlier_ratio`` (B,) and keeps the parameters after the
@@ -119,7 +123,8 @@ class HypothesisOptimizer:
                  overlap: bool = True, instance: Optional[torch.Tensor] = None,
                  inlier_threshold: Optional[float] = None,
                  camera_positions: Optional[torch.Tensor] = None,
-                 camera_orientations: Optional[torch.Tensor] = None):
+                 camera_orientations: Optional[torch.Tensor] = None,
+                 point_constraint=None):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
@@ -128,10 +133,17 @@ class HypothesisOptimizer:
             raise ValueError("give camera_positions and camera_orientations together")
         multiview = camera_positions is not None
         can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder)) \
-            and not multiview
+            and not multiview and point_constraint is None
+        # (source (3,), target (3,), weight): simple_setup.py:164-175, 224, 299
+        self.point_constraint = None
+        if point_constraint is not None:
+            source, target, weight = point_constraint
+            self.point_constraint = (torch.as_tensor(source, dtype=torch.float32, device=position.device),
+                                     torch.as_tensor(target, dtype=torch.float32, device=position.device),
+                                     float(weight))
         if optimizer == "fused" and not can_fuse:
-            raise ValueError("optimizer='fused' needs CUDA tensors, fixed grids or a FusedTailDecoder, and "
-                             "a single view")
+            raise ValueError("optimizer='fused' needs CUDA tensors, fixed grids or a FusedTailDecoder, "
+                             "a single view and no point constraint")
         self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
         self.overlap = bool(overlap)
         self.lrs, self.betas, self.eps = tuple(float(x) for x in lrs), tuple(betas), float(eps)
@@ -397,6 +409,15 @@ class HypothesisOptimizer:
         self.last_losses = self._loss
         return self.last_losses
 
+    def _constraint_loss(self):
+        """weight * point_constraint_loss on the un-normalised orientation (simple_setup.py:164-175)."""
+        if self.point_constraint is None:
+            return 0.0
+        from . import views
+
+        source, target, weight = self.point_constraint
+        return weight * views.point_constraint_loss(self.orientation, source, target)
+
     def _multiview_step(self) -> torch.Tensor:
         """One iteration over V views of the same object (simple_setup.py:420-462): the pose is moved
         into every camera frame, every view is rendered, compared and scored against its own observed
@@ -418,6 +439,8 @@ class HypothesisOptimizer:
             if self.pc_weight and self._view_points[v].shape[0] > 0:
                 loss = loss + self.pc_weight * losses.point_loss(self._view_points[v], p_v, q_v,
                                                                  self.scale, grids4)
+        if self.point_constraint is not None:
+            loss = loss + self._constraint_loss()
         loss.sum().backward()
         self.optimizer.step()
         with torch.no_grad():
@@ -518,6 +541,8 @@ class HypothesisOptimizer:
         if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda \
                 and self.point_counts is None:  # the chained operator takes one shared cloud
             loss, depth = self._fused_loss(q)
+            if self.point_constraint is not None:
+                loss = loss + self._constraint_loss()
             loss.sum().backward()
             self.optimizer.step()
             with torch.no_grad():
@@ -541,6 +566,8 @@ class HypothesisOptimizer:
                 loss_pc = loss_pc * torch.where(n > 0, self.points.shape[1] / n.clamp(min=1.0),
                                                 torch.zeros_like(n))
             loss = loss + self.pc_weight * loss_pc
+        if self.point_constraint is not None:
+            loss = loss + self._constraint_loss()
         loss.sum().backward()
         self.optimizer.step()
         with torch.no_grad():

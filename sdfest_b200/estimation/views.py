@@ -50,9 +50,22 @@ def rotation_matrix(q: torch.Tensor) -> torch.Tensor:
 
 
 def quaternion_apply(quaternions: torch.Tensor, points: torch.Tensor) -> torch.Tensor:
-    """Rotate points (...,3) by unit quaternions (...,4) (quaternion_utils.py:37-54: q (x) (v,0) (x) q^-1,
-    which for |q| = 1 is R(q) v)."""
-    return (rotation_matrix(quaternions) @ points[..., None])[..., 0]
+    """q (x) (v,0) (x) conj(q) for points (...,3) and quaternions (...,4) with broadcasting
+    (quaternion_utils.py:37-54), expanded to  (w^2 - |u|^2) v + 2 (u.v) u + 2 w (u x v)  for q = (u, w).
+    For |q| = 1 this is the rotation R(q) v; like the reference it is NOT normalised, so a non-unit
+    quaternion also scales by |q|^2 -- which matters for the gradient of the point-constraint loss, taken
+    w.r.t. the un-normalised orientation (simple_setup.py:164-175)."""
+    u, w = quaternions[..., :3], quaternions[..., 3:]
+    return ((w * w - (u * u).sum(-1, keepdim=True)) * points
+            + 2.0 * (u * points).sum(-1, keepdim=True) * u
+            + 2.0 * w * torch.linalg.cross(u.expand(torch.broadcast_shapes(u.shape, points.shape)),
+                                           points.expand(torch.broadcast_shapes(u.shape, points.shape)), dim=-1))
+
+
+def point_constraint_loss(orientation_q: torch.Tensor, source: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """|| q (x) source (x) conj(q) - target ||  (estimation/losses.py:138-153), batched over (...,4)
+    orientations; source, target (3,)."""
+    return torch.linalg.norm(quaternion_apply(orientation_q, source) - target, dim=-1)
 
 
 def to_camera_frames(position: torch.Tensor, orientation: torch.Tensor, camera_positions: torch.Tensor,
@@ -60,7 +73,8 @@ def to_camera_frames(position: torch.Tensor, orientation: torch.Tensor, camera_p
     """Object poses (B,3), (B,4) in the world frame -> (V,B,3), (V,B,4) in each of V camera frames
     (simple_setup.py:423-431).  camera_positions (V,3), camera_orientations (V,4) camera-to-world."""
     q_w2c = quaternion_invert(camera_orientations)
-    position_c = quaternion_apply(q_w2c[:, None], position[None] - camera_positions[:, None])
+    # camera orientations are unit quaternions: the rotation-matrix form of quaternion_apply
+    position_c = (rotation_matrix(q_w2c[:, None]) @ (position[None] - camera_positions[:, None])[..., None])[..., 0]
     orientation_c = quaternion_multiply(q_w2c[:, None], orientation[None])
     return position_c, orientation_c
 

@@ -26,6 +26,18 @@ def test_quaternion_helpers_match_reference_golden():
     torch.testing.assert_close(out[2, 5], views.quaternion_multiply(z["q1"][2], z["q2"][5]))
 
 
+def test_non_unit_quaternions_and_point_constraint_loss_match_reference_golden():
+    """The reference never normalises inside quaternion_apply; the point-constraint loss is evaluated on
+    the un-normalised orientation and its gradient depends on that (losses.py:138-153)."""
+    z = _golden()
+    torch.testing.assert_close(views.quaternion_apply(z["q_raw"], z["points"][:6]), z["apply_raw"], rtol=0, atol=1e-13)
+    q = z["q_raw"].clone().requires_grad_(True)
+    loss = views.point_constraint_loss(q, z["source"], z["target"])
+    torch.testing.assert_close(loss.detach(), z["constraint_loss"], rtol=0, atol=1e-13)
+    loss.sum().backward()
+    torch.testing.assert_close(q.grad, z["constraint_grad"], rtol=0, atol=1e-12)
+
+
 def test_camera_frames_match_the_reference_view_loop():
     z = _golden()
     pos_c, ori_c = views.to_camera_frames(z["position"], z["orientation"], z["camera_positions"],
@@ -116,6 +128,18 @@ def test_multiview_step_plumbing_on_cpu(monkeypatch):
         torch.testing.assert_close(la, lb)
     torch.testing.assert_close(a.position.detach(), b.position.detach())
     torch.testing.assert_close(a.orientation.detach(), b.orientation.detach())
+
+    # point constraint (simple_setup.py:164-175): one more loss term on the un-normalised orientation
+    src, tgt = torch.tensor([0.0, 1.0, 0.0]), torch.tensor([0.0, 0.0, 1.0])
+    c = HypothesisOptimizer(cam, 0.005, obs[0], pos, quat, scale, sdf=sdf, point_constraint=(src, tgt, 2.0))
+    d = HypothesisOptimizer(cam, 0.005, obs[0], pos, quat, scale, sdf=sdf, optimizer="torch")
+    assert c.optimizer_impl == "torch"
+    lc, ld = c.step(), d.step()
+    torch.testing.assert_close(lc - ld, 2.0 * views.point_constraint_loss(quat, src, tgt))
+    assert float((c.orientation.detach() - d.orientation.detach()).abs().max()) > 1e-4
+    with pytest.raises(ValueError):
+        HypothesisOptimizer(cam, 0.005, obs[0], pos, quat, scale, sdf=sdf, point_constraint=(src, tgt, 2.0),
+                            optimizer="fused")
 
     for bad in (dict(camera_positions=cam_p), dict(camera_positions=cam_p, camera_orientations=cam_q[:1]),
                 dict(camera_positions=cam_p, camera_orientations=cam_q, instance=torch.zeros(B, dtype=torch.long))):
