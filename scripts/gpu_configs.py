@@ -23,7 +23,6 @@ C5  end-to-end analysis-by-synthesis: 256 object instances sharded over the rank
 Writes gpurun_out/<tag>_configs_n<G>.json and prints it.  Time = CUDA events, max over ranks.
 """
 import json
-import math
 import os
 import sys
 
