@@ -8,3 +8,5 @@ from .decoder import (FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail
 from .fused import decode_render_compare  # noqa: F401
 from .view_dataset import BatchedSDFViewGenerator  # noqa: F401
 from . import runtime_analysis  # noqa: F401
+from .pipeline import NoDepthError, SDFPipeline  # noqa: F401
+from . import views  # noqa: F401
