@@ -178,3 +178,68 @@ def test_hypothesis_optimizer_instance_bookkeeping_on_cpu():
                 dict(depth_obs=depth, instance=-instance)):
         with pytest.raises(ValueError):
             HypothesisOptimizer(cam, 0.005, bad["depth_obs"], pos, quat, scale, sdf=sdf, instance=bad["instance"])
+
+
+def _stand_in_render_and_compare(sdf, position, orientation, inv_scale, depth_obs, threshold, camera):
+    B = position.shape[0]
+    target = depth_obs[depth_obs > 0].mean()
+    loss = (position[:, 2] + target) ** 2 + 0.1 * (orientation[:, 3] - 1) ** 2 + 0.01 * inv_scale
+    return loss, depth_obs[None].expand(B, -1, -1) * 1.01, torch.ones(B)
+
+
+def _loop_inputs(n_total):
+    cam = Camera(16, 12, 14.0, 14.0, 8.0, 6.0, pixel_center=0.5)
+    obs = torch.zeros(12, 16)
+    obs[3:8, 4:10] = 0.9
+    g = torch.Generator().manual_seed(4)
+    pos = torch.tensor([[0.0, 0.0, -1.0]]) + 0.05 * torch.randn(n_total, 3, generator=g)
+    quat = torch.nn.functional.normalize(torch.tensor([[0.0, 0, 0, 1]]) + 0.1 * torch.randn(n_total, 4, generator=g), dim=1)
+    scale = 0.3 + 0.02 * torch.rand(n_total, generator=g)
+    sdf = torch.rand(1, 8, 8, 8, generator=g) - 0.3
+    return cam, obs, pos, quat, scale, sdf
+
+
+def _loop_worker(rank, world, port, n_total, q):
+    from sdfest_b200.estimation import HypothesisOptimizer, hypotheses
+
+    hypotheses.render_and_compare = _stand_in_render_and_compare  # the CUDA renderer's stand-in on CPU
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cam, obs, pos, quat, scale, sdf = _loop_inputs(n_total)
+        lo, hi = shard_range(n_total, rank, world)
+        opt = HypothesisOptimizer(cam, 0.005, obs, pos[lo:hi], quat[lo:hi], scale[lo:hi], sdf=sdf,
+                                  inlier_threshold=0.03)
+        gathered = opt.run(4, gather_every=2)
+        q.put((rank, gathered.tolist(), opt.position.detach().tolist()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_sharded_loop_equals_the_single_process_loop():
+    """HypothesisOptimizer.run over two gloo ranks with an uneven shard (3 + 2 hypotheses): every rank
+    ends with all five losses, in hypothesis order, equal to the unsharded run (hypotheses are
+    independent: the only exchange is the loss all-gather)."""
+    n_total = 5
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 77
+    procs = [ctx.Process(target=_loop_worker, args=(r, 2, port, n_total, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    single_q = ctx.Queue()
+    one = ctx.Process(target=_loop_worker, args=(0, 1, port + 1, n_total, single_q))
+    one.start()
+    _, want, want_pos = single_q.get(timeout=180)
+    one.join(timeout=60)
+    assert len(want) == n_total
+    for rank, losses_all, _ in out:
+        np.testing.assert_allclose(losses_all, want, rtol=1e-6)
+    np.testing.assert_allclose(out[0][2] + out[1][2], want_pos, rtol=1e-6)
