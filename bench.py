@@ -267,7 +267,8 @@ def main():
     obs = render_depth_batched(syn.hypothesis_grids(base["shape_param"], R, dev), base["position"],
                                base["orientation"], base["inv_scale"], THRESHOLD, cam)[0].contiguous()
 
-    stats = forward_stats(grids, pos, quat, inv_s, THRESHOLD, cam)
+    stats_full = forward_stats(grids, pos, quat, inv_s, THRESHOLD, cam)
+    stats = forward_stats(grids, pos, quat, inv_s, THRESHOLD, cam, empty_space=True)
     S, Hh_all = stats["samples"], stats["hit_pixels"]
     P = W * H
 
@@ -294,11 +295,21 @@ def main():
         _lib.check(lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, stream),
                    "sdfr_skew_grids")
 
+    bounds = torch.empty((B, 8), dtype=torch.int32, device=dev)
+
+    def bound():
+        # empty-space bounds of the skewed grids for this step's poses (sdfr_grid_bounds): rays that
+        # cannot hit anything are written as 0 without marching; every other ray is marched exactly as
+        # the reference marches it.  Part of every step for the same reason as the layout pass.
+        _lib.check(lib.sdfr_grid_bounds(skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(),
+                                        inv_s.data_ptr(), B, THRESHOLD, bounds.data_ptr(), stream),
+                   "sdfr_grid_bounds")
+
     def fwd():
         _lib.check(lib.sdfr_compare_forward(
             skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
             inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
-            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, stream),
+            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, bounds.data_ptr(), stream),
             "sdfr_compare_forward")
 
     def bwd():
@@ -306,16 +317,16 @@ def main():
             depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None, skewed.data_ptr(), R,
             SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
             CX, CY, FX, FY, g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
-            g_is.data_ptr(), flags_b, stream), "sdfr_compare_backward")
+            g_is.data_ptr(), flags_b, bounds.data_ptr(), stream), "sdfr_compare_backward")
 
-    def fused(dense=False):
+    def fused(dense=False, use_bounds=True):
         _lib.check(lib.sdfr_compare_fused(
             (grids if dense else skewed).data_ptr(), R, RRR if dense else SK,
             _lib.LAYOUT_DENSE if dense else _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
             inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
             depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), RRR,
-            g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b, stream),
-            "sdfr_compare_fused")
+            g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
+            bounds.data_ptr() if use_bounds else None, stream), "sdfr_compare_fused")
 
     def scale():
         _lib.check(lib.sdfr_scale_grads(
@@ -326,6 +337,7 @@ def main():
         # layout pass, then forward render + masked-L1 compare + backward in ONE traversal, then
         # the deferred per-hypothesis normalisation of the gradients
         skew()
+        bound()
         fused()
         scale()
         if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
@@ -371,7 +383,10 @@ def main():
 
     # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
     skew()
+    bound()
     fused_ms = timed(fused, K, 2) / K
+    fused_nobounds_ms = timed(lambda: fused(False, False), K, 2) / K
+    bound_ms = timed(bound, K, 2) / K
     fused_dense_ms = timed(lambda: fused(True), K, 2) / K
     skew_ms = timed(skew, K, 2) / K
     scale_ms = timed(scale, K, 2) / K
@@ -512,13 +527,16 @@ def main():
             "fused_incl_memsets": {"ms": fused_ms, "bytes": fused_bytes, "GBps": fused_bytes / fused_ms / 1e6},
             "fused_dense_layout_incl_memsets": {"ms": fused_dense_ms, "bytes": fused_bytes,
                                                 "GBps": fused_bytes / fused_dense_ms / 1e6},
+            "fused_without_empty_space_bounds": {"ms": fused_nobounds_ms},
+            "grid_bounds": {"ms": bound_ms, "bytes": 4 * SK * B, "GBps": 4 * SK * B / bound_ms / 1e6},
             "skew_grids": {"ms": skew_ms, "bytes": 4 * (RRR + SK) * B, "GBps": 4 * (RRR + SK) * B / skew_ms / 1e6},
             "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
             "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
             "unfused_backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
         },
         "work": {"samples_S": S, "hit_pixels": Hh_all, "overlap_pixels_Hh": n_over,
-                 "box_pixels": stats["box_pixels"], "pixels": P * B},
+                 "box_pixels": stats["box_pixels"], "pixels": P * B,
+                 "without_empty_space_bounds": {"samples_S": stats_full["samples"], "box_pixels": stats_full["box_pixels"]}},
     }
 
     line = {
@@ -540,7 +558,7 @@ def main():
                 "ms_per_step_cuda_graph": (e2e_graph_s / Ke * 1e3) if e2e_graph_s else e2e_check_g,
                 "d2h": "loss, n_overlap, 8 pose gradients per hypothesis; SDF gradients stay on the device",
                 "checksum": e2e_check},
-        "gpu_launches": 4 * K,  # skew + pose-zero + fused + scale kernels per step
+        "gpu_launches": 6 * K,  # skew + bounds init + bounds scan + pose-zero + fused + scale kernels per step
         "clocks": clocks.summary(),
         "lib": lib.sdfr_build_info().decode(),
     }

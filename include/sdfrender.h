@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 7
+#define SDFR_ABI_VERSION 8
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -101,13 +101,42 @@ int sdfr_skew_grids(const float* sdf, int resolution, long long sdf_stride, int 
                     float* skewed, long long skewed_stride, void* stream);
 
 /*
+ * Cell bounds of a grid: the first / last CELL index per axis (cell i spans voxels i and i+1) whose
+ * smallest corner value is below `tau`, the largest value the interpolated field can have where the
+ * march of any hypothesis using the grid can still terminate (sdf_renderer_cuda.cu:286: dist <
+ * threshold * t, so trilinear < threshold * t / scale <= tau).  lo > hi: no such cell.
+ */
+typedef struct sdfr_cell_bounds {
+  int lo[3];
+  int hi[3];
+  float tau;
+  int pad;
+} sdfr_cell_bounds;
+
+/*
+ * Empty-space bounds for the render entry points (their optional `bounds` argument).  The reference
+ * marches every ray that enters the grid's [-1,1]^3 box (sdf_renderer_cuda.cu:272-293); most of
+ * them cross only space where the field stays above the hit threshold and end with depth 0.  This
+ * pass finds, per grid, the box of cells where a hit is possible at all; the render kernels then write 0
+ * for rays that miss that box (plus one cell of margin) without marching them, and march all other
+ * rays from the reference's own box entry -- identical samples, identical depth, identical gradients.
+ * One entry per grid: bounds[b] for grid sdf + b*sdf_stride, a single entry (valid for all `batch`
+ * hypotheses) when sdf_stride == 0.  position / inv_scale / threshold are those of the render that
+ * will use the bounds (tau depends on them); an entry is ignored by a render whose own tau is larger.
+ * Cost: one read of the grids (~8 us for 64 x 64^3 on a B200).
+ */
+int sdfr_grid_bounds(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
+                     const float* position, const float* inv_scale, int batch, float threshold,
+                     sdfr_cell_bounds* bounds, void* stream);
+
+/*
  * Forward: replaces sdf_renderer_cpp.forward (sdf_renderer.cpp:42-61 ->
  * sdf_renderer_cuda.cu:472-510 -> forward kernel :241-298), batched over `batch` hypotheses.
  */
 int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, int sdf_layout, const float* position,
                  const float* orientation, const float* inv_scale, int batch, int width,
                  int height, float cx, float cy, float fx, float fy, float threshold,
-                 float* depth, void* stream);
+                 float* depth, const sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * Same as sdfr_forward, additionally accumulating work counters into stats[4] (device,
@@ -117,21 +146,23 @@ int sdfr_forward(const float* sdf, int resolution, long long sdf_stride, int sdf
 int sdfr_forward_stats(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                        const float* position, const float* orientation, const float* inv_scale,
                        int batch, int width, int height, float cx, float cy, float fx, float fy,
-                       float threshold, float* depth, unsigned long long* stats, void* stream);
+                       float threshold, float* depth, unsigned long long* stats,
+                       const sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * Backward: replaces sdf_renderer_cpp.backward (sdf_renderer.cpp:63-86 ->
  * sdf_renderer_cuda.cu:512-556 -> backward kernel :300-468), batched.
  * grad_depth, depth: [batch,height,width].  grad_sdf: hypothesis b accumulates into
  * grad_sdf + b*grad_sdf_stride (0 = all hypotheses into one grid).  grad_position [batch,3],
- * grad_orientation [batch,4] (x,y,z,w), grad_inv_scale [batch].
+ * grad_orientation [batch,4] (x,y,z,w), grad_inv_scale [batch].  `bounds` (optional) must be bounds
+ * that were valid for the forward that produced `depth`; they only shrink the image region scanned.
  */
 int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int resolution,
                   long long sdf_stride, int sdf_layout, const float* position, const float* orientation,
                   const float* inv_scale, int batch, int width, int height, float cx, float cy,
                   float fx, float fy, float* grad_sdf, long long grad_sdf_stride,
                   float* grad_position, float* grad_orientation, float* grad_inv_scale,
-                  unsigned flags, void* stream);
+                  unsigned flags, const sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * Fused render-and-compare, forward: renders `batch` hypotheses and compares each with an
@@ -146,7 +177,7 @@ int sdfr_compare_forward(const float* sdf, int resolution, long long sdf_stride,
                          const float* inv_scale, int batch, int width, int height, float cx,
                          float cy, float fx, float fy, float threshold, const float* depth_obs,
                          long long obs_stride, float* depth, float* loss_sum, float* n_overlap,
-                         unsigned flags, void* stream);
+                         unsigned flags, const sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * Fused render-and-compare, backward: gradient of  sum_b upstream[b] * loss_sum[b]/n_overlap[b]
@@ -161,7 +192,7 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
                           int width, int height, float cx, float cy, float fx, float fy,
                           float* grad_sdf, long long grad_sdf_stride, float* grad_position,
                           float* grad_orientation, float* grad_inv_scale, unsigned flags,
-                          void* stream);
+                          const sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * Fused render-and-compare with the backward folded into the SAME traversal (one kernel): as
@@ -178,7 +209,8 @@ int sdfr_compare_fused(const float* sdf, int resolution, long long sdf_stride, i
                        float threshold, const float* depth_obs, long long obs_stride,
                        float* depth, float* loss_sum, float* n_overlap, float* grad_sdf,
                        long long grad_sdf_stride, float* grad_position, float* grad_orientation,
-                       float* grad_inv_scale, unsigned flags, void* stream);
+                       float* grad_inv_scale, unsigned flags, const sdfr_cell_bounds* bounds,
+                       void* stream);
 
 /* In place:  grad[b] *= (upstream ? upstream[b] : 1) / n_overlap[b]  (0 where n_overlap == 0)
  * for the buffers selected by `flags`. */
@@ -197,7 +229,7 @@ int sdfr_forward_composite(const float* sdf, int resolution, long long sdf_strid
                            const float* position, const float* orientation,
                            const float* inv_scale, int n_objects, int width, int height,
                            float cx, float cy, float fx, float fy, float threshold, float* depth,
-                           int* winner, void* stream);
+                           int* winner, const sdfr_cell_bounds* bounds, void* stream);
 
 /* Backward of sdfr_forward_composite: every pixel back-propagates to its winner. */
 int sdfr_backward_composite(const float* grad_depth, const float* depth, const int* winner,
@@ -319,7 +351,7 @@ int sdfr_compare_fused_inliers(const float* sdf, int resolution, long long sdf_s
                                float rel_threshold, float* n_inlier, float* grad_sdf,
                                long long grad_sdf_stride, float* grad_position,
                                float* grad_orientation, float* grad_inv_scale, unsigned flags,
-                               void* stream);
+                               const sdfr_cell_bounds* bounds, void* stream);
 
 int sdfr_track_best(float* n_inlier, float* n_valid, const float* position, const float* orientation,
                     const float* scale, const float* latent, int latent_size, int batch,

@@ -62,7 +62,8 @@ def hypothesis_step(state, loss_sum, n_overlap, gr_p, gr_q, gr_is, depth_weight,
     n = np.asarray(n_overlap, np.float64).reshape(-1)
     loss = np.zeros_like(scale)
     if loss_sum is not None:
-        loss = depth_weight * np.where(n > 0, np.asarray(loss_sum, np.float64) / np.where(n > 0, n, 1), 0.0)
+        # no overlap: NaN, the reference's mean over an empty selection (simple_setup.py:131)
+        loss = depth_weight * np.where(n > 0, np.asarray(loss_sum, np.float64) / np.where(n > 0, n, 1), np.nan)
     if point_sum is not None:
         loss = loss + point_weight * np.asarray(point_sum, np.float64)
     g_p, g_o, g_s = chain_gradients(ori, scale, n, gr_p, gr_q, gr_is, depth_weight, g2_p, g2_q, g2_s)

@@ -29,9 +29,9 @@ depth = torch.empty(B, H, W, device=dev); sums = torch.zeros(2, B, device=dev)
 g_sdf = torch.empty_like(grids); g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 def fused():
-    assert 0 == (lib.sdfr_compare_fused(skewed.data_ptr(), R, SK, 1, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), R**3, g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, st))
+    assert 0 == (lib.sdfr_compare_fused(skewed.data_ptr(), R, SK, 1, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), R**3, g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, None, st))
 def fwd():
-    assert 0 == (lib.sdfr_forward(skewed.data_ptr(), R, SK, 1, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR, depth.data_ptr(), st))
+    assert 0 == (lib.sdfr_forward(skewed.data_ptr(), R, SK, 1, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR, depth.data_ptr(), None, st))
 def timed(fn, n=40):
     ts = []
     for i in range(n + 5):

@@ -60,11 +60,11 @@ st = torch.cuda.current_stream().cuda_stream
 
 def ours_single_cabi():
     lib.sdfr_forward(grid.data_ptr(), R, 0, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1, W, H,
-                     320.0, 240.0, 320.0, 320.0, THR, depth1.data_ptr(), st)
+                     320.0, 240.0, 320.0, 320.0, THR, depth1.data_ptr(), None, st)
     lib.sdfr_backward(g.data_ptr(), depth1.data_ptr(), grid.data_ptr(), R, 0, 0, p.data_ptr(),
                       q.data_ptr(), s.data_ptr(), 1, W, H, 320.0, 240.0, 320.0, 320.0,
                       gs.data_ptr(), 0, gp.data_ptr(), gq.data_ptr(), gi.data_ptr(),
-                      _lib.GRAD_ALL | _lib.ZERO_GRADS, st)
+                      _lib.GRAD_ALL | _lib.ZERO_GRADS, None, st)
 
 
 out["c1_ours_autograd"] = timed(ours_single)
@@ -93,7 +93,7 @@ depth = torch.empty(B, H, W, device=dev)
 sums = torch.zeros(2, B, device=dev)
 obs = torch.empty(H, W, device=dev)
 lib.sdfr_forward(grids.data_ptr(), R, 0, 0, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), 1, W, H,
-                 320.0, 240.0, 320.0, 320.0, THR, obs.data_ptr(), st)
+                 320.0, 240.0, 320.0, 320.0, THR, obs.data_ptr(), None, st)
 g_sdf = torch.empty_like(grids)
 g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
 RRR = R ** 3
@@ -117,7 +117,7 @@ def fwd(layout=1):
     lib.sdfr_compare_forward(ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                              inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
                              obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
-                             sums[1].data_ptr(), _lib.ZERO_GRADS, st)
+                             sums[1].data_ptr(), _lib.ZERO_GRADS, None, st)
 
 
 def fused(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
@@ -126,7 +126,7 @@ def fused(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
                            inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
                            obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
                            sums[1].data_ptr(), g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
-                           g_quat.data_ptr(), g_is.data_ptr(), flags, st)
+                           g_quat.data_ptr(), g_is.data_ptr(), flags, None, st)
 
 
 def bwd(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
@@ -135,7 +135,7 @@ def bwd(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
                               ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                               inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0,
                               g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
-                              g_is.data_ptr(), flags, st)
+                              g_is.data_ptr(), flags, None, st)
 
 
 fwd()

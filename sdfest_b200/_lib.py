@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -39,23 +39,25 @@ SIGNATURES = {
     "sdfr_last_error": (ctypes.c_char_p, []),
     "sdfr_build_info": (ctypes.c_char_p, []),
     "sdfr_max_steps": (c_int, []),
-    "sdfr_forward": (c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P]),
+    # the trailing (_P, _P) of the render entry points are (bounds or NULL, stream)
+    "sdfr_grid_bounds": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_int, c_float, _P, _P]),
+    "sdfr_forward": (c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
     "sdfr_forward_stats": (
-        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P, _P]),
     "sdfr_backward": (
-        c_int, [_P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
+        c_int, [_P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P, _P]),
     "sdfr_compare_forward": (
         c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
-                c_uint, _P]),
+                c_uint, _P, _P]),
     "sdfr_compare_backward": (
         c_int, [_P, _P, c_longlong, _P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS,
-                c_uint, _P]),
+                c_uint, _P, _P]),
     "sdfr_compare_fused": (
         c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
-                *_GRADS, c_uint, _P]),
+                *_GRADS, c_uint, _P, _P]),
     "sdfr_compare_fused_inliers": (
         c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, c_longlong, _P, _P, _P,
-                c_float, _P, *_GRADS, c_uint, _P]),
+                c_float, _P, *_GRADS, c_uint, _P, _P]),
     "sdfr_skewed_pitches": (c_int, [c_int, _P, _P, _P]),
     "sdfr_skew_grids": (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P]),
     "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P]),
@@ -83,7 +85,7 @@ SIGNATURES = {
     "sdfr_conv3d_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P]),
     "sdfr_conv3d_backward_data": (c_int, [_P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P, _P]),
     "sdfr_forward_composite": (
-        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
+        c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P, _P]),
     "sdfr_backward_composite": (
         c_int, [_P, _P, _P, _P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, *_GRADS, c_uint, _P]),
 }

@@ -29,8 +29,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
+N_PARTS = 4  # sdfrender.cu compiles as four translation units (-DSDFR_PART=1..4) in parallel
+OBJ_DIR = os.path.join(os.path.dirname(PKG_DIR), "build")
 
 
 def find_nvcc() -> str:
@@ -51,12 +52,33 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and up_to_date():
         return LIB_PATH
     extra = os.environ.get("SDFR_NVCC_EXTRA", "").split()  # tuning experiments (-DSDFR_FWD_BLOCKS=4)
-    cmd = [find_nvcc(), *NVCC_FLAGS, *extra, *SOURCES, "-o", LIB_PATH]
-    if verbose:
-        cmd[1:1] = ["-Xptxas", "-v"]
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
-    return LIB_PATH
+    nvcc = find_nvcc()
+    out_lib = os.environ.get("SDFR_BUILD_OUT") or LIB_PATH  # tuning experiments build a second library
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    tag = "".join(c if c.isalnum() else "_" for c in os.path.basename(out_lib))
+    objs, procs = [], []
+    for part in range(1, N_PARTS + 1):
+        obj = os.path.join(OBJ_DIR, f"{tag}_part{part}.o")
+        cmd = [nvcc, *NVCC_FLAGS, *extra, f"-DSDFR_PART={part}", "-c", *SOURCES, "-o", obj]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        log = open(obj + ".log", "w")
+        procs.append((subprocess.Popen(cmd, stdout=log, stderr=subprocess.STDOUT), cmd, log))
+        objs.append(obj)
+    failed = None
+    for proc, cmd, log in procs:
+        rc = proc.wait()
+        log.close()
+        text = open(log.name).read()
+        if verbose or rc != 0:
+            sys.stdout.write(text)
+        if rc != 0 and failed is None:
+            failed = subprocess.CalledProcessError(rc, cmd)
+    if failed is not None:
+        raise failed
+    subprocess.check_call([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", *objs, "-o", out_lib])
+    return out_lib
 
 
 if __name__ == "__main__":

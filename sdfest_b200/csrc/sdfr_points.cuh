@@ -159,7 +159,7 @@ sdfr_point_loss_kernel(const __grid_constant__ PointParams P) {
         }
       }
     }
-    if (BACKWARD && WANT_SDF) scatter_sdf_warp<0>(gsdf, G, pg, has, lane);
+    if (BACKWARD && WANT_SDF) scatter_sdf_warp<0>(gsdf, G, pg.base, pg.w, has, lane);
   }
 
   /* CTA reduction: one value (forward) or eight (backward) */

@@ -25,7 +25,9 @@
  *     m = m + (g - m)(1 - b1);  v = b2 v + (1 - b2) g g;
  *     p += -(lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
  *   orientation /= |orientation|;  unit_orientation = orientation / |orientation|;  inv_scale = 1/scale
- *   loss      = depth_weight * (n_overlap > 0 ? loss_sum / n_overlap : 0) + point_weight * point_sum
+ *   loss      = depth_weight * (n_overlap > 0 ? loss_sum / n_overlap : NaN) + point_weight * point_sum
+ *               (NaN = the reference's mean over an empty overlap; such a hypothesis must never rank
+ *               best -- its gradients are 0, not NaN, so the optimiser state stays finite)
  * and optionally clears the gradient inputs it consumed, so that the next iteration's kernels can
  * accumulate into them without a memset node.
  */
@@ -130,7 +132,9 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
   /* ---- arithmetic ---- */
   const float coef = n > 0.0f ? P.depth_weight / n : 0.0f;
   float l = 0.0f;
-  if (P.loss_sum && n > 0.0f) l = P.depth_weight * (lsum / n);
+  /* no overlap: the reference's mean over an empty selection is NaN (simple_setup.py:131) and so is its
+   * loss; the GRADIENTS stay 0 here (coef above) instead of poisoning Adam as the reference's do */
+  if (P.loss_sum) l = n > 0.0f ? P.depth_weight * (lsum / n) : __int_as_float(0x7fc00000);
   if (P.point_sum) l += P.point_weight * psum;
   float bc1 = 1.0f, bc2_sqrt = 1.0f;
   if (!frozen) {

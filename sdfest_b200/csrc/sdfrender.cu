@@ -35,9 +35,26 @@
 #include "../../include/sdfrender.h"
 #include "sdfr_core.cuh"
 
+/* The library is one source file compiled either whole (SDFR_PART undefined / 0) or as four
+ * translation units in parallel (sdfest_b200/build.py: -DSDFR_PART=1..4; 1 = forward, 2 = fused
+ * forward, 3 = backward / composite / grid passes, 4 = point loss, decoder, optimiser step). */
+#ifndef SDFR_PART
+#define SDFR_PART 0
+#endif
+#define SDFR_IN_PART(k) (SDFR_PART == 0 || SDFR_PART == (k))
+
+namespace sdfr_detail {
+#if SDFR_PART <= 1
+thread_local char g_err[256] = "";
+#else
+extern thread_local char g_err[256];
+#endif
+}  // namespace sdfr_detail
+
 namespace {
 
 using namespace sdfr;
+using sdfr_detail::g_err;
 
 constexpr int kTileW = 32;
 constexpr int kTileH = 8;
@@ -45,8 +62,6 @@ constexpr int kThreads = kTileW * kTileH;  // 256 = 8 warps of 8x4 pixels
 constexpr int kWarps = kThreads / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kListCap = 1024; /* warp tiles per work-list chunk of the forward kernels */
-
-thread_local char g_err[256] = "";
 
 int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -66,6 +81,10 @@ struct Pose {
   const float* __restrict__ position;     // [B,3]
   const float* __restrict__ orientation;  // [B,4]
   const float* __restrict__ inv_scale;    // [B]
+  const CellBounds* __restrict__ bounds;  // optional cell bounds of the grids (sdfr_grid_bounds)
+  int bounds_stride;                      // 0: one entry shared by all hypotheses, 1: one per hypothesis
+  int R;
+  float threshold;
 };
 
 struct FwdParams {
@@ -127,7 +146,8 @@ struct BwdParams {
 __device__ __forceinline__ void build_frame(Frame& smemF, HullEdge* edges, const Pose& pose, int b,
                                             const Camera& cam, int lane) {
   Frame F;
-  frame_pose(F, pose.position + 3 * b, pose.orientation + 4 * b, pose.inv_scale + b);
+  frame_pose(F, pose.position + 3 * b, pose.orientation + 4 * b, pose.inv_scale + b,
+             pose.bounds ? pose.bounds + (size_t)b * pose.bounds_stride : nullptr, pose.R, pose.threshold);
   float col = 0.f, row = 0.f;
   const bool ok = project_corner(F, cam, lane & 7, col, row);
   const bool all_ok = __all_sync(kFull, ok);
@@ -272,18 +292,18 @@ __device__ __forceinline__ Tiling cta_prologue(Frame& Fs, HullEdge* edges, float
 }
 
 template <int RT>
-__device__ __forceinline__ void scatter_sdf(float* __restrict__ gs, const Grid& G,
-                                            const PixelGrad& pg) {
+__device__ __forceinline__ void scatter_sdf(float* __restrict__ gs, const Grid& G, int base,
+                                            const float (&w)[8]) {
   const int R = RT > 0 ? RT : G.R, R2 = R * R;
-  gs += pg.base;
-  atomicAdd(gs, pg.w[0]);
-  atomicAdd(gs + 1, pg.w[1]);
-  atomicAdd(gs + R, pg.w[2]);
-  atomicAdd(gs + R + 1, pg.w[3]);
-  atomicAdd(gs + R2, pg.w[4]);
-  atomicAdd(gs + R2 + 1, pg.w[5]);
-  atomicAdd(gs + R2 + R, pg.w[6]);
-  atomicAdd(gs + R2 + R + 1, pg.w[7]);
+  gs += base;
+  atomicAdd(gs, w[0]);
+  atomicAdd(gs + 1, w[1]);
+  atomicAdd(gs + R, w[2]);
+  atomicAdd(gs + R + 1, w[3]);
+  atomicAdd(gs + R2, w[4]);
+  atomicAdd(gs + R2 + 1, w[5]);
+  atomicAdd(gs + R2 + R, w[6]);
+  atomicAdd(gs + R2 + R + 1, w[7]);
 }
 
 /*
@@ -294,9 +314,9 @@ __device__ __forceinline__ void scatter_sdf(float* __restrict__ gs, const Grid& 
  * by all 32 lanes; `has` marks lanes that carry a contribution.
  */
 template <int RT>
-__device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const Grid& G, PixelGrad& pg,
-                                                 bool has, int lane) {
-  const int key = has ? pg.base : -1;
+__device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const Grid& G, int base,
+                                                 float (&w)[8], bool has, int lane) {
+  const int key = has ? base : -1;
   bool alive = has;
 #pragma unroll
   for (int k = 0; k < 5; ++k) {
@@ -306,38 +326,75 @@ __device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const G
     const bool lower = (lane & (1 << k)) == 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float o = __shfl_xor_sync(kFull, pg.w[i], 1 << k);
-      if (merge && lower) pg.w[i] += o;
+      const float o = __shfl_xor_sync(kFull, w[i], 1 << k);
+      if (merge && lower) w[i] += o;
     }
     if (merge && !lower) alive = false;
   }
-  if (alive) scatter_sdf<RT>(gs, G, pg);
+  if (alive) scatter_sdf<RT>(gs, G, base, w);
 }
 
-/* registers -> warp shuffle -> shared -> 8 atomics per CTA (the reference issues 8 same-address
- * atomics per hit pixel, cu:459-466).  Contains one barrier: call from uniform control flow. */
-__device__ __forceinline__ void reduce_pose(float (&acc)[8], float (*red)[8], int b,
+/* Pose gradients of a CTA.  Every thread keeps its 13 moment sums (sdfr_core.cuh:
+ * pixel_backward_moments) in SHARED memory, acc_s[i][thread] -- 13 registers that would otherwise be
+ * live across the whole march loop (they were the fused kernel's spill) -- and in DOUBLE: the products
+ * are fp32, the running sums are not, so a gradient that nearly cancels over the pixels (a rotationally
+ * symmetric shape's orientation gradient) keeps the digits the per-pixel formulation has.  A hit pixel
+ * costs 13 conflict-free read-modify-writes.  At the end: warp shuffle -> warp 0 applies the 13 -> 8 map
+ * of the hypothesis once -> 8 atomics per CTA (the reference issues 8 same-address atomics per hit
+ * pixel, cu:459-466).  Contains two barriers: call from uniform control flow. */
+typedef double MomentAcc[kMoments][kThreads];
+
+__device__ __forceinline__ void moments_clear(MomentAcc& acc_s) {
+#pragma unroll
+  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] = 0.0;
+}
+
+__device__ __forceinline__ void moments_add(MomentAcc& acc_s, const float (&m)[kMoments]) {
+#pragma unroll
+  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] += (double)m[i];
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+/* The 13 -> 8 map runs once per CTA in one thread; kept out of line so that its double-precision
+ * temporaries never compete with the march loop for the kernel's 48 registers. */
+__device__ __noinline__ void pose_from_moments(const Frame* F, const Grid* G, const double* m, int stride,
+                                               float* out) {
+  double mm[kMoments];
+#pragma unroll
+  for (int i = 0; i < kMoments; ++i) mm[i] = m[(size_t)i * stride];
+  moments_to_pose(*F, *G, mm, out);
+}
+
+__device__ __forceinline__ void reduce_pose(MomentAcc& acc_s, const Frame& F, const Grid& G, int b,
                                             float* gp, float* gq, float* gi, unsigned flags) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  /* warp w sums moments w, w + 8 over the 256 threads; the totals land in row i, column 0 */
+  for (int i = warp; i < kMoments; i += kWarps) {
+    double v = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-  if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) red[warp][i] = acc[i];
+    for (int j = 0; j < kThreads / 32; ++j) v += acc_s[i][lane + 32 * j];
+    v = warp_sum_d(v);
+    if (lane == 0) acc_s[i][0] = v;
   }
   __syncthreads();
-  if (threadIdx.x < 8) {
-    float s = 0.0f;
-#pragma unroll
-    for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
-    const int i = threadIdx.x;
-    if (s != 0.0f) {
-      if (i < 3) {
-        if (flags & SDFR_GRAD_POSITION) atomicAdd(gp + 3 * b + i, s);
-      } else if (i < 7) {
-        if (flags & SDFR_GRAD_ORIENTATION) atomicAdd(gq + 4 * b + (i - 3), s);
+  __shared__ float pose_out[8];
+  if (warp == 0) {
+    if (lane == 0) pose_from_moments(&F, &G, &acc_s[0][0], kThreads, pose_out);
+    __syncwarp();
+    const float v = lane < 8 ? pose_out[lane] : 0.0f;
+    if (lane < 8 && v != 0.0f) {
+      if (lane < 3) {
+        if (flags & SDFR_GRAD_POSITION) atomicAdd(gp + 3 * b + lane, v);
+      } else if (lane < 7) {
+        if (flags & SDFR_GRAD_ORIENTATION) atomicAdd(gq + 4 * b + (lane - 3), v);
       } else {
-        if (flags & SDFR_GRAD_INV_SCALE) atomicAdd(gi + b, s);
+        if (flags & SDFR_GRAD_INV_SCALE) atomicAdd(gi + b, v);
       }
     }
   }
@@ -359,7 +416,8 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
   __shared__ HullEdge edges[kMaxHullEdges];
-  __shared__ float red[kWarps][8];
+  __shared__ double acc_mem[(MODE == 2 && WANT_POSE) ? kMoments * kThreads : 1];
+  MomentAcc& acc_s = *reinterpret_cast<MomentAcc*>(acc_mem);
   __shared__ int next_q, n_live;
   __shared__ unsigned worklist[kListCap];
 
@@ -409,9 +467,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
    * rays finish early takes the next entry).  Testing inside the drain loop instead cost ~90 warp
    * instructions per culled warp tile and ~50 per live one -- 21 % of all executed instructions at
    * BASELINE config 2 (profiles/r01g_ncu_fused_segments.txt). */
-  float acc[8]; /* MODE 2: pose gradients */
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  if (MODE == 2 && WANT_POSE) moments_clear(acc_s); /* own column only: no barrier needed */
   float err_acc = 0.0f, cnt_acc = 0.0f, inl_acc = 0.0f;
   unsigned st_steps = 0, st_entered = 0, st_hit = 0, st_capped = 0;
   const int n_rect = T.rtw * T.rth;
@@ -468,7 +524,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
         const float uy = P.use_tables ? rowy[py - T.tab_y0 * kTileH] : pixel_dy(py, P.cam.cy, P.cam.fy);
         ray = make_ray(F, ux, uy);
         float t_min, t_max;
-        if (ray_box(F, ray, t_min, t_max)) {
+        if (ray_enters_cull_box(F, ray) && ray_box(F, ray, t_min, t_max)) {
           int steps;
           bool capped;
           z = march<RT, LT>(grid, Gc, F, ray, t_min, t_max, P.threshold, steps, capped);
@@ -498,20 +554,22 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
         }
       }
       if (MODE == 2 && __any_sync(kFull, sgn != 0.0f)) {
-        PixelGrad pg;
-        if (sgn != 0.0f)
-          pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, z, sgn,
-                                                      (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
+        int base = 0;
+        float w8[8];
+        if (sgn != 0.0f) {
+          float m[kMoments];
+#pragma unroll
+          for (int i = 0; i < kMoments; ++i) m[i] = 0.0f;
+          pixel_backward_moments<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, z, sgn,
+                                                              (P.flags & SDFR_SDF_GRAD_EXACT) != 0, base, w8, m);
+          if (WANT_POSE) moments_add(acc_s, m);
+        }
         if (WANT_SDF) {
 #ifdef SDFR_NO_WARP_AGGREGATION
-          if (sgn != 0.0f) scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg);
+          if (sgn != 0.0f) scatter_sdf<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, base, w8);
 #else
-          scatter_sdf_warp<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, pg, sgn != 0.0f, lane);
+          scatter_sdf_warp<RT>(P.grad_sdf + (size_t)b * P.grad_sdf_stride, Gc, base, w8, sgn != 0.0f, lane);
 #endif
-        }
-        if (WANT_POSE && sgn != 0.0f) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * sgn;
         }
       }
       if (lane == 0) q = atomicAdd(&next_q, 1);
@@ -542,7 +600,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
     }
   }
   if (MODE == 2 && WANT_POSE)
-    reduce_pose(acc, red, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
+    reduce_pose(acc_s, F, Gc, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -554,12 +612,16 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
 /* Register budget of the backward kernels: the SDF+pose variant needs ~80 registers; squeezed
  * into 64 (4 CTAs/SM) it spills, and the spill traffic (7 M write sectors per launch at C2,
  * profiles/r01d_bwd_ncu.txt) made it 4x slower than either single-purpose variant. */
+#ifndef SDFR_BWD_BLOCKS
+#define SDFR_BWD_BLOCKS 4
+#endif
 template <int RT, int LT, int MODE, bool WANT_SDF, bool WANT_POSE>
-__global__ void __launch_bounds__(kThreads, (WANT_SDF && WANT_POSE) ? 3 : 4)
+__global__ void __launch_bounds__(kThreads, SDFR_BWD_BLOCKS)
 sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
-  __shared__ float red[kWarps][8];
+  __shared__ double acc_mem[WANT_POSE ? kMoments * kThreads : 1];
+  MomentAcc& acc_s = *reinterpret_cast<MomentAcc*>(acc_mem);
 
   const int b = blockIdx.y + P.z_offset;
   const int g = blockIdx.x, G = gridDim.x;
@@ -585,10 +647,9 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   const float* __restrict__ grid = P.sdf + (size_t)b * P.sdf_stride;
   float* __restrict__ gsdf = WANT_SDF ? P.grad_sdf + (size_t)b * P.grad_sdf_stride : nullptr;
   const bool exact = (P.flags & SDFR_SDF_GRAD_EXACT) != 0;
+  const Grid Gc = RT > 0 ? make_grid(RT, LT) : P.grid;
 
-  float acc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  if (WANT_POSE) moments_clear(acc_s);
 
   /* the scan is latency bound (two dependent-free loads per pixel, ~7 % of the warp tiles hold
    * work): the loads of the NEXT tile are issued before the current one is processed */
@@ -619,30 +680,36 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
     const bool cvalid = valid;
     w.next();
     fetch(r + G);
-    if (!cvalid || zc == 0.0f) continue;
-    float gup;
-    if (MODE == 0) {
-      gup = uc;
-    } else {
-      gup = (zc > 0.0f && uc > 0.0f) ? ((zc > uc) ? coef : ((zc < uc) ? -coef : 0.0f)) : 0.0f;
+    float gup = 0.0f;
+    if (cvalid && zc != 0.0f) {
+      if (MODE == 0) {
+        gup = uc;
+      } else {
+        gup = (zc > 0.0f && uc > 0.0f) ? ((zc > uc) ? coef : ((zc < uc) ? -coef : 0.0f)) : 0.0f;
+      }
     }
-    if (gup == 0.0f) continue;
-    const float ux = P.use_tables ? colx[(ctx - T.tab_x0) * kTileW + lx]
-                                  : pixel_dx(cpx, P.cam.cx, P.cam.fx);
-    const float uy = P.use_tables ? rowy[(cty - T.tab_y0) * kTileH + ly]
-                                  : pixel_dy(cpy, P.cam.cy, P.cam.fy);
-    const Ray ray = make_ray(F, ux, uy);
-    PixelGrad pg;
-    pixel_backward<RT, WANT_SDF, WANT_POSE, LT>(grid, P.grid, F, ray, zc, gup, exact, pg);
-    if (WANT_SDF) scatter_sdf<RT>(gsdf, P.grid, pg);
-    if (WANT_POSE) {
+    const bool has = gup != 0.0f;
+    if (!__any_sync(kFull, has)) continue; /* the loop is uniform over the CTA: all 32 lanes are here */
+    int base = 0;
+    float w8[8];
+    if (has) {
+      const float ux = P.use_tables ? colx[(ctx - T.tab_x0) * kTileW + lx]
+                                    : pixel_dx(cpx, P.cam.cx, P.cam.fx);
+      const float uy = P.use_tables ? rowy[(cty - T.tab_y0) * kTileH + ly]
+                                    : pixel_dy(cpy, P.cam.cy, P.cam.fy);
+      const Ray ray = make_ray(F, ux, uy);
+      float m[kMoments];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += pg.pose[i] * gup;
+      for (int i = 0; i < kMoments; ++i) m[i] = 0.0f;
+      pixel_backward_moments<RT, WANT_SDF, WANT_POSE, LT>(grid, Gc, F, ray, zc, gup, exact, base, w8, m);
+      if (WANT_POSE) moments_add(acc_s, m);
     }
+    /* neighbouring rays of the warp's 8x4 pixels mostly end in the same cell: merge, then RED */
+    if (WANT_SDF) scatter_sdf_warp<RT>(gsdf, Gc, base, w8, has, lane);
   }
 
   if (WANT_POSE)
-    reduce_pose(acc, red, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
+    reduce_pose(acc_s, F, Gc, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
 }
 
 /* grad *= upstream[b] / n_overlap[b]: the normalisation the fused compare kernel defers. */
@@ -697,6 +764,7 @@ __global__ void sdfr_zero_small_kernel(float* a, int na, float* b, int nb, float
  * ---------------------------------------------------------------------------------------- */
 constexpr int kMaxObjPerPass = 32;
 
+template <int RT, int LT>
 __global__ void __launch_bounds__(kThreads)
 sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects,
                               int* __restrict__ winner_out) {
@@ -710,6 +778,7 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
   const int ly = ((warp >> 2) << 2) + (lane >> 3);
   const int px = bx0 + lx, py = by0 + ly;
   const bool inside = px < P.cam.W && py < P.cam.H;
+  const Grid Gc = RT > 0 ? make_grid(RT, LT) : P.grid;
 
   if (warp == 1) colx[lane] = pixel_dx(bx0 + lane, P.cam.cx, P.cam.fx);
   if (warp == 2 && lane < kTileH) rowy[lane] = pixel_dy(by0 + lane, P.cam.cy, P.cam.fy);
@@ -727,11 +796,11 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
       if (px < F.x0 || px >= F.x1 || py < F.y0 || py >= F.y1) continue;
       const Ray r = make_ray(F, colx[lx], rowy[ly]);
       float t_min, t_max;
-      if (!ray_box(F, r, t_min, t_max)) continue;
+      if (!ray_enters_cull_box(F, r) || !ray_box(F, r, t_min, t_max)) continue;
       int steps;
       bool capped;
-      const float z = march<0>(P.sdf + (size_t)(k0 + k) * P.sdf_stride, P.grid, F, r, t_min,
-                               t_max, P.threshold, steps, capped);
+      const float z = march<RT, LT>(P.sdf + (size_t)(k0 + k) * P.sdf_stride, Gc, F, r, t_min,
+                                    t_max, P.threshold, steps, capped);
       if (z > 0.0f && (win < 0 || z < best)) {
         best = z;
         win = k0 + k;
@@ -745,7 +814,7 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
   }
 }
 
-template <bool WANT_SDF, bool WANT_POSE>
+template <int RT, int LT, bool WANT_SDF, bool WANT_POSE>
 __global__ void __launch_bounds__(kThreads)
 sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
   __shared__ float colx[kTileW];
@@ -758,6 +827,7 @@ sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
   const int px = bx0 + lx, py = by0 + ly;
   const bool inside = px < P.cam.W && py < P.cam.H;
   const size_t pix = (size_t)py * P.cam.W + px;
+  const Grid Gc = RT > 0 ? make_grid(RT, LT) : P.grid;
 
   float z = 0.0f, gup = 0.0f;
   int win = -1;
@@ -784,51 +854,126 @@ sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
 
     Frame F; /* every lane builds the pose part in registers; no rectangle needed */
     frame_pose(F, P.pose.position + 3 * k, P.pose.orientation + 4 * k, P.pose.inv_scale + k);
-    float acc[8];
+    float acc[kMoments];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+    for (int i = 0; i < kMoments; ++i) acc[i] = 0.0f;
+    int base = 0;
+    float w8[8];
     if (mine) {
       const Ray r = make_ray(F, colx[lx], rowy[ly]);
-      const float* __restrict__ g = P.sdf + (size_t)k * P.sdf_stride;
-      PixelGrad pg;
-      pixel_backward<0, WANT_SDF, WANT_POSE>(g, P.grid, F, r, z, gup,
-                                             (P.flags & SDFR_SDF_GRAD_EXACT) != 0, pg);
-      if (WANT_SDF) {
-        float* __restrict__ gs = P.grad_sdf + (size_t)k * P.grad_sdf_stride + pg.base;
-        const int R = P.grid.R, R2 = P.grid.R2;
-        atomicAdd(gs, pg.w[0]);
-        atomicAdd(gs + 1, pg.w[1]);
-        atomicAdd(gs + R, pg.w[2]);
-        atomicAdd(gs + R + 1, pg.w[3]);
-        atomicAdd(gs + R2, pg.w[4]);
-        atomicAdd(gs + R2 + 1, pg.w[5]);
-        atomicAdd(gs + R2 + R, pg.w[6]);
-        atomicAdd(gs + R2 + R + 1, pg.w[7]);
-      }
-      if (WANT_POSE) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = pg.pose[i] * gup;
-      }
+      pixel_backward_moments<RT, WANT_SDF, WANT_POSE, LT>(P.sdf + (size_t)k * P.sdf_stride, Gc, F, r, z, gup,
+                                                          (P.flags & SDFR_SDF_GRAD_EXACT) != 0, base, w8, acc);
     }
+    if (WANT_SDF) scatter_sdf_warp<RT>(P.grad_sdf + (size_t)k * P.grad_sdf_stride, Gc, base, w8, mine, lane);
     if (WANT_POSE) {
+      double accd[kMoments];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = warp_sum(acc[i]);
-      if (lane < 8) {
-        float s = acc[0];
+      for (int i = 0; i < kMoments; ++i) accd[i] = warp_sum_d((double)acc[i]);
+      float out[8];
+      pose_from_moments(&F, &Gc, accd, 1, out);
+      float v = out[0];
 #pragma unroll
-        for (int i = 1; i < 8; ++i) s = (lane == i) ? acc[i] : s;
-        if (s != 0.0f) {
-          if (lane < 3) {
-            if (P.flags & SDFR_GRAD_POSITION) atomicAdd(P.grad_position + 3 * k + lane, s);
-          } else if (lane < 7) {
-            if (P.flags & SDFR_GRAD_ORIENTATION)
-              atomicAdd(P.grad_orientation + 4 * k + (lane - 3), s);
-          } else {
-            if (P.flags & SDFR_GRAD_INV_SCALE) atomicAdd(P.grad_inv_scale + k, s);
-          }
+      for (int i = 1; i < 8; ++i) v = (lane == i) ? out[i] : v;
+      if (lane < 8 && v != 0.0f) {
+        if (lane < 3) {
+          if (P.flags & SDFR_GRAD_POSITION) atomicAdd(P.grad_position + 3 * k + lane, v);
+        } else if (lane < 7) {
+          if (P.flags & SDFR_GRAD_ORIENTATION) atomicAdd(P.grad_orientation + 4 * k + (lane - 3), v);
+        } else {
+          if (P.flags & SDFR_GRAD_INV_SCALE) atomicAdd(P.grad_inv_scale + k, v);
         }
       }
     }
+  }
+}
+
+/*
+ * Cell bounds of the grids (CellBounds, sdfr_core.cuh): per grid, the first / last cell index per axis
+ * whose smallest corner value lies below the hit-threshold bound tau of the hypotheses that render it.
+ * Rays that miss that box (plus a one-cell margin) cannot terminate anywhere, so the render kernels
+ * zero them without marching; rays that enter it are marched exactly as the reference marches them.
+ * For the reference workloads the object fills about a third of the [-1,1]^3 box's silhouette: two
+ * thirds of the rays the reference marches are proven empty by 6 integers per grid.
+ *   init kernel: tau per grid (max over the hypotheses sharing it), bounds := empty
+ *   scan kernel: CTA per (x cell layer, grid); a warp owns a (x, y) row of cells, lane = z (coalesced
+ *   reads of the 4 rows the cells touch), the cell minimum via one shuffle, ballots give the z range.
+ */
+__global__ void sdfr_bounds_init_kernel(const float* __restrict__ pos, const float* __restrict__ inv_scale,
+                                        int batch, int n_grids, float threshold, CellBounds* __restrict__ out) {
+  const int n = blockIdx.x;
+  float tau = 0.0f;
+  if (n_grids == 1) { /* one grid shared by the whole batch */
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) tau = fmaxf(tau, hit_tau(pos + 3 * b, inv_scale[b], threshold));
+  } else if (threadIdx.x == 0) {
+    tau = hit_tau(pos + 3 * n, inv_scale[n], threshold);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(kFull, tau, o));
+  __shared__ float red[32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tau;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) tau = fmaxf(tau, red[w]);
+    CellBounds cb;
+    cb.lo[0] = cb.lo[1] = cb.lo[2] = 0x7fffffff;
+    cb.hi[0] = cb.hi[1] = cb.hi[2] = -1;
+    cb.tau = tau;
+    cb.pad = 0;
+    out[n] = cb;
+  }
+}
+
+/* CTA = (x cell layer ix, tile of cell rows y0.., grid n).  Phase 1: the element-wise minimum of the two
+ * voxel layers ix, ix+1 over the tile's (rows + 1) x R values goes to shared memory -- every thread
+ * issues all its loads before the first use, so a CTA has its whole 2 x (rows+1) x R x 4 bytes in flight
+ * (a first version that walked the rows with one dependent load round trip each ran at 1 TB/s).
+ * Phase 2: a cell's minimum is the minimum of 4 neighbours in that plane; ballots give the z range. */
+__global__ void __launch_bounds__(256)
+sdfr_bounds_scan_kernel(const float* __restrict__ sdf, long long sdf_stride, int R, int py, int px,
+                        int tile_rows, CellBounds* __restrict__ out) {
+  extern __shared__ float plane[]; /* (rows + 1) x R */
+  __shared__ int s_lo[2], s_hi[2];
+  const int n = blockIdx.z, ix = blockIdx.x, y0 = blockIdx.y * tile_rows;
+  const int rows = min(tile_rows, R - 1 - y0); /* cell rows of this tile */
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ g0 = sdf + (size_t)n * sdf_stride + (size_t)ix * px + (size_t)y0 * py;
+  const float* __restrict__ g1 = g0 + px;
+  const float tau = out[n].tau;
+  if (threadIdx.x < 2) {
+    s_lo[threadIdx.x] = 0x7fffffff;
+    s_hi[threadIdx.x] = -1;
+  }
+  for (int y = warp; y <= rows; y += kWarps) {
+    const float* __restrict__ a = g0 + (size_t)y * py;
+    const float* __restrict__ b = g1 + (size_t)y * py;
+    for (int z = lane; z < R; z += 32) plane[y * R + z] = fminf(__ldg(a + z), __ldg(b + z));
+  }
+  __syncthreads();
+  int ylo = 0x7fffffff, yhi = -1, zlo = 0x7fffffff, zhi = -1;
+  for (int y = warp; y < rows; y += kWarps) {
+    const float* __restrict__ r0 = plane + y * R;
+    for (int z0 = 0; z0 < R - 1; z0 += 32) {
+      const int z = z0 + lane;
+      bool below = false;
+      if (z < R - 1) below = fminf(fminf(r0[z], r0[z + 1]), fminf(r0[R + z], r0[R + z + 1])) < tau;
+      const unsigned mask = __ballot_sync(kFull, below);
+      if (mask) {
+        ylo = min(ylo, y0 + y);
+        yhi = max(yhi, y0 + y);
+        zlo = min(zlo, z0 + __ffs(mask) - 1);
+        zhi = max(zhi, z0 + 31 - __clz(mask));
+      }
+    }
+  }
+  if (lane == 0 && yhi >= 0) {
+    atomicMin(&s_lo[0], ylo); atomicMax(&s_hi[0], yhi);
+    atomicMin(&s_lo[1], zlo); atomicMax(&s_hi[1], zhi);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0 && s_hi[0] >= 0) {
+    atomicMin(&out[n].lo[0], ix); atomicMax(&out[n].hi[0], ix);
+    atomicMin(&out[n].lo[1], s_lo[0]); atomicMax(&out[n].hi[1], s_hi[0]);
+    atomicMin(&out[n].lo[2], s_lo[1]); atomicMax(&out[n].hi[2], s_hi[1]);
   }
 }
 
@@ -1081,14 +1226,28 @@ int zero_grads(unsigned flags, int R, int batch, float* gs, long long gs_stride,
   return rc;
 }
 
+Pose make_pose(const float* pos, const float* quat, const float* inv_scale, const sdfr_cell_bounds* bounds,
+               long long sdf_stride, int R, float threshold) {
+  Pose p;
+  p.position = pos;
+  p.orientation = quat;
+  p.inv_scale = inv_scale;
+  p.bounds = reinterpret_cast<const CellBounds*>(bounds);
+  p.bounds_stride = sdf_stride != 0 ? 1 : 0; /* one entry per grid */
+  p.R = R;
+  p.threshold = threshold;
+  return p;
+}
+
 FwdParams fwd_params(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                      const float* quat, const float* inv_scale, int W, int H, float cx, float cy,
-                     float fx, float fy, float threshold, float* depth) {
+                     float fx, float fy, float threshold, float* depth,
+                     const sdfr_cell_bounds* bounds = nullptr) {
   FwdParams P;
   memset(&P, 0, sizeof(P));
   P.sdf = sdf;
   P.sdf_stride = sdf_stride;
-  P.pose = Pose{pos, quat, inv_scale};
+  P.pose = make_pose(pos, quat, inv_scale, bounds, sdf_stride, R, threshold);
   P.grid = make_grid(R, layout);
   P.cam = Camera{W, H, cx, cy, fx, fy};
   P.threshold = threshold;
@@ -1099,13 +1258,14 @@ FwdParams fwd_params(const float* sdf, int R, long long sdf_stride, int layout, 
 BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_stride, int layout,
                      const float* pos, const float* quat, const float* inv_scale, int W, int H,
                      float cx, float cy, float fx, float fy, float* gs, long long gs_stride,
-                     float* gp, float* gq, float* gi, unsigned flags) {
+                     float* gp, float* gq, float* gi, unsigned flags,
+                     const sdfr_cell_bounds* bounds = nullptr, float threshold = 0.0f) {
   BwdParams P;
   memset(&P, 0, sizeof(P));
   P.depth = depth;
   P.sdf = sdf;
   P.sdf_stride = sdf_stride;
-  P.pose = Pose{pos, quat, inv_scale};
+  P.pose = make_pose(pos, quat, inv_scale, bounds, sdf_stride, R, threshold);
   P.grid = make_grid(R, layout);
   P.cam = Camera{W, H, cx, cy, fx, fy};
   P.grad_sdf = gs;
@@ -1117,14 +1277,17 @@ BwdParams bwd_params(const float* depth, const float* sdf, int R, long long sdf_
   return P;
 }
 
+#if SDFR_IN_PART(4)
 #include "sdfr_points.cuh"
 #include "sdfr_decoder.cuh"
 #include "sdfr_step.cuh"
+#endif
 
 }  // namespace
 
 extern "C" {
 
+#if SDFR_IN_PART(1)
 int sdfr_abi_version(void) { return SDFR_ABI_VERSION; }
 const char* sdfr_last_error(void) { return g_err; }
 const char* sdfr_build_info(void) {
@@ -1132,35 +1295,42 @@ const char* sdfr_build_info(void) {
 }
 int sdfr_max_steps(void) { return sdfr::kMaxSteps; }
 
+#endif
+#if SDFR_IN_PART(1)
 int sdfr_forward(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                  const float* quat, const float* inv_scale, int batch, int W, int H, float cx,
-                 float cy, float fx, float fy, float threshold, float* depth, void* stream) {
+                 float cy, float fx, float fy, float threshold, float* depth,
+                 const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (batch == 0 || W == 0 || H == 0) return 0;
   if (!depth) return fail(SDFR_E_NULL, "depth is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           threshold, depth);
+                           threshold, depth, bounds);
   return launch_forward<0, false>(P, batch, (cudaStream_t)stream);
 }
 
+#endif
+#if SDFR_IN_PART(1)
 int sdfr_forward_stats(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                        const float* quat, const float* inv_scale, int batch, int W, int H,
                        float cx, float cy, float fx, float fy, float threshold, float* depth,
-                       unsigned long long* stats, void* stream) {
+                       unsigned long long* stats, const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (batch == 0 || W == 0 || H == 0) return 0;
   if (!depth || !stats) return fail(SDFR_E_NULL, "depth or stats is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           threshold, depth);
+                           threshold, depth, bounds);
   P.stats = stats;
   return launch_forward<0, true>(P, batch, (cudaStream_t)stream);
 }
 
+#endif
+#if SDFR_IN_PART(3)
 int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf, int R,
                   long long sdf_stride, int layout, const float* pos, const float* quat,
                   const float* inv_scale, int batch, int W, int H, float cx, float cy, float fx,
                   float fy, float* gs, long long gs_stride, float* gp, float* gq, float* gi,
-                  unsigned flags, void* stream) {
+                  unsigned flags, const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (batch == 0) return 0;
@@ -1172,16 +1342,19 @@ int sdfr_backward(const float* grad_depth, const float* depth, const float* sdf,
   if (empty) return 0;
   if (!grad_depth || !depth) return fail(SDFR_E_NULL, "grad_depth or depth is NULL");
   BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           gs, gs_stride, gp, gq, gi, flags);
+                           gs, gs_stride, gp, gq, gi, flags, bounds);
   P.grad_depth = grad_depth;
   return launch_backward<0>(P, batch, (flags & SDFR_ZERO_GRADS) != 0, s);
 }
 
+#endif
+#if SDFR_IN_PART(1)
 int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                          const float* quat, const float* inv_scale, int batch, int W, int H,
                          float cx, float cy, float fx, float fy, float threshold,
                          const float* depth_obs, long long obs_stride, float* depth,
-                         float* loss_sum, float* n_overlap, unsigned flags, void* stream) {
+                         float* loss_sum, float* n_overlap, unsigned flags,
+                         const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (flags & ~SDFR_ZERO_GRADS) return fail(SDFR_E_FLAGS, "unknown flag bits");
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
@@ -1195,7 +1368,7 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layo
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           threshold, depth);
+                           threshold, depth, bounds);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
   P.loss_sum = loss_sum;
@@ -1203,12 +1376,15 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layo
   return launch_forward<1, false>(P, batch, s);
 }
 
+#endif
+#if SDFR_IN_PART(3)
 int sdfr_compare_backward(const float* depth, const float* depth_obs, long long obs_stride,
                           const float* n_overlap, const float* upstream, const float* sdf, int R,
                           long long sdf_stride, int layout, const float* pos, const float* quat,
                           const float* inv_scale, int batch, int W, int H, float cx, float cy,
                           float fx, float fy, float* gs, long long gs_stride, float* gp,
-                          float* gq, float* gi, unsigned flags, void* stream) {
+                          float* gq, float* gi, unsigned flags, const sdfr_cell_bounds* bounds,
+                          void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
@@ -1222,7 +1398,7 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   if (!depth || !depth_obs || !n_overlap)
     return fail(SDFR_E_NULL, "depth, depth_obs or n_overlap is NULL");
   BwdParams P = bwd_params(depth, sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           gs, gs_stride, gp, gq, gi, flags);
+                           gs, gs_stride, gp, gq, gi, flags, bounds);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
   P.n_overlap = n_overlap;
@@ -1230,13 +1406,15 @@ int sdfr_compare_backward(const float* depth, const float* depth_obs, long long 
   return launch_backward<1>(P, batch, (flags & SDFR_ZERO_GRADS) != 0, s);
 }
 
+#endif
+#if SDFR_IN_PART(2)
 static int compare_fused_impl(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                               const float* quat, const float* inv_scale, int batch, int W, int H,
                               float cx, float cy, float fx, float fy, float threshold,
                               const float* depth_obs, long long obs_stride, float* depth,
                               float* loss_sum, float* n_overlap, float rel_threshold, float* n_inlier,
                               float* gs, long long gs_stride, float* gp, float* gq, float* gi,
-                              unsigned flags, void* stream) {
+                              unsigned flags, const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
@@ -1257,7 +1435,7 @@ static int compare_fused_impl(const float* sdf, int R, long long sdf_stride, int
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           threshold, depth);
+                           threshold, depth, bounds);
   P.depth_obs = depth_obs;
   P.obs_stride = obs_stride;
   P.loss_sum = loss_sum;
@@ -1278,10 +1456,11 @@ int sdfr_compare_fused(const float* sdf, int R, long long sdf_stride, int layout
                        float cx, float cy, float fx, float fy, float threshold,
                        const float* depth_obs, long long obs_stride, float* depth,
                        float* loss_sum, float* n_overlap, float* gs, long long gs_stride,
-                       float* gp, float* gq, float* gi, unsigned flags, void* stream) {
+                       float* gp, float* gq, float* gi, unsigned flags,
+                       const sdfr_cell_bounds* bounds, void* stream) {
   return compare_fused_impl(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, cx, cy, fx, fy,
                             threshold, depth_obs, obs_stride, depth, loss_sum, n_overlap, 0.0f, nullptr,
-                            gs, gs_stride, gp, gq, gi, flags, stream);
+                            gs, gs_stride, gp, gq, gi, flags, bounds, stream);
 }
 
 int sdfr_compare_fused_inliers(const float* sdf, int R, long long sdf_stride, int layout,
@@ -1290,16 +1469,18 @@ int sdfr_compare_fused_inliers(const float* sdf, int R, long long sdf_stride, in
                                const float* depth_obs, long long obs_stride, float* depth,
                                float* loss_sum, float* n_overlap, float rel_threshold, float* n_inlier,
                                float* gs, long long gs_stride, float* gp, float* gq, float* gi,
-                               unsigned flags, void* stream) {
+                               unsigned flags, const sdfr_cell_bounds* bounds, void* stream) {
   if (batch > 0 && !n_inlier) return fail(SDFR_E_NULL, "n_inlier is NULL");
   if (!(rel_threshold <= 1.0f))
     return fail(SDFR_E_SHAPE, "fused inlier count: rel_threshold <= 1 expected (a missed pixel has "
                               "relative error 1; use sdfr_inlier_count for larger thresholds)");
   return compare_fused_impl(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, cx, cy, fx, fy,
                             threshold, depth_obs, obs_stride, depth, loss_sum, n_overlap, rel_threshold,
-                            n_inlier, gs, gs_stride, gp, gq, gi, flags, stream);
+                            n_inlier, gs, gs_stride, gp, gq, gi, flags, bounds, stream);
 }
 
+#endif
+#if SDFR_IN_PART(3)
 int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int batch, float* gs,
                      long long gs_stride, float* gp, float* gq, float* gi, unsigned flags,
                      void* stream) {
@@ -1322,17 +1503,22 @@ int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int b
   return check_launch("sdfr_scale_grads_kernel");
 }
 
+#endif
+#if SDFR_IN_PART(3)
 int sdfr_forward_composite(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                            const float* quat, const float* inv_scale, int n_objects, int W,
                            int H, float cx, float cy, float fx, float fy, float threshold,
-                           float* depth, int* winner, void* stream) {
+                           float* depth, int* winner, const sdfr_cell_bounds* bounds, void* stream) {
   if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, n_objects, W, H)) return rc;
   if (W == 0 || H == 0) return 0;
   if (!depth || !winner) return fail(SDFR_E_NULL, "depth or winner is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,
-                           threshold, depth);
-  sdfr_forward_composite_kernel<<<tile_grid(W, H, 1), kThreads, 0, (cudaStream_t)stream>>>(
-      P, n_objects, winner);
+                           threshold, depth, bounds);
+  const bool skewed = P.grid.py != P.grid.R;
+#define SDFR_CALL(RT, LT) \
+  sdfr_forward_composite_kernel<RT, LT><<<tile_grid(W, H, 1), kThreads, 0, (cudaStream_t)stream>>>(P, n_objects, winner)
+  SDFR_DISPATCH_RT_LT(R, skewed, SDFR_CALL);
+#undef SDFR_CALL
   return check_launch("sdfr_forward_composite_kernel");
 }
 
@@ -1360,13 +1546,44 @@ int sdfr_backward_composite(const float* grad_depth, const float* depth, const i
       (flags & (SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE)) != 0;
   if (!want_sdf && !want_pose) return 0;
   const dim3 grid = tile_grid(W, H, 1);
-  if (want_sdf && want_pose)
-    sdfr_backward_composite_kernel<true, true><<<grid, kThreads, 0, s>>>(P);
-  else if (want_sdf)
-    sdfr_backward_composite_kernel<true, false><<<grid, kThreads, 0, s>>>(P);
-  else
-    sdfr_backward_composite_kernel<false, true><<<grid, kThreads, 0, s>>>(P);
+  const bool skewed = P.grid.py != P.grid.R;
+#define SDFR_CALL(RT, LT)                                                                         \
+  do {                                                                                            \
+    if (want_sdf && want_pose) sdfr_backward_composite_kernel<RT, LT, true, true><<<grid, kThreads, 0, s>>>(P);  \
+    else if (want_sdf) sdfr_backward_composite_kernel<RT, LT, true, false><<<grid, kThreads, 0, s>>>(P);         \
+    else sdfr_backward_composite_kernel<RT, LT, false, true><<<grid, kThreads, 0, s>>>(P);                       \
+  } while (0)
+  SDFR_DISPATCH_RT_LT(R, skewed, SDFR_CALL);
+#undef SDFR_CALL
   return check_launch("sdfr_backward_composite_kernel");
+}
+
+int sdfr_grid_bounds(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
+                     const float* inv_scale, int batch, float threshold, sdfr_cell_bounds* bounds,
+                     void* stream) {
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED) return fail(SDFR_E_FLAGS, "unknown sdf_layout");
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (batch < 0 || sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative batch or sdf_stride");
+  if (!(threshold >= 0.0f)) return fail(SDFR_E_SHAPE, "threshold must be >= 0");
+  if (batch == 0) return 0;
+  if (!sdf || !pos || !inv_scale || !bounds) return fail(SDFR_E_NULL, "grid bounds: NULL pointer");
+  const int n_grids = sdf_stride == 0 ? 1 : batch;
+  const Grid G = make_grid(R, layout);
+  cudaStream_t s = (cudaStream_t)stream;
+  CellBounds* out = reinterpret_cast<CellBounds*>(bounds);
+  sdfr_bounds_init_kernel<<<n_grids, n_grids == 1 ? 256 : 32, 0, s>>>(pos, inv_scale, batch, n_grids, threshold, out);
+  /* cell rows per tile: the (rows + 1) x R plane must fit 32 KB of shared memory */
+  int tile_rows = (32 * 1024 / (int)sizeof(float)) / R - 1;
+  if (tile_rows > R - 1) tile_rows = R - 1;
+  if (tile_rows < 1) tile_rows = 1;
+  const int n_tiles = (R - 1 + tile_rows - 1) / tile_rows;
+  const size_t smem = (size_t)(tile_rows + 1) * R * sizeof(float);
+  for (int z0 = 0; z0 < n_grids; z0 += 65535) {
+    const int nz = n_grids - z0 < 65535 ? n_grids - z0 : 65535;
+    sdfr_bounds_scan_kernel<<<dim3(R - 1, n_tiles, nz), 256, smem, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride,
+                                                                      R, G.py, G.px, tile_rows, out + z0);
+  }
+  return check_launch("sdfr_bounds_scan_kernel");
 }
 
 int sdfr_skewed_pitches(int R, int* pitch_y, int* pitch_x, long long* elems) {
@@ -1398,6 +1615,8 @@ int sdfr_skew_grids(const float* sdf, int R, long long sdf_stride, int batch, fl
   return check_launch("sdfr_skew_kernel");
 }
 
+#endif
+#if SDFR_IN_PART(4)
 int sdfr_point_loss_forward(const float* points, long long points_stride, int n_points,
                             const float* sdf, int R, long long sdf_stride, int layout,
                             const float* pos, const float* quat, const float* scale, int batch,
@@ -1641,6 +1860,8 @@ int sdfr_upsample3d_backward(const float* grad_y, int n_volumes, int in_size, in
   return launch_tail_backward(P, n_volumes, (cudaStream_t)stream);
 }
 
+#endif
+#if SDFR_IN_PART(4)
 static int conv3_check(int batch, int ci, int co, int in_size, int k) {
   if (k != 3) return fail(SDFR_E_SHAPE, "conv3d: only kernel_size 3 is implemented (every reference decoder trunk uses 3)");
   if (batch < 0 || ci < 1 || ci > 4096 || co < 1 || co > 4096)
@@ -1680,4 +1901,5 @@ int sdfr_conv3d_backward_data(const float* grad_y, const float* y, int batch, in
   return launch_conv3<true>(P, in_channels, batch, (cudaStream_t)stream);
 }
 
+#endif
 }  // extern "C"

@@ -7,6 +7,8 @@ from .sdf_renderer import (  # noqa: F401
     Camera,
     SDFRendererFunctionGPU,
     forward_stats,
+    get_empty_space_policy,
+    grid_bounds,
     get_sdf_grad_mode,
     get_sdf_layout_policy,
     render_and_compare,
@@ -14,6 +16,7 @@ from .sdf_renderer import (  # noqa: F401
     render_depth_batched,
     render_depth_composite,
     render_depth_gpu,
+    set_empty_space_policy,
     set_sdf_grad_mode,
     set_sdf_layout_policy,
 )

@@ -92,6 +92,53 @@ def _grid_operand(sdf: torch.Tensor, R: int, stride: int, n_render: int, pixels:
     return skewed, (0 if stride == 0 else elems), _lib.LAYOUT_SKEWED
 
 
+_EMPTY_SPACE_POLICIES = ("auto", "on", "off")
+_empty_space_policy = "auto"
+
+
+def set_empty_space_policy(policy: str) -> None:
+    """Whether renders first bound the part of each grid where a hit is possible at all.
+
+    The reference marches every ray that enters the grid's [-1,1]^3 box (sdf_renderer_cuda.cu:
+    272-293); most of them cross only space where the field stays above the hit threshold.
+    ``sdfr_grid_bounds`` (one read of the grids) finds the box of cells where the march can terminate;
+    rays that miss it are written as 0 without marching, every other ray is marched exactly as before --
+    identical images and gradients.  ``"auto"`` (default): when the rendering work outweighs the pass;
+    ``"on"`` / ``"off"``: always / never.
+    """
+    global _empty_space_policy
+    if policy not in _EMPTY_SPACE_POLICIES:
+        raise ValueError(f"empty-space policy must be one of {_EMPTY_SPACE_POLICIES}")
+    _empty_space_policy = policy
+
+
+def get_empty_space_policy() -> str:
+    return _empty_space_policy
+
+
+def grid_bounds(src: torch.Tensor, R: int, src_stride: int, layout: int, position: torch.Tensor,
+                inv_scale: torch.Tensor, threshold: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Cell bounds (``sdfr_cell_bounds`` records, int32 ``(n_grids, 8)``) of the grid operand ``src``
+    (as ``_grid_operand`` returns it) for a render of ``position`` / ``inv_scale`` at ``threshold``."""
+    B = int(inv_scale.numel())
+    n_grids = 1 if src_stride == 0 else B
+    if out is None:
+        out = torch.empty((n_grids, 8), dtype=torch.int32, device=src.device)
+    _lib.check(_lib.lib().sdfr_grid_bounds(src.data_ptr(), R, src_stride, layout, position.data_ptr(),
+                                           inv_scale.data_ptr(), B, float(threshold), out.data_ptr(),
+                                           _stream()), "sdfr_grid_bounds")
+    return out
+
+
+def _bounds_operand(src, R, src_stride, layout, position, inv_scale, threshold, n_render, pixels):
+    """Bounds tensor for a render of ``n_render`` images of ``pixels`` pixels, or None (policy)."""
+    n_grids = 1 if src_stride == 0 else n_render
+    policy = _empty_space_policy
+    if policy == "off" or (policy == "auto" and n_render * pixels < 2 * n_grids * R ** 3):
+        return None
+    return grid_bounds(src, R, src_stride, layout, position, inv_scale, threshold)
+
+
 class Camera:
     """Pinhole camera parameters (reference sdf_renderer.py:31-133).
 
@@ -231,7 +278,7 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
             _lib.check(_lib.lib().sdfr_forward(
                 src.data_ptr(), R, 0, layout, position.data_ptr(), orientation.data_ptr(),
                 inv_scale.data_ptr(), 1, W, H, cx, cy, fx, fy, float(threshold),
-                image.data_ptr(), _stream()), "sdfr_forward")
+                image.data_ptr(), None, _stream()), "sdfr_forward")
         ctx.save_for_backward(image, sdf, position, orientation, inv_scale)
         ctx.cam = (W, H, cx, cy, fx, fy)
         ctx.sdf_grad_mode = sdf_grad_mode
@@ -266,7 +313,7 @@ class SDFRendererFunctionGPU(torch.autograd.Function):
                     int(sdf.shape[-1]), 0, _lib.LAYOUT_DENSE, position.data_ptr(),
                     orientation.data_ptr(),
                     inv_scale.data_ptr(), 1, W, H, cx, cy, fx, fy, _ptr(g_sdf), 0, _ptr(g_p),
-                    _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_backward")
+                    _ptr(g_q), _ptr(g_is), flags, None, _stream()), "sdfr_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None
 
 
@@ -340,12 +387,14 @@ class _BatchedRender(torch.autograd.Function):
         with _on_device_of(sdf):
             depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
             src, src_stride, layout = _grid_operand(sdf, R, stride, B, W * H)
+            bounds = _bounds_operand(src, R, src_stride, layout, position, inv_scale, threshold, B, W * H)
             _lib.check(_lib.lib().sdfr_forward(
                 src.data_ptr(), R, src_stride, layout, position.data_ptr(),
                 orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
-                float(threshold), depth.data_ptr(), _stream()), "sdfr_forward")
+                float(threshold), depth.data_ptr(), _ptr(bounds), _stream()), "sdfr_forward")
         ctx.save_for_backward(depth, sdf, position, orientation, inv_scale)
         ctx.meta = (B, R, stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
+        ctx.bounds = bounds  # valid for this depth image: the backward scans a smaller region
         return depth
 
     @staticmethod
@@ -367,7 +416,7 @@ class _BatchedRender(torch.autograd.Function):
                     grad_depth.data_ptr(), depth.data_ptr(), sdf.data_ptr(), R, stride,
                     _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
                     inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, _ptr(g_sdf), stride,
-                    _ptr(g_p), _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_backward")
+                    _ptr(g_p), _ptr(g_q), _ptr(g_is), flags, _ptr(ctx.bounds), _stream()), "sdfr_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None
 
 
@@ -411,6 +460,7 @@ class _RenderAndCompare(torch.autograd.Function):
             sums = torch.empty((2, B), dtype=torch.float32, device=sdf.device)
             lib = _lib.lib()
             src, src_stride, layout = _grid_operand(sdf, R, stride, B, W * H)
+            bounds = _bounds_operand(src, R, src_stride, layout, position, inv_scale, threshold, B, W * H)
             if fused:
                 flags = _grad_flags(needs, sdf_grad_mode) | _lib.ZERO_GRADS
                 grads = [torch.empty_like(t) if n else None
@@ -421,19 +471,20 @@ class _RenderAndCompare(torch.autograd.Function):
                     float(threshold),
                     depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
                     sums[1].data_ptr(), _ptr(grads[0]), stride, _ptr(grads[1]), _ptr(grads[2]),
-                    _ptr(grads[3]), flags, _stream()), "sdfr_compare_fused")
+                    _ptr(grads[3]), flags, _ptr(bounds), _stream()), "sdfr_compare_fused")
             else:
                 _lib.check(lib.sdfr_compare_forward(
                     src.data_ptr(), R, src_stride, layout, position.data_ptr(),
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
                     float(threshold),
                     depth_obs.data_ptr(), obs_stride, depth.data_ptr(), sums[0].data_ptr(),
-                    sums[1].data_ptr(), _lib.ZERO_GRADS, _stream()), "sdfr_compare_forward")
+                    sums[1].data_ptr(), _lib.ZERO_GRADS, _ptr(bounds), _stream()), "sdfr_compare_forward")
             loss = sums[0] / sums[1]  # NaN where nothing overlaps, as torch.mean of an empty set
             n_overlap = sums[1].clone()
         ctx.save_for_backward(depth, depth_obs, sums, sdf, position, orientation, inv_scale)
         ctx.meta = (B, R, stride, obs_stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
         ctx.fused_grads = grads if fused else None
+        ctx.bounds = bounds
         ctx.mark_non_differentiable(depth, n_overlap)
         return loss, depth, n_overlap
 
@@ -466,7 +517,7 @@ class _RenderAndCompare(torch.autograd.Function):
                     position.data_ptr(), orientation.data_ptr(), inv_scale.data_ptr(), B, W, H,
                     cx, cy, fx, fy,
                     _ptr(g_sdf), stride, _ptr(g_p), _ptr(g_q), _ptr(g_is),
-                    flags | _lib.ZERO_GRADS, _stream()), "sdfr_compare_backward")
+                    flags | _lib.ZERO_GRADS, _ptr(ctx.bounds), _stream()), "sdfr_compare_backward")
         return g_sdf, g_p, g_q, g_is, None, None, None, None
 
 
@@ -493,11 +544,13 @@ class _CompositeRender(torch.autograd.Function):
             depth = torch.empty((H, W), dtype=torch.float32, device=sdf.device)
             winner = torch.empty((H, W), dtype=torch.int32, device=sdf.device)
             src, src_stride, layout = _grid_operand(sdf, R, stride, K, W * H // max(K, 1))
+            bounds = _bounds_operand(src, R, src_stride, layout, position, inv_scale, threshold, K,
+                                     W * H // max(K, 1))
             _lib.check(_lib.lib().sdfr_forward_composite(
                 src.data_ptr(), R, src_stride, layout, position.data_ptr(),
                 orientation.data_ptr(), inv_scale.data_ptr(), K, W, H, cx, cy, fx, fy,
                 float(threshold),
-                depth.data_ptr(), winner.data_ptr(), _stream()), "sdfr_forward_composite")
+                depth.data_ptr(), winner.data_ptr(), _ptr(bounds), _stream()), "sdfr_forward_composite")
         ctx.save_for_backward(depth, winner, sdf, position, orientation, inv_scale)
         ctx.meta = (K, R, stride, W, H, cx, cy, fx, fy, sdf_grad_mode)
         ctx.mark_non_differentiable(winner)
@@ -539,20 +592,24 @@ def render_depth_composite(sdf: torch.Tensor, position: torch.Tensor, orientatio
                                   sdf_grad_mode)
 
 
-def forward_stats(sdf, position, orientation, inv_scale, threshold, camera):
+def forward_stats(sdf, position, orientation, inv_scale, threshold, camera, empty_space: bool = False):
     """Work counters of a batched render: dict(samples, box_pixels, hit_pixels, capped_rays).
 
     ``samples`` is the S and ``hit_pixels`` the Hh of the roofline's algorithmic-bytes formula
-    (DESIGN.md); the depth image is rendered as a side effect and discarded.
+    (DESIGN.md); the depth image is rendered as a side effect and discarded.  ``box_pixels`` counts the
+    rays that are marched: all rays entering the grid's box, or -- ``empty_space=True`` -- only those
+    that enter the empty-space bounds of ``sdfr_grid_bounds``.
     """
     B, R, stride = _check_batch(sdf, position, orientation, inv_scale)
     W, H, cx, cy, fx, fy = _camera_params(camera)
     with _on_device_of(sdf):
         depth = torch.empty((B, H, W), dtype=torch.float32, device=sdf.device)
         stats = torch.zeros(4, dtype=torch.int64, device=sdf.device)
+        bounds = grid_bounds(sdf, R, stride, _lib.LAYOUT_DENSE, position, inv_scale, threshold) \
+            if empty_space else None
         _lib.check(_lib.lib().sdfr_forward_stats(
             sdf.data_ptr(), R, stride, _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
             inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, float(threshold), depth.data_ptr(),
-            stats.data_ptr(), _stream()), "sdfr_forward_stats")
+            stats.data_ptr(), _ptr(bounds), _stream()), "sdfr_forward_stats")
         s = stats.tolist()
     return {"samples": s[0], "box_pixels": s[1], "hit_pixels": s[2], "capped_rays": s[3]}

@@ -88,13 +88,13 @@ class _DecodeRenderCompare(torch.autograd.Function):
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
                     float(threshold), depth_obs.data_ptr(), obs_stride, depth.data_ptr(),
                     sums[0].data_ptr(), sums[1].data_ptr(), _ptr(g_sdf), R ** 3, _ptr(g_p), _ptr(g_q),
-                    _ptr(g_is), rflags | _lib.ZERO_GRADS, st), "sdfr_compare_fused")
+                    _ptr(g_is), rflags | _lib.ZERO_GRADS, None, st), "sdfr_compare_fused")
             else:
                 _lib.check(lib.sdfr_compare_forward(
                     grids.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, position.data_ptr(),
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
                     float(threshold), depth_obs.data_ptr(), obs_stride, depth.data_ptr(),
-                    sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, st), "sdfr_compare_forward")
+                    sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, None, st), "sdfr_compare_forward")
             loss_depth = sums[0] / sums[1]  # NaN where nothing overlaps (torch.mean of an empty set)
             loss = float(depth_weight) * torch.nan_to_num(loss_depth, nan=0.0)
             loss_pc = None

@@ -133,7 +133,8 @@ class HypothesisOptimizer:
             raise ValueError("give camera_positions and camera_orientations together")
         multiview = camera_positions is not None
         can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder)) \
-            and not multiview and point_constraint is None
+            and not multiview and point_constraint is None \
+            and (latent is None or int(latent.shape[1]) <= 64)  # sdfr_hypothesis_step: kStepMaxLatent
         # (source (3,), target (3,), weight): simple_setup.py:164-175, 224, 299
         self.point_constraint = None
         if point_constraint is not None:
@@ -146,6 +147,9 @@ class HypothesisOptimizer:
                              "a single view and no point constraint")
         self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
         self.overlap = bool(overlap)
+        # corner weights of the SDF gradient: the module default at construction time
+        from ..differentiable_renderer.sdf_renderer import get_sdf_grad_mode
+        self.sdf_grad_mode = get_sdf_grad_mode()
         self.lrs, self.betas, self.eps = tuple(float(x) for x in lrs), tuple(betas), float(eps)
         self.camera, self.threshold, self.group = camera, float(threshold), group
         self.depth_obs = depth_obs.contiguous()
@@ -222,7 +226,8 @@ class HypothesisOptimizer:
         self._graph = None
         self._shard_sizes = None  # exchanged on the first gather of run()
         if self.optimizer_impl == "fused":
-            self._init_fused()
+            with torch.cuda.device(self.position.device):
+                self._init_fused()
 
     # ------------------------------------------------------------------------------------
     # optimizer="fused": one iteration = a handful of C-ABI launches, no autograd outside the trunk
@@ -292,6 +297,10 @@ class HypothesisOptimizer:
             self._g_both = torch.empty((2 if M else 1, B, R ** 3), dtype=torch.float32, device=dev)
             self._g_sdf = self._g_both[0]
             self._g_sdf_pc = self._g_both[1] if M else None
+        from ..differentiable_renderer.sdf_renderer import get_empty_space_policy
+        n_grids = 1 if self._grid_op[1] == 0 else B
+        self._bounds = None if get_empty_space_policy() == "off" else \
+            torch.empty((n_grids, 8), dtype=torch.int32, device=dev)
         # second stream: the point loss runs beside the render (both only read the grids), the
         # gradient-grid clears beside the decoder trunk; forks and joins are captured by capture()
         self._side = torch.cuda.Stream(dev) if self.overlap else None
@@ -344,6 +353,15 @@ class HypothesisOptimizer:
         flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
         if dec is not None:
             flags |= _lib.GRAD_SDF
+        render_flags = flags | (_lib.SDF_GRAD_EXACT if self.sdf_grad_mode == "exact" else 0)
+        # empty-space bounds of this iteration's grids and poses (the hit-threshold bound depends on
+        # position and scale): rays that cannot hit anything are not marched, all others unchanged
+        bounds = None
+        if self._bounds is not None:
+            _lib.check(lib.sdfr_grid_bounds(
+                grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._inv_scale.data_ptr(), B,
+                self.threshold, self._bounds.data_ptr(), _stream()), "sdfr_grid_bounds")
+            bounds = self._bounds.data_ptr()
 
         def point_loss():
             _lib.check(lib.sdfr_point_loss_fused(
@@ -365,16 +383,16 @@ class HypothesisOptimizer:
                 self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
                 b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), self.inlier_threshold,
                 self._inl[0].data_ptr(), _ptr(self._g_sdf), R ** 3,
-                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
-                "sdfr_compare_fused_inliers")
+                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), render_flags, bounds,
+                _stream()), "sdfr_compare_fused_inliers")
         else:
             _lib.check(lib.sdfr_compare_fused(
                 grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._unit_q.data_ptr(),
                 self._inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy, self.threshold,
                 self.depth_obs.data_ptr(), self._obs_stride, self._depth.data_ptr(),
                 b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), _ptr(self._g_sdf), R ** 3,
-                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), flags, _stream()),
-                "sdfr_compare_fused")
+                b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), render_flags, bounds,
+                _stream()), "sdfr_compare_fused")
         if M and side is not None:
             main.wait_stream(side)
         if self.inlier_threshold is not None and not inl_fused:
@@ -430,12 +448,13 @@ class HypothesisOptimizer:
         grids4 = grids if grids.dim() == 4 else grids[None]
         position_c, orientation_c = views.to_camera_frames(self.position, q, *self._views)
         inv_scale = (1.0 / self.scale).contiguous()
-        loss, depth = 0.0, None
+        loss, depth, no_overlap = 0.0, None, None
         for v in range(self.depth_obs.shape[0]):
             p_v, q_v = position_c[v].contiguous(), orientation_c[v].contiguous()
             loss_depth, depth, _ = render_and_compare(grids, p_v, q_v, inv_scale, self.depth_obs[v],
                                                       self.threshold, self.camera)
             loss = loss + self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
+            no_overlap = torch.isnan(loss_depth) if no_overlap is None else (no_overlap | torch.isnan(loss_depth))
             if self.pc_weight and self._view_points[v].shape[0] > 0:
                 loss = loss + self.pc_weight * losses.point_loss(self._view_points[v], p_v, q_v,
                                                                  self.scale, grids4)
@@ -447,7 +466,7 @@ class HypothesisOptimizer:
             self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if self.inlier_threshold is not None:
             self._track_best_torch(depth, self.depth_obs[-1])
-        self.last_losses = loss.detach()
+        self.last_losses = self._reported(loss, no_overlap)
         return self.last_losses
 
     def _track_best_torch(self, depth: torch.Tensor, obs: Optional[torch.Tensor] = None) -> None:
@@ -498,6 +517,10 @@ class HypothesisOptimizer:
         default stream (sdf_renderer_cuda.cu:495)."""
         if not self.position.is_cuda:
             raise RuntimeError("CUDA graphs need CUDA tensors")
+        with torch.cuda.device(self.position.device):
+            self._capture(warmup)
+
+    def _capture(self, warmup: int) -> None:
         side = torch.cuda.Stream(self.position.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -524,23 +547,26 @@ class HypothesisOptimizer:
         (estimation/fused.py): no dense grid, no separate layout / scaling / add passes."""
         dec = self.decoder
         w, b = dec.tail_parameters()
-        loss, depth, _, _ = decode_render_compare(
+        loss, depth, _, loss_depth = decode_render_compare(
             dec.trunk(self.latent), w, b, self.position, q.contiguous(), self.scale,
             self.depth_obs, self.points if self.pc_weight and self.points.shape[0] > 0 else None,
             dec.volume_size, self.threshold, self.camera, base=dec.base,
             depth_weight=self.depth_weight, pc_weight=self.pc_weight)
-        return loss, depth
+        return loss, depth, torch.isnan(loss_depth)
 
     def _eager_step(self) -> torch.Tensor:
         if self.optimizer_impl == "fused":
-            return self._fused_iteration()
+            # the C ABI launches on the CURRENT device's stream: make the tensors' device current
+            # (OptionalCUDAGuard of sdf_renderer.cpp:58, 82)
+            with torch.cuda.device(self.position.device):
+                return self._fused_iteration()
         if self._views is not None:
             return self._multiview_step()
         self.optimizer.zero_grad(set_to_none=True)
         q = self.orientation / torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if isinstance(self.decoder, FusedTailDecoder) and self.position.is_cuda \
                 and self.point_counts is None:  # the chained operator takes one shared cloud
-            loss, depth = self._fused_loss(q)
+            loss, depth, no_overlap = self._fused_loss(q)
             if self.point_constraint is not None:
                 loss = loss + self._constraint_loss()
             loss.sum().backward()
@@ -549,12 +575,13 @@ class HypothesisOptimizer:
                 self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
             if self.inlier_threshold is not None:
                 self._track_best_torch(depth)
-            self.last_losses = loss.detach()
+            self.last_losses = self._reported(loss, no_overlap)
             return self.last_losses
         grids = self._grids()
         loss_depth, depth, _ = render_and_compare(grids, self.position, q.contiguous(),
                                               (1.0 / self.scale).contiguous(), self.depth_obs,
                                               self.threshold, self.camera)
+        no_overlap = torch.isnan(loss_depth)
         loss = self.depth_weight * torch.nan_to_num(loss_depth, nan=0.0)
         if self.pc_weight and self.points.shape[-2] > 0:
             # NB: the reference passes the un-normalised quaternion and lets pc_loss normalise it
@@ -574,8 +601,19 @@ class HypothesisOptimizer:
             self.orientation /= torch.linalg.norm(self.orientation, dim=1, keepdim=True)
         if self.inlier_threshold is not None:
             self._track_best_torch(depth)
-        self.last_losses = loss.detach()
+        self.last_losses = self._reported(loss, no_overlap)
         return self.last_losses
+
+    @staticmethod
+    def _reported(loss: torch.Tensor, no_overlap: Optional[torch.Tensor]) -> torch.Tensor:
+        """The loss a caller sees: NaN where the rendered and the observed depth do not overlap -- the
+        reference's mean over an empty selection (simple_setup.py:131).  The optimised loss uses 0
+        there (zero gradients instead of the reference's NaN gradients), but a hypothesis that left the
+        frustum must never rank best: ``global_best`` and ``SDFPipeline`` map NaN to +inf."""
+        loss = loss.detach()
+        if no_overlap is None:
+            return loss
+        return torch.where(no_overlap, torch.full_like(loss, float("nan")), loss)
 
     def run(self, iterations: int, gather_every: int = 0):
         """`iterations` steps; with gather_every=k the losses of all ranks are all-gathered every

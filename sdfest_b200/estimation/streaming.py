@@ -106,7 +106,7 @@ class StreamedRenderCompare:
                     self.W, self.H, self.cx, self.cy, self.fx, self.fy, self.threshold,
                     self.d_obs.data_ptr(), 0, self.depth.data_ptr() + b0 * self.H * self.W * f4,
                     self.sums[0].data_ptr() + b0 * f4, self.sums[1].data_ptr() + b0 * f4, *grads,
-                    self.flags, st), "sdfr_compare_fused")
+                    self.flags, None, st), "sdfr_compare_fused")
                 _lib.check(lib.sdfr_scale_grads(
                     self.sums[1].data_ptr() + b0 * f4, None, R, n, *grads, _lib.GRAD_ALL, st),
                     "sdfr_scale_grads")

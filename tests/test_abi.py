@@ -59,19 +59,24 @@ def test_flag_values_match_header():
 def test_argument_errors_need_no_gpu(lib):
     cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
     # empty batch / empty image: success, nothing launched
-    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 0, *cam, 0.01, None, None) == 0
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 0, *cam, 0.01, None, None, None) == 0
     assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 1, 0, 8, 4.0, 4.0, 4.0, 4.0, 0.01,
-                            None, None) == 0
+                            None, None, None) == 0
     # NULL inputs
-    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 1, *cam, 0.01, None, None) == -1
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, 1, *cam, 0.01, None, None, None) == -1
     assert b"NULL" in lib.sdfr_last_error()
     # bad resolution / negative sizes
-    assert lib.sdfr_forward(None, 1, 0, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
-    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, -1, *cam, 0.01, None, None) == -2
-    assert lib.sdfr_forward(None, 4, -5, 0, None, None, None, 1, *cam, 0.01, None, None) == -2
+    assert lib.sdfr_forward(None, 1, 0, 0, None, None, None, 1, *cam, 0.01, None, None, None) == -2
+    assert lib.sdfr_forward(None, 4, 0, 0, None, None, None, -1, *cam, 0.01, None, None, None) == -2
+    assert lib.sdfr_forward(None, 4, -5, 0, None, None, None, 1, *cam, 0.01, None, None, None) == -2
     # unknown flags in backward
     assert lib.sdfr_backward(None, None, None, 4, 0, 0, None, None, None, 0, *cam, None, 0, None,
-                             None, None, 0x8000, None) == -3
+                             None, None, 0x8000, None, None) == -3
+    # grid bounds: empty batch is a no-op, NULL pointers and bad sizes are argument errors
+    assert lib.sdfr_grid_bounds(None, 64, 0, 0, None, None, 0, 0.005, None, None) == 0
+    assert lib.sdfr_grid_bounds(None, 64, 0, 0, None, None, 1, 0.005, None, None) == -1
+    assert lib.sdfr_grid_bounds(None, 1, 0, 0, None, None, 1, 0.005, None, None) == -2
+    assert lib.sdfr_grid_bounds(None, 64, 0, 0, None, None, 1, -1.0, None, None) == -2
     with pytest.raises(RuntimeError, match="argument error"):
         _lib.check(-1, "sdfr_forward")
 
@@ -94,7 +99,7 @@ def test_skewed_layout_geometry():
     assert lib.sdfr_skew_grids(None, 64, 0, 1, None, 0, None) == -1
     # unknown layout id
     cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
-    assert lib.sdfr_forward(None, 4, 0, 7, None, None, None, 1, *cam, 0.01, None, None) == -3
+    assert lib.sdfr_forward(None, 4, 0, 7, None, None, None, 1, *cam, 0.01, None, None, None) == -3
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

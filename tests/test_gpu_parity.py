@@ -392,7 +392,7 @@ def test_depth_buffer_is_fully_written(cuda_device):
     out = torch.full((H, W), float("nan"), device=cuda_device)
     _lib.check(lib.sdfr_forward(sdf.data_ptr(), 16, 0, 0, p.data_ptr(), q.data_ptr(), s.data_ptr(), 1,
                                 W, H, cam["cx"], cam["cy"], cam["fx"], cam["fy"], 0.005,
-                                out.data_ptr(), torch.cuda.current_stream().cuda_stream), "fwd")
+                                out.data_ptr(), None, torch.cuda.current_stream().cuda_stream), "fwd")
     assert not torch.isnan(out).any() and (out > 0).any() and (out == 0).any()
 
 
@@ -446,7 +446,7 @@ def test_non_default_stream_and_graph_capture(cuda_device):
     with torch.cuda.graph(graph):
         _lib.check(lib.sdfr_forward(a[0].data_ptr(), 64, 0, 0, a[1].data_ptr(), a[2].data_ptr(),
                                     a[3].data_ptr(), B, W, H, cp["cx"], cp["cy"], cp["fx"],
-                                    cp["fy"], thr, out.data_ptr(),
+                                    cp["fy"], thr, out.data_ptr(), None,
                                     torch.cuda.current_stream().cuda_stream), "captured forward")
     out.zero_()
     graph.replay()

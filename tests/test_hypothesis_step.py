@@ -86,10 +86,12 @@ def test_oracle_matches_torch_adam(L, with_points):
     np.testing.assert_allclose(np.linalg.norm(unit, axis=1), 1.0, atol=1e-14)
     np.testing.assert_allclose(inv, 1.0 / st["scale"])
     n = case["n_overlap"]
-    exp = np.where(n > 0, case["loss_sum"] / np.where(n > 0, n, 1), 0.0)
+    # no overlap: NaN like the reference's mean over an empty selection (simple_setup.py:131)
+    exp = np.where(n > 0, case["loss_sum"] / np.where(n > 0, n, 1), np.nan)
     if with_points:
         exp = exp + 0.01 * case["point_sum"]
-    np.testing.assert_allclose(loss, exp)
+    assert np.isnan(exp).any() and not np.isnan(exp).all()
+    np.testing.assert_allclose(loss, exp, equal_nan=True)
 
 
 # ------------------------------------------------------------------------------------------
@@ -133,7 +135,7 @@ def test_step_kernel_matches_oracle(cuda_device, B, L, with_points):
             np.testing.assert_allclose(got.cpu().numpy(), st[name], rtol=2e-5, atol=2e-6, err_msg=name)
     np.testing.assert_allclose(unit.cpu().numpy(), unit_o, rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(inv.cpu().numpy(), inv_o, rtol=2e-5)
-    np.testing.assert_allclose(loss.cpu().numpy(), loss_o, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(loss.cpu().numpy(), loss_o, rtol=1e-5, atol=1e-6, equal_nan=True)
     np.testing.assert_allclose(m.cpu().numpy(), st["m"], rtol=1e-4, atol=1e-6)
 
     # NO_UPDATE leaves parameters and state alone; CLEAR_INPUTS zeroes what was consumed
@@ -586,7 +588,7 @@ def test_compare_fused_inliers_counts_in_the_same_traversal(cuda_device, per_hyp
         head = (grids.data_ptr(), R, gstride, layout, opt.position.data_ptr(), opt._unit_q.data_ptr(),
                 opt._inv_scale.data_ptr(), B, W, H, W / 2, H / 2, W / 2, W / 2, opt.threshold, obs.data_ptr(),
                 H * W if per_hypothesis_obs else 0, depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr())
-        tail = (None, 0, gp.data_ptr(), gq.data_ptr(), gi.data_ptr(), flags, None)
+        tail = (None, 0, gp.data_ptr(), gq.data_ptr(), gi.data_ptr(), flags, None, None)  # ..., bounds, stream
         if name == "plain":
             _lib.check(lib.sdfr_compare_fused(*head, *tail), name)
         else:
@@ -607,8 +609,8 @@ def test_compare_fused_inliers_counts_in_the_same_traversal(cuda_device, per_hyp
     want = [hs.inlier_counts(o[b] if per_hypothesis_obs else o, d[b], thr)[0] for b in range(B)]
     assert sums[2].tolist() == want and max(want) > 50
     # thresholds above 1 would have to count missed pixels: rejected
-    assert lib.sdfr_compare_fused_inliers(*head, 1.5, sums[2].data_ptr(), *tail) == -2
-    assert lib.sdfr_compare_fused_inliers(*head, thr, None, *tail) == -1
+    assert lib.sdfr_compare_fused_inliers(*head, 1.5, sums[2].data_ptr(), None, *tail) == -2
+    assert lib.sdfr_compare_fused_inliers(*head, thr, None, None, *tail) == -1
 
 
 @pytest.mark.gpu

@@ -122,3 +122,47 @@ def grad_close(a, b, rtol=1e-3, what=""):
     err = np.abs(a - b).max() / scale
     assert err <= rtol, f"{what}: max err {err:.3e} relative to max|ref|={scale:.3e}"
     return err
+
+
+def sdf_grad_parity(a, b, rtol=1e-3, pixel_bound=None, max_flip_pixels=4, what=""):
+    """SDF-gradient gate.  |a-b| <= rtol * max|b| for all voxels, EXCEPT the voxels of at most
+    `max_flip_pixels` hit pixels whose cell lookup flipped: the backward re-derives the hit point from the
+    stored depth and floors it to a cell (sdf_renderer_cuda.cu:336-354); a coordinate within an ulp of a
+    cell face lands in either cell depending on how the compiler contracts `o + t*d` into an fma, and the
+    reference's weight list (cu:373-388) is not continuous across cell faces, so such a pixel moves its
+    whole contribution (8 + 8 voxels).  Each outlier is bounded by one pixel's contribution `pixel_bound`
+    (max |grad_depth| * scale).  Returns (max relative error of the inliers, number of outlier voxels)."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    scale = max(np.abs(b).max(), 1e-30)
+    err = np.abs(a - b)
+    bad = err > rtol * scale
+    n_bad = int(bad.sum())
+    assert n_bad <= 16 * max_flip_pixels, f"{what}: {n_bad} voxels off by more than {rtol} of max|ref|={scale:.3e}"
+    if n_bad:
+        bound = pixel_bound if pixel_bound is not None else 0.2 * scale
+        assert err[bad].max() <= 1.001 * bound, f"{what}: outlier {err[bad].max():.3e} exceeds one pixel's contribution {bound:.3e}"
+    return float(err[~bad].max() / scale), n_bad
+
+
+def pose_grad_parity(got, bw, g, rtol=1e-3, what=""):
+    """Pose-gradient gate against an oracle backward `bw` run with want_deriv=True and upstream image
+    `g`: per parameter group (position, orientation, inv_scale)
+        |got - ref| <= rtol * max|ref| + 16 eps * max_i sum_pixels |g * d depth / d theta_i|,
+    eps = 2^-24.  The second term is the forward error bound of ANY fp32 evaluation of these sums: when a
+    gradient (nearly) cancels over the pixels -- the orientation gradient of a rotationally symmetric
+    shape -- the reference's own atomics do not reproduce it to rtol of its tiny maximum either.
+    `got` = (position (3,), orientation (4,), inv_scale scalar).  Returns the largest error relative to
+    the tolerance's first term (so <= 1 means "inside rtol alone")."""
+    ref = (np.asarray(bw["g_position"], np.float64), np.asarray(bw["g_orientation"], np.float64),
+           np.asarray([bw["g_inv_scale"]], np.float64))
+    absum = np.abs(np.asarray(g, np.float64)[None] * np.asarray(bw["deriv"], np.float64)).sum((1, 2))
+    worst = 0.0
+    for a, b, sl, nm in zip(got, ref, (slice(0, 3), slice(3, 7), slice(7, 8)), ("position", "orientation", "inv_scale")):
+        a = np.asarray(a, np.float64).reshape(-1)
+        scale = max(np.abs(b).max(), 1e-30)
+        err = np.abs(a - b).max()
+        tol = rtol * scale + 16 * 2.0 ** -24 * absum[sl].max()
+        assert err <= tol, f"{what} {nm}: err {err:.3e} > {tol:.3e} (max|ref| {scale:.3e}, abs-sum {absum[sl].max():.3e})"
+        worst = max(worst, err / (rtol * scale))
+    return worst
