@@ -305,6 +305,12 @@ def main():
                                         inv_s.data_ptr(), B, THRESHOLD, bounds.data_ptr(), stream),
                    "sdfr_grid_bounds")
 
+    def skew_bound():
+        # layout pass and bounds pass as ONE read of the dense grids (sdfr_skew_grids_bounds)
+        _lib.check(lib.sdfr_skew_grids_bounds(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, pos.data_ptr(),
+                                              inv_s.data_ptr(), THRESHOLD, bounds.data_ptr(), stream),
+                   "sdfr_skew_grids_bounds")
+
     def fwd():
         _lib.check(lib.sdfr_compare_forward(
             skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
@@ -336,8 +342,7 @@ def main():
     def step():
         # layout pass, then forward render + masked-L1 compare + backward in ONE traversal, then
         # the deferred per-hypothesis normalisation of the gradients
-        skew()
-        bound()
+        skew_bound()
         fused()
         scale()
         if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
@@ -387,6 +392,7 @@ def main():
     fused_ms = timed(fused, K, 2) / K
     fused_nobounds_ms = timed(lambda: fused(False, False), K, 2) / K
     bound_ms = timed(bound, K, 2) / K
+    skew_bound_ms = timed(skew_bound, K, 2) / K
     fused_dense_ms = timed(lambda: fused(True), K, 2) / K
     skew_ms = timed(skew, K, 2) / K
     scale_ms = timed(scale, K, 2) / K
@@ -529,6 +535,8 @@ def main():
                                                 "GBps": fused_bytes / fused_dense_ms / 1e6},
             "fused_without_empty_space_bounds": {"ms": fused_nobounds_ms},
             "grid_bounds": {"ms": bound_ms, "bytes": 4 * SK * B, "GBps": 4 * SK * B / bound_ms / 1e6},
+            "skew_grids_bounds": {"ms": skew_bound_ms, "bytes": 4 * (RRR + SK) * B,
+                                  "GBps": 4 * (RRR + SK) * B / skew_bound_ms / 1e6},
             "skew_grids": {"ms": skew_ms, "bytes": 4 * (RRR + SK) * B, "GBps": 4 * (RRR + SK) * B / skew_ms / 1e6},
             "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
             "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
@@ -558,7 +566,7 @@ def main():
                 "ms_per_step_cuda_graph": (e2e_graph_s / Ke * 1e3) if e2e_graph_s else e2e_check_g,
                 "d2h": "loss, n_overlap, 8 pose gradients per hypothesis; SDF gradients stay on the device",
                 "checksum": e2e_check},
-        "gpu_launches": 6 * K,  # skew + bounds init + bounds scan + pose-zero + fused + scale kernels per step
+        "gpu_launches": 5 * K,  # bounds init + skew/bounds scan + pose-zero + fused + scale kernels per step
         "clocks": clocks.summary(),
         "lib": lib.sdfr_build_info().decode(),
     }

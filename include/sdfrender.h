@@ -130,6 +130,16 @@ int sdfr_grid_bounds(const float* sdf, int resolution, long long sdf_stride, int
                      sdfr_cell_bounds* bounds, void* stream);
 
 /*
+ * sdfr_skew_grids and sdfr_grid_bounds in ONE read of the dense grids: writes the skewed copies and
+ * their cell bounds (for renders that read the skewed copies).  With sdf_stride == 0 one shared grid is
+ * copied once and gets one bounds entry valid for all `batch` hypotheses.
+ */
+int sdfr_skew_grids_bounds(const float* sdf, int resolution, long long sdf_stride, int batch,
+                           float* skewed, long long skewed_stride, const float* position,
+                           const float* inv_scale, float threshold, sdfr_cell_bounds* bounds,
+                           void* stream);
+
+/*
  * Forward: replaces sdf_renderer_cpp.forward (sdf_renderer.cpp:42-61 ->
  * sdf_renderer_cuda.cu:472-510 -> forward kernel :241-298), batched over `batch` hypotheses.
  */

@@ -108,6 +108,15 @@ skewed = torch.empty(B, SK, device=dev)
 lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, st)
 
 
+bounds = torch.empty(B, 8, dtype=torch.int32, device=dev)
+lib.sdfr_grid_bounds(skewed.data_ptr(), R, SK, 1, pos.data_ptr(), inv_s.data_ptr(), B, THR, bounds.data_ptr(), st)
+USE_BOUNDS = [True]
+
+
+def bptr():
+    return bounds.data_ptr() if USE_BOUNDS[0] else None
+
+
 def src(layout):
     return (skewed.data_ptr(), SK, 1) if layout else (grids.data_ptr(), RRR, 0)
 
@@ -117,7 +126,7 @@ def fwd(layout=1):
     lib.sdfr_compare_forward(ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                              inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
                              obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
-                             sums[1].data_ptr(), _lib.ZERO_GRADS, None, st)
+                             sums[1].data_ptr(), _lib.ZERO_GRADS, bptr(), st)
 
 
 def fused(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
@@ -126,7 +135,7 @@ def fused(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
                            inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0, THR,
                            obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(),
                            sums[1].data_ptr(), g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
-                           g_quat.data_ptr(), g_is.data_ptr(), flags, None, st)
+                           g_quat.data_ptr(), g_is.data_ptr(), flags, bptr(), st)
 
 
 def bwd(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
@@ -135,7 +144,7 @@ def bwd(layout=1, flags=_lib.GRAD_ALL | _lib.ZERO_GRADS):
                               ptr, R, stride, lt, pos.data_ptr(), quat.data_ptr(),
                               inv_s.data_ptr(), B, W, H, 320.0, 240.0, 320.0, 320.0,
                               g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
-                              g_is.data_ptr(), flags, None, st)
+                              g_is.data_ptr(), flags, bptr(), st)
 
 
 fwd()

@@ -336,58 +336,48 @@ __device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const G
 
 /* Pose gradients of a CTA.  Every thread keeps its 13 moment sums (sdfr_core.cuh:
  * pixel_backward_moments) in SHARED memory, acc_s[i][thread] -- 13 registers that would otherwise be
- * live across the whole march loop (they were the fused kernel's spill) -- and in DOUBLE: the products
- * are fp32, the running sums are not, so a gradient that nearly cancels over the pixels (a rotationally
- * symmetric shape's orientation gradient) keeps the digits the per-pixel formulation has.  A hit pixel
- * costs 13 conflict-free read-modify-writes.  At the end: warp shuffle -> warp 0 applies the 13 -> 8 map
- * of the hypothesis once -> 8 atomics per CTA (the reference issues 8 same-address atomics per hit
- * pixel, cu:459-466).  Contains two barriers: call from uniform control flow. */
-typedef double MomentAcc[kMoments][kThreads];
+ * live across the whole march loop (they were the fused kernel's spill).  A hit pixel costs 13
+ * conflict-free read-modify-writes.  At the end: warp shuffle -> warp 0 applies the 13 -> 8 map of the
+ * hypothesis once -> 8 atomics per CTA (the reference issues 8 same-address atomics per hit pixel,
+ * cu:459-466).  Measured and dropped: double-precision per-thread sums (+30 us on the 240 us fused
+ * launch: the B200's DADD / F2F.F64 rate) and a double-precision reduction + map in one thread (+15 us:
+ * a serial chain of ~200 DP operations per CTA); neither moved the error, which is the fp32 rounding of
+ * the per-pixel products.  Contains two barriers: call from uniform control flow. */
+typedef float MomentAcc[kMoments][kThreads];
 
 __device__ __forceinline__ void moments_clear(MomentAcc& acc_s) {
 #pragma unroll
-  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] = 0.0;
+  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] = 0.0f;
 }
 
 __device__ __forceinline__ void moments_add(MomentAcc& acc_s, const float (&m)[kMoments]) {
 #pragma unroll
-  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] += (double)m[i];
-}
-
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
-  return v;
-}
-
-/* The 13 -> 8 map runs once per CTA in one thread; kept out of line so that its double-precision
- * temporaries never compete with the march loop for the kernel's 48 registers. */
-__device__ __noinline__ void pose_from_moments(const Frame* F, const Grid* G, const double* m, int stride,
-                                               float* out) {
-  double mm[kMoments];
-#pragma unroll
-  for (int i = 0; i < kMoments; ++i) mm[i] = m[(size_t)i * stride];
-  moments_to_pose(*F, *G, mm, out);
+  for (int i = 0; i < kMoments; ++i) acc_s[i][threadIdx.x] += m[i];
 }
 
 __device__ __forceinline__ void reduce_pose(MomentAcc& acc_s, const Frame& F, const Grid& G, int b,
                                             float* gp, float* gq, float* gi, unsigned flags) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float totals[kMoments];
   __syncthreads();
-  /* warp w sums moments w, w + 8 over the 256 threads; the totals land in row i, column 0 */
+  /* warp w sums moments w, w + 8 over the 256 threads */
   for (int i = warp; i < kMoments; i += kWarps) {
-    double v = 0.0;
+    float v = 0.0f;
 #pragma unroll
     for (int j = 0; j < kThreads / 32; ++j) v += acc_s[i][lane + 32 * j];
-    v = warp_sum_d(v);
-    if (lane == 0) acc_s[i][0] = v;
+    v = warp_sum(v);
+    if (lane == 0) totals[i] = v;
   }
   __syncthreads();
-  __shared__ float pose_out[8];
   if (warp == 0) {
-    if (lane == 0) pose_from_moments(&F, &G, &acc_s[0][0], kThreads, pose_out);
-    __syncwarp();
-    const float v = lane < 8 ? pose_out[lane] : 0.0f;
+    float m[kMoments];
+#pragma unroll
+    for (int i = 0; i < kMoments; ++i) m[i] = totals[i];
+    float out[8];
+    moments_to_pose(F, G, m, out);
+    float v = out[0];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) v = lane == i ? out[i] : v;
     if (lane < 8 && v != 0.0f) {
       if (lane < 3) {
         if (flags & SDFR_GRAD_POSITION) atomicAdd(gp + 3 * b + lane, v);
@@ -416,7 +406,7 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
   __shared__ HullEdge edges[kMaxHullEdges];
-  __shared__ double acc_mem[(MODE == 2 && WANT_POSE) ? kMoments * kThreads : 1];
+  __shared__ float acc_mem[(MODE == 2 && WANT_POSE) ? kMoments * kThreads : 1];
   MomentAcc& acc_s = *reinterpret_cast<MomentAcc*>(acc_mem);
   __shared__ int next_q, n_live;
   __shared__ unsigned worklist[kListCap];
@@ -620,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, SDFR_BWD_BLOCKS)
 sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   extern __shared__ float tables[];
   __shared__ Frame Fs;
-  __shared__ double acc_mem[WANT_POSE ? kMoments * kThreads : 1];
+  __shared__ float acc_mem[WANT_POSE ? kMoments * kThreads : 1];
   MomentAcc& acc_s = *reinterpret_cast<MomentAcc*>(acc_mem);
 
   const int b = blockIdx.y + P.z_offset;
@@ -866,11 +856,10 @@ sdfr_backward_composite_kernel(const __grid_constant__ BwdParams P) {
     }
     if (WANT_SDF) scatter_sdf_warp<RT>(P.grad_sdf + (size_t)k * P.grad_sdf_stride, Gc, base, w8, mine, lane);
     if (WANT_POSE) {
-      double accd[kMoments];
 #pragma unroll
-      for (int i = 0; i < kMoments; ++i) accd[i] = warp_sum_d((double)acc[i]);
+      for (int i = 0; i < kMoments; ++i) acc[i] = warp_sum(acc[i]);
       float out[8];
-      pose_from_moments(&F, &Gc, accd, 1, out);
+      moments_to_pose(F, Gc, acc, out);
       float v = out[0];
 #pragma unroll
       for (int i = 1; i < 8; ++i) v = (lane == i) ? out[i] : v;
@@ -923,45 +912,93 @@ __global__ void sdfr_bounds_init_kernel(const float* __restrict__ pos, const flo
   }
 }
 
-/* CTA = (x cell layer ix, tile of cell rows y0.., grid n).  Phase 1: the element-wise minimum of the two
- * voxel layers ix, ix+1 over the tile's (rows + 1) x R values goes to shared memory -- every thread
- * issues all its loads before the first use, so a CTA has its whole 2 x (rows+1) x R x 4 bytes in flight
- * (a first version that walked the rows with one dependent load round trip each ran at 1 TB/s).
- * Phase 2: a cell's minimum is the minimum of 4 neighbours in that plane; ballots give the z range. */
-__global__ void __launch_bounds__(256)
+/* CTA = (x cell layer ix, block of 8 row strips, grid n); a warp owns a strip of kBoundsRows cell rows.
+ * Lane l holds, for each of the strip's kBoundsRows + 1 voxel rows, the voxel-layer-pair minimum at
+ * z = z0 + 2l, z0 + 2l + 1 (64 values = 63 cells per warp step): ALL loads of the strip are issued
+ * before the first use (36 independent loads per thread), then the y-pair minimum is a min of two
+ * registers and the z-pair minimum one min in the thread and one shuffle -- ~0.3 instructions per
+ * cell, no shared memory.
+ * History (ncu r02e, bench r02d/r02f): a shared-memory plane with 4 neighbour reads per cell was
+ * issue-bound at 43 us for 64 x 64^3; walking the rows with the loads inside the loop that also votes
+ * was latency-bound at 54 us (the votes keep the compiler from hoisting the next rows' loads).
+ * WRITE_SKEW: the source is the DENSE grid and the kernel also writes the skewed copy (each voxel by the
+ * warp that owns it), so that the layout pass and the bounds pass are one read of the grids. */
+constexpr int kBoundsRows = 4;
+
+template <bool WRITE_SKEW>
+__global__ void __launch_bounds__(256, 3)
 sdfr_bounds_scan_kernel(const float* __restrict__ sdf, long long sdf_stride, int R, int py, int px,
-                        int tile_rows, CellBounds* __restrict__ out) {
-  extern __shared__ float plane[]; /* (rows + 1) x R */
+                        CellBounds* __restrict__ out, float* __restrict__ skew, long long skew_stride,
+                        int spy, int spx) {
   __shared__ int s_lo[2], s_hi[2];
-  const int n = blockIdx.z, ix = blockIdx.x, y0 = blockIdx.y * tile_rows;
-  const int rows = min(tile_rows, R - 1 - y0); /* cell rows of this tile */
+  const int n = blockIdx.z, ix = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* __restrict__ g0 = sdf + (size_t)n * sdf_stride + (size_t)ix * px + (size_t)y0 * py;
+  const float* __restrict__ g0 = sdf + (size_t)n * sdf_stride + (size_t)ix * px;
   const float* __restrict__ g1 = g0 + px;
+  float* __restrict__ d0 = WRITE_SKEW ? skew + (size_t)n * skew_stride + (size_t)ix * spx : nullptr;
+  const bool last_layer = ix == R - 2; /* this CTA also owns voxel layer R-1 */
   const float tau = out[n].tau;
   if (threadIdx.x < 2) {
     s_lo[threadIdx.x] = 0x7fffffff;
     s_hi[threadIdx.x] = -1;
   }
-  for (int y = warp; y <= rows; y += kWarps) {
-    const float* __restrict__ a = g0 + (size_t)y * py;
-    const float* __restrict__ b = g1 + (size_t)y * py;
-    for (int z = lane; z < R; z += 32) plane[y * R + z] = fminf(__ldg(a + z), __ldg(b + z));
-  }
   __syncthreads();
+  const int y_begin = ((int)blockIdx.y * kWarps + warp) * kBoundsRows;
   int ylo = 0x7fffffff, yhi = -1, zlo = 0x7fffffff, zhi = -1;
-  for (int y = warp; y < rows; y += kWarps) {
-    const float* __restrict__ r0 = plane + y * R;
-    for (int z0 = 0; z0 < R - 1; z0 += 32) {
-      const int z = z0 + lane;
-      bool below = false;
-      if (z < R - 1) below = fminf(fminf(r0[z], r0[z + 1]), fminf(r0[R + z], r0[R + z + 1])) < tau;
-      const unsigned mask = __ballot_sync(kFull, below);
-      if (mask) {
-        ylo = min(ylo, y0 + y);
-        yhi = max(yhi, y0 + y);
-        zlo = min(zlo, z0 + __ffs(mask) - 1);
-        zhi = max(zhi, z0 + 31 - __clz(mask));
+  if (y_begin < R - 1) {
+    for (int z0 = 0; z0 < R - 1; z0 += 63) { /* values z0 .. z0 + 63 give cells z0 .. z0 + 62 */
+      const int za = z0 + 2 * lane, zb = za + 1;
+      const bool oka = za < R, okb = zb < R;
+      float a0[kBoundsRows + 1], a1[kBoundsRows + 1], b0[kBoundsRows + 1], b1[kBoundsRows + 1];
+#pragma unroll
+      for (int j = 0; j <= kBoundsRows; ++j) { /* voxel rows y_begin .. y_begin + kBoundsRows */
+        const int y = y_begin + j;
+        const bool row = y < R;
+        const float* __restrict__ r0 = g0 + (size_t)y * py;
+        const float* __restrict__ r1 = g1 + (size_t)y * py;
+        a0[j] = (row && oka) ? __ldg(r0 + za) : 3.0e38f;
+        a1[j] = (row && oka) ? __ldg(r1 + za) : 3.0e38f;
+        b0[j] = (row && okb) ? __ldg(r0 + zb) : 3.0e38f;
+        b1[j] = (row && okb) ? __ldg(r1 + zb) : 3.0e38f;
+      }
+      if (WRITE_SKEW) {
+#pragma unroll
+        for (int j = 0; j <= kBoundsRows; ++j) {
+          const int y = y_begin + j;
+          /* the strip owns its first kBoundsRows voxel rows; the last voxel row of the grid belongs to
+           * the strip that reads it as its halo */
+          const bool own = y < R && (j < kBoundsRows || y == R - 1);
+          /* value z0 + 63 is re-read by the next z step, which owns it -- unless there is none */
+          const bool own_b = okb && (lane < 31 || z0 + 63 >= R - 1);
+          if (own) {
+            float* __restrict__ w0 = d0 + (size_t)y * spy;
+            if (oka) w0[za] = a0[j];
+            if (own_b) w0[zb] = b0[j];
+            if (last_layer) {
+              if (oka) w0[spx + za] = a1[j];
+              if (own_b) w0[spx + zb] = b1[j];
+            }
+          }
+        }
+      }
+      float pa = fminf(a0[0], a1[0]), pb = fminf(b0[0], b1[0]);
+#pragma unroll
+      for (int j = 1; j <= kBoundsRows; ++j) { /* cell row y = y_begin + j - 1 */
+        const int y = y_begin + j - 1;
+        const float ca = fminf(a0[j], a1[j]), cb = fminf(b0[j], b1[j]);
+        const float ma = fminf(pa, ca), mb = fminf(pb, cb);
+        const float nxt = __shfl_down_sync(kFull, ma, 1);
+        const bool cell_row = y < R - 1;
+        const bool below_a = cell_row && zb < R && fminf(ma, mb) < tau;                    /* cell za: voxels za, za + 1 */
+        const bool below_b = cell_row && lane < 31 && zb + 1 < R && fminf(mb, nxt) < tau;  /* cell zb: voxels zb, zb + 1 */
+        const unsigned mka = __ballot_sync(kFull, below_a), mkb = __ballot_sync(kFull, below_b);
+        if (mka | mkb) {
+          ylo = min(ylo, y);
+          yhi = max(yhi, y);
+          if (mka) { zlo = min(zlo, z0 + 2 * (__ffs(mka) - 1)); zhi = max(zhi, z0 + 2 * (31 - __clz(mka))); }
+          if (mkb) { zlo = min(zlo, z0 + 2 * (__ffs(mkb) - 1) + 1); zhi = max(zhi, z0 + 2 * (31 - __clz(mkb)) + 1); }
+        }
+        pa = ca; pb = cb;
       }
     }
   }
@@ -1558,6 +1595,30 @@ int sdfr_backward_composite(const float* grad_depth, const float* depth, const i
   return check_launch("sdfr_backward_composite_kernel");
 }
 
+static int launch_bounds_scan(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
+                              const float* inv_scale, int batch, float threshold, sdfr_cell_bounds* bounds,
+                              float* skewed, long long skewed_stride, cudaStream_t s) {
+  const int n_grids = sdf_stride == 0 ? 1 : batch;
+  const Grid G = make_grid(R, layout);
+  const Grid GS = make_grid(R, kLayoutSkewed);
+  CellBounds* out = reinterpret_cast<CellBounds*>(bounds);
+  sdfr_bounds_init_kernel<<<n_grids, n_grids == 1 ? 256 : 32, 0, s>>>(pos, inv_scale, batch, n_grids, threshold, out);
+  /* kBoundsRows cell rows per warp, 8 warps per CTA: one CTA per x layer up to R = 65 */
+  const int y_blocks = (R - 1 + kWarps * kBoundsRows - 1) / (kWarps * kBoundsRows);
+  for (int z0 = 0; z0 < n_grids; z0 += 65535) {
+    const int nz = n_grids - z0 < 65535 ? n_grids - z0 : 65535;
+    const dim3 grid(R - 1, y_blocks, nz);
+    if (skewed)
+      sdfr_bounds_scan_kernel<true><<<grid, 256, 0, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride, R, G.py, G.px,
+                                                         out + z0, skewed + (size_t)z0 * skewed_stride,
+                                                         skewed_stride, GS.py, GS.px);
+    else
+      sdfr_bounds_scan_kernel<false><<<grid, 256, 0, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride, R, G.py, G.px,
+                                                          out + z0, nullptr, 0, 0, 0);
+  }
+  return check_launch("sdfr_bounds_scan_kernel");
+}
+
 int sdfr_grid_bounds(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
                      const float* inv_scale, int batch, float threshold, sdfr_cell_bounds* bounds,
                      void* stream) {
@@ -1567,23 +1628,24 @@ int sdfr_grid_bounds(const float* sdf, int R, long long sdf_stride, int layout, 
   if (!(threshold >= 0.0f)) return fail(SDFR_E_SHAPE, "threshold must be >= 0");
   if (batch == 0) return 0;
   if (!sdf || !pos || !inv_scale || !bounds) return fail(SDFR_E_NULL, "grid bounds: NULL pointer");
-  const int n_grids = sdf_stride == 0 ? 1 : batch;
-  const Grid G = make_grid(R, layout);
-  cudaStream_t s = (cudaStream_t)stream;
-  CellBounds* out = reinterpret_cast<CellBounds*>(bounds);
-  sdfr_bounds_init_kernel<<<n_grids, n_grids == 1 ? 256 : 32, 0, s>>>(pos, inv_scale, batch, n_grids, threshold, out);
-  /* cell rows per tile: the (rows + 1) x R plane must fit 32 KB of shared memory */
-  int tile_rows = (32 * 1024 / (int)sizeof(float)) / R - 1;
-  if (tile_rows > R - 1) tile_rows = R - 1;
-  if (tile_rows < 1) tile_rows = 1;
-  const int n_tiles = (R - 1 + tile_rows - 1) / tile_rows;
-  const size_t smem = (size_t)(tile_rows + 1) * R * sizeof(float);
-  for (int z0 = 0; z0 < n_grids; z0 += 65535) {
-    const int nz = n_grids - z0 < 65535 ? n_grids - z0 : 65535;
-    sdfr_bounds_scan_kernel<<<dim3(R - 1, n_tiles, nz), 256, smem, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride,
-                                                                      R, G.py, G.px, tile_rows, out + z0);
-  }
-  return check_launch("sdfr_bounds_scan_kernel");
+  return launch_bounds_scan(sdf, R, sdf_stride, layout, pos, inv_scale, batch, threshold, bounds, nullptr, 0,
+                            (cudaStream_t)stream);
+}
+
+int sdfr_skew_grids_bounds(const float* sdf, int R, long long sdf_stride, int batch, float* skewed,
+                           long long skewed_stride, const float* pos, const float* inv_scale, float threshold,
+                           sdfr_cell_bounds* bounds, void* stream) {
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (batch < 0 || sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative batch or sdf_stride");
+  if (!(threshold >= 0.0f)) return fail(SDFR_E_SHAPE, "threshold must be >= 0");
+  if (batch == 0) return 0;
+  if (!sdf || !skewed || !pos || !inv_scale || !bounds) return fail(SDFR_E_NULL, "skew + bounds: NULL pointer");
+  const Grid G = make_grid(R, kLayoutSkewed);
+  if (skewed_stride < (long long)R * G.px)
+    return fail(SDFR_E_SHAPE, "skewed_stride smaller than sdfr_skewed_pitches' elems");
+  if (sdf_stride == 0 && batch > 1) skewed_stride = 0; /* one shared grid: one skewed copy */
+  return launch_bounds_scan(sdf, R, sdf_stride, SDFR_LAYOUT_DENSE, pos, inv_scale, batch, threshold, bounds, skewed,
+                            skewed_stride, (cudaStream_t)stream);
 }
 
 int sdfr_skewed_pitches(int R, int* pitch_y, int* pitch_x, long long* elems) {

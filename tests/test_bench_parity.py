@@ -27,7 +27,7 @@ from oracle import build_ref
 from sdfest_b200 import _lib
 from sdfest_b200 import synthetic as syn
 from sdfest_b200.differentiable_renderer import Camera, render_depth_batched, render_depth_composite
-from util import depth_parity, grad_close, pose_grad_parity, sdf_grad_parity
+from util import cell_face_mask, depth_parity, grad_close, pose_grad_parity, sdf_grad_parity
 
 pytestmark = pytest.mark.gpu
 
@@ -163,7 +163,8 @@ def test_c2_benchmarked_path_matches_oracle(c2):
                                     n["inv_s"][b], W, H, sdf_grad_mode="reference", want_deriv=True,
                                     nthreads=os.cpu_count() or 1, **CAM)
         errs["position"] = max(errs["position"], pose_grad_parity(
-            (n["g_pos"][b], n["g_quat"][b], n["g_is"][b]), bw, g, GRAD_RTOL, f"hypothesis {b}") * GRAD_RTOL)
+            (n["g_pos"][b], n["g_quat"][b], n["g_is"][b]), bw, g, GRAD_RTOL, f"hypothesis {b}",
+            position=n["pos"][b], inv_scale=n["inv_s"][b]) * GRAD_RTOL)
         e, n_bad = sdf_grad_parity(n["g_sdf"][b], bw["g_sdf"], GRAD_RTOL, np.abs(g).max() / n["inv_s"][b], what=f"sdf[{b}]")
         errs["sdf"] = max(errs["sdf"], e)
         errs["sdf_cell_flip_voxels"] = errs.get("sdf_cell_flip_voxels", 0) + n_bad
@@ -233,6 +234,14 @@ def test_c3_composite_at_size_matches_oracle(cuda_device):
     assert (w_gpu == w_or).mean() > 0.9995
     assert len(set(np.unique(w_gpu)) - {-1}) >= 12, "most of the 16 objects must be visible"
     g = np.random.default_rng(4).standard_normal((H3, W3)).astype(np.float32)
+    # no upstream gradient where the hit point sits on a cell face (tests/util.py::cell_face_mask)
+    d_first = depth.detach().cpu().numpy()
+    n_masked = 0
+    for k in range(K):
+        face = cell_face_mask(np.where(w_gpu == k, d_first, 0), npos[k], nq[k], ns[k], 128, **cam_d)
+        g[face] = 0.0
+        n_masked += int(face.sum())
+    assert n_masked < 0.05 * (w_gpu >= 0).sum()
     depth.backward(torch.as_tensor(g, device=cuda_device))
     d_np = depth.detach().cpu().numpy()
     errs = dict(position=0.0, sdf=0.0)
@@ -246,7 +255,7 @@ def test_c3_composite_at_size_matches_oracle(cuda_device):
         gk = np.where(dk != 0, g, 0)
         errs["position"] = max(errs["position"], pose_grad_parity(
             (a[1].grad[k].cpu().numpy(), a[2].grad[k].cpu().numpy(), a[3].grad[k].cpu().numpy()), bw, gk,
-            GRAD_RTOL, f"obj{k}") * GRAD_RTOL)
+            GRAD_RTOL, f"obj{k}", position=npos[k], inv_scale=ns[k]) * GRAD_RTOL)
         e, n_bad = sdf_grad_parity(a[0].grad[k].cpu().numpy(), bws[k]["g_sdf"], GRAD_RTOL,
                                    float(np.abs(g).max() / ns[k]), what=f"obj{k} sdf")
         errs["sdf"] = max(errs["sdf"], e)
@@ -301,7 +310,7 @@ def test_c4_shared_grid_pose_sweep_matches_oracle(cuda_device, category):
         bw = oracle.render_backward(g.astype(np.float32), d_gpu, ngrid, p, q, s, W, H, want_sdf=False,
                                     want_deriv=True, nthreads=os.cpu_count() or 1, **CAM)
         pose_grad_parity((g_pos[b].cpu().numpy(), g_quat[b].cpu().numpy(), float(g_is[b])), bw, g, GRAD_RTOL,
-                         f"{category}[{b}]")
+                         f"{category}[{b}]", position=p, inv_scale=s)
     _record(f"c4_{category}_vs_oracle", dict(depth=_merge(infos)))
 
 
@@ -334,6 +343,44 @@ def test_grid_bounds_kernel_matches_oracle(c2, layout):
     tau = max(gb.hit_tau(n["pos"][b], n["inv_s"][b], THR) for b in range(B))
     lo, hi = gb.cell_bounds(n["grids"][0], tau)
     assert got[6:7].view(np.float32)[0] == tau and (got[0:3] == lo).all() and (got[3:6] == hi).all()
+
+
+def test_skew_and_bounds_in_one_pass(c2):
+    """sdfr_skew_grids_bounds == sdfr_skew_grids + sdfr_grid_bounds (what bench.py's step launches)."""
+    lib, B, dev = _lib.lib(), c2["B"], c2["dev"]
+    st = torch.cuda.current_stream().cuda_stream
+    RRR, SK = R ** 3, c2["SK"]
+    sep_sk = torch.full((B, SK), -7.0, device=dev)
+    sep_b = torch.empty((B, 8), dtype=torch.int32, device=dev)
+    _lib.check(lib.sdfr_skew_grids(c2["grids"].data_ptr(), R, RRR, B, sep_sk.data_ptr(), SK, st), "skew")
+    _lib.check(lib.sdfr_grid_bounds(sep_sk.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, c2["pos"].data_ptr(),
+                                    c2["inv_s"].data_ptr(), B, THR, sep_b.data_ptr(), st), "bounds")
+    one_sk = torch.full((B, SK), -7.0, device=dev)
+    one_b = torch.full((B, 8), -3, dtype=torch.int32, device=dev)
+    _lib.check(lib.sdfr_skew_grids_bounds(c2["grids"].data_ptr(), R, RRR, B, one_sk.data_ptr(), SK,
+                                          c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), THR, one_b.data_ptr(), st),
+               "sdfr_skew_grids_bounds")
+    torch.cuda.synchronize()
+    assert torch.equal(one_sk, sep_sk)
+    assert torch.equal(one_b[:, :7], sep_b[:, :7])
+    # odd resolution, shared grid
+    R2 = 37
+    g = torch.rand(R2, R2, R2, device=dev) - 0.3
+    n_sk = ctypes.c_longlong(0)
+    _lib.check(lib.sdfr_skewed_pitches(R2, None, None, ctypes.byref(n_sk)), "pitches")
+    a_sk, b_sk = torch.full((1, n_sk.value), -7.0, device=dev), torch.full((1, n_sk.value), -7.0, device=dev)
+    a_b, b_b = torch.empty((1, 8), dtype=torch.int32, device=dev), torch.empty((1, 8), dtype=torch.int32, device=dev)
+    _lib.check(lib.sdfr_skew_grids(g.data_ptr(), R2, 0, 1, a_sk.data_ptr(), n_sk.value, st), "skew")
+    _lib.check(lib.sdfr_grid_bounds(g.data_ptr(), R2, 0, _lib.LAYOUT_DENSE, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(),
+                                    B, 0.0, a_b.data_ptr(), st), "bounds")
+    _lib.check(lib.sdfr_skew_grids_bounds(g.data_ptr(), R2, 0, B, b_sk.data_ptr(), n_sk.value, c2["pos"].data_ptr(),
+                                          c2["inv_s"].data_ptr(), 0.0, b_b.data_ptr(), st), "skew+bounds")
+    torch.cuda.synchronize()
+    assert torch.equal(a_sk, b_sk) and torch.equal(a_b[:, :7], b_b[:, :7])
+    from oracle import grid_bounds as gb
+
+    lo, hi = gb.cell_bounds(g.cpu().numpy(), float(a_b[0, 6:7].view(torch.float32)))
+    assert (a_b[0, 0:3].cpu().numpy() == lo).all() and (a_b[0, 3:6].cpu().numpy() == hi).all()
 
 
 def test_c2_with_empty_space_bounds_is_unchanged(c2):

@@ -10,8 +10,9 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from sdfest_b200.differentiable_renderer import Camera
+from oracle.pc_loss import pc_loss, point_loss  # torch restatement of the reference's loss (test infrastructure)
 from sdfest_b200.estimation import (depth_to_pointcloud, depth_to_pointclouds, gather_losses, global_best,
-                                    pc_loss, point_loss, shard_range, subsample_points)
+                                    shard_range, subsample_points)
 from util import GOLDEN_DIR
 
 
@@ -200,9 +201,10 @@ def _loop_inputs(n_total):
 
 
 def _loop_worker(rank, world, port, n_total, q):
-    from sdfest_b200.estimation import HypothesisOptimizer, hypotheses
+    from sdfest_b200.estimation import HypothesisOptimizer, hypotheses, losses
 
     hypotheses.render_and_compare = _stand_in_render_and_compare  # the CUDA renderer's stand-in on CPU
+    losses.point_loss = point_loss  # and the CUDA point loss's (the product has no CPU path)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     if world > 1:

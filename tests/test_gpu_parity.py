@@ -707,7 +707,7 @@ def test_streamed_host_buffers_match_device_path(cuda_device, graph):
 def _pcloss_reference(points, pos, quat, scale, sdf):
     """float64 torch restatement of the reference's pc_loss (pinned to its golden vector by
     tests/test_estimation_host.py) -> per-hypothesis mean |.| and autograd gradients."""
-    from sdfest_b200.estimation import pc_loss
+    from oracle.pc_loss import pc_loss
 
     a = [t.detach().double().cpu().requires_grad_(True) for t in (pos, quat, scale, sdf)]
     pts = points.detach().double().cpu()

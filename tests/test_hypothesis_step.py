@@ -609,8 +609,8 @@ def test_compare_fused_inliers_counts_in_the_same_traversal(cuda_device, per_hyp
     want = [hs.inlier_counts(o[b] if per_hypothesis_obs else o, d[b], thr)[0] for b in range(B)]
     assert sums[2].tolist() == want and max(want) > 50
     # thresholds above 1 would have to count missed pixels: rejected
-    assert lib.sdfr_compare_fused_inliers(*head, 1.5, sums[2].data_ptr(), None, *tail) == -2
-    assert lib.sdfr_compare_fused_inliers(*head, thr, None, None, *tail) == -1
+    assert lib.sdfr_compare_fused_inliers(*head, 1.5, sums[2].data_ptr(), *tail) == -2
+    assert lib.sdfr_compare_fused_inliers(*head, thr, None, *tail) == -1
 
 
 @pytest.mark.gpu

@@ -52,6 +52,10 @@ def _fake_render_and_compare(sdf, position, orientation, inv_scale, depth_obs, t
 @pytest.fixture
 def scene(monkeypatch):
     monkeypatch.setattr(hypotheses, "render_and_compare", _fake_render_and_compare)
+    from oracle.pc_loss import point_loss
+    from sdfest_b200.estimation import losses
+
+    monkeypatch.setattr(losses, "point_loss", point_loss)  # the product's point loss is CUDA-only
     depth = torch.full((H, W), 0.8)
     depth[0, 0] = 5.0  # far-field outlier inside the mask
     mask = torch.zeros(H, W, dtype=torch.bool)

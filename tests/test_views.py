@@ -85,6 +85,10 @@ def test_multiview_step_plumbing_on_cpu(monkeypatch):
         return loss, depth, torch.ones(B)
 
     monkeypatch.setattr(hypotheses, "render_and_compare", fake_render_and_compare)
+    from oracle.pc_loss import point_loss
+    from sdfest_b200.estimation import losses
+
+    monkeypatch.setattr(losses, "point_loss", point_loss)  # the product's point loss is CUDA-only
     W, H, B = 16, 12, 3
     cam = Camera(W, H, 14.0, 14.0, 8.0, 6.0, pixel_center=0.5)
     obs = torch.zeros(2, H, W)

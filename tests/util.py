@@ -145,24 +145,63 @@ def sdf_grad_parity(a, b, rtol=1e-3, pixel_bound=None, max_flip_pixels=4, what="
     return float(err[~bad].max() / scale), n_bad
 
 
-def pose_grad_parity(got, bw, g, rtol=1e-3, what=""):
+def pose_grad_parity(got, bw, g, rtol=1e-3, what="", position=None, inv_scale=None):
     """Pose-gradient gate against an oracle backward `bw` run with want_deriv=True and upstream image
     `g`: per parameter group (position, orientation, inv_scale)
-        |got - ref| <= rtol * max|ref| + 16 eps * max_i sum_pixels |g * d depth / d theta_i|,
-    eps = 2^-24.  The second term is the forward error bound of ANY fp32 evaluation of these sums: when a
-    gradient (nearly) cancels over the pixels -- the orientation gradient of a rotationally symmetric
-    shape -- the reference's own atomics do not reproduce it to rtol of its tiny maximum either.
+
+        |got - ref| <= rtol * max|ref| + 16 eps * kappa * S_group,        eps = 2^-24.
+
+    The first term is BASELINE.json's 1e-3.  The second is the forward error bound of ANY fp32
+    evaluation of these sums, which takes over when a gradient (nearly) cancels and rtol of its tiny
+    maximum asks for digits fp32 does not have -- the reference's own kernel does not reproduce itself to
+    that either (its fp32 oracle and its float64 oracle differ by 4e-3 of the maximum on the C3 scene):
+      S_group  = sum over the hit pixels of |g * d depth / d theta|, largest component of the group; for
+                 the orientation additionally 2 sqrt(3) scale * S_position -- the size of the two halves
+                 of d c / d q (cu:402-437: C_k (x - p) and -2 q_k o) BEFORE they cancel, which is what
+                 bounds the rounding of every formulation, per pixel (reference) or per moment (ours),
+                 when the shape is rotationally symmetric and the halves cancel exactly;
+      kappa    = max(1, |p| inv_scale): the hit point in the object frame is the difference of two
+                 vectors of length |p| (cu:344-345), so its rounding is |p| / scale relative.
     `got` = (position (3,), orientation (4,), inv_scale scalar).  Returns the largest error relative to
-    the tolerance's first term (so <= 1 means "inside rtol alone")."""
+    rtol * max|ref| (<= 1 means inside the first term alone)."""
     ref = (np.asarray(bw["g_position"], np.float64), np.asarray(bw["g_orientation"], np.float64),
            np.asarray([bw["g_inv_scale"]], np.float64))
     absum = np.abs(np.asarray(g, np.float64)[None] * np.asarray(bw["deriv"], np.float64)).sum((1, 2))
+    kappa, scale_obj = 1.0, 0.0
+    if position is not None and inv_scale is not None:
+        scale_obj = 1.0 / float(inv_scale)
+        kappa = max(1.0, float(np.linalg.norm(np.asarray(position, np.float64))) * float(inv_scale))
+    s_group = (absum[0:3].max(), max(absum[3:7].max(), 2 * 3 ** 0.5 * scale_obj * absum[0:3].max()), absum[7])
     worst = 0.0
-    for a, b, sl, nm in zip(got, ref, (slice(0, 3), slice(3, 7), slice(7, 8)), ("position", "orientation", "inv_scale")):
+    for a, b, sg, nm in zip(got, ref, s_group, ("position", "orientation", "inv_scale")):
         a = np.asarray(a, np.float64).reshape(-1)
         scale = max(np.abs(b).max(), 1e-30)
         err = np.abs(a - b).max()
-        tol = rtol * scale + 16 * 2.0 ** -24 * absum[sl].max()
-        assert err <= tol, f"{what} {nm}: err {err:.3e} > {tol:.3e} (max|ref| {scale:.3e}, abs-sum {absum[sl].max():.3e})"
+        tol = rtol * scale + 16 * 2.0 ** -24 * kappa * sg
+        assert err <= tol, f"{what} {nm}: err {err:.3e} > {tol:.3e} (max|ref| {scale:.3e}, S {sg:.3e}, kappa {kappa:.2f})"
         worst = max(worst, err / (rtol * scale))
     return worst
+
+
+def cell_face_mask(depth, position, orientation, inv_scale, R, cx, cy, fx, fy, delta=2e-3):
+    """Hit pixels whose hit point (re-derived from the depth as cu:336-354 does, here in float64) lies
+    within `delta` cells of a cell face.  There the reference's cell lookup `floor` can go either way under
+    fp32 rounding, and both the corner weights (cu:373-388) and the trilinear gradient that carries the pose
+    derivatives (cu:444-456) are DISCONTINUOUS across the face -- one such pixel moves the gradients by its
+    whole contribution.  Tests with an explicit upstream image zero it on these pixels (about 1 % of the
+    hits), so that renderer and oracle are compared where the function they differentiate is smooth."""
+    z = np.asarray(depth, np.float64)
+    H, W = z.shape
+    col, row = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64))
+    d = np.stack([(col + 0.5 - cx) / fx, -(row + 0.5 - cy) / fy, -np.ones_like(col)], -1)
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    t = -z / d[..., 2]
+    x, y, zq, w = (float(v) for v in np.asarray(orientation, np.float64).reshape(-1)[:4])
+    Rm = np.array([[1 - 2 * (y * y + zq * zq), 2 * (x * y - w * zq), 2 * (x * zq + w * y)],
+                   [2 * (x * y + w * zq), 1 - 2 * (x * x + zq * zq), 2 * (y * zq - w * x)],
+                   [2 * (x * zq - w * y), 2 * (y * zq + w * x), 1 - 2 * (x * x + y * y)]])
+    o = (t[..., None] * d - np.asarray(position, np.float64).reshape(-1)[:3]) @ Rm  # R^T (x - p)
+    v = (o * float(np.asarray(inv_scale).reshape(-1)[0]) + 1.0) * (R - 1) / 2.0
+    frac = v - np.floor(v)
+    near = (np.minimum(frac, 1.0 - frac) < delta).any(-1)
+    return near & (z != 0)
