@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 8
+#define SDFR_ABI_VERSION 9
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -304,8 +304,11 @@ int sdfr_point_loss_fused(const float* points, long long points_stride, int n_po
  *   8..) and step [batch] (int32), all caller-zeroed before the first call;
  *   then orientation is renormalised in place and, if given,
  *   unit_orientation = orientation/|orientation|, inv_scale = 1/scale  (the next iteration's
- *   renderer inputs), loss = depth_weight * loss_sum/n_overlap (0 without overlap, the reference's
- *   nan_to_num) + point_weight * point_sum.
+ *   renderer inputs), loss = depth_weight * loss_sum/n_overlap (NaN without overlap: the reference's
+ *   mean over an empty selection, simple_setup.py:131 -- the gradients are 0 there, not NaN) +
+ *   point_weight * point_sum + loss_extra.
+ * g_orientation_raw (optional) is added to the orientation gradient AFTER the chain rule, i.e. it is a
+ * gradient w.r.t. the un-normalised orientation: the point-constraint loss of simple_setup.py:164-175.
  * gr_* are the RAW gradients of sdfr_compare_fused (w.r.t. the unit quaternion and inv_scale);
  * g2_* an already weighted second set (sdfr_point_loss_fused: w.r.t. the quaternion it was given --
  * the unit one -- and scale).  Any gradient pointer may be NULL (= 0); latent / g_latent NULL or
@@ -319,10 +322,53 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
                          float* gr_position, float* gr_orientation, float* gr_inv_scale,
                          float depth_weight, float* point_sum, float point_weight,
                          float* g2_position, float* g2_orientation, float* g2_scale,
-                         float* g_latent, float* exp_avg, float* exp_avg_sq, int* step,
-                         const float* lr, float beta1, float beta2, float eps,
-                         float* unit_orientation, float* inv_scale, float* loss, unsigned flags,
+                         float* g_latent, float* g_orientation_raw, float* loss_extra, float* exp_avg,
+                         float* exp_avg_sq, int* step, const float* lr, float beta1, float beta2,
+                         float eps, float* unit_orientation, float* inv_scale, float* loss,
+                         unsigned flags, void* stream);
+
+/*
+ * Several camera views of one object (estimation/simple_setup.py:420-446): the pose lives in the world
+ * frame and is moved into each of n_views camera frames,
+ *   position_c[v,b]    = R(conj(cam_orientation[v])) (position[b] - cam_position[v])
+ *   orientation_c[v,b] = conj(cam_orientation[v]) (x) unit_orientation[b]      (scalar-last, unit)
+ *   inv_scale_c[v,b]   = inv_scale[b]
+ * (initialization/quaternion_utils.py:12-66); outputs [n_views, batch, ...] so that view v is one
+ * batched render of `batch` hypotheses at position_c + v*batch*3 etc.
+ */
+int sdfr_view_poses(const float* position, const float* unit_orientation, const float* inv_scale,
+                    const float* cam_position, const float* cam_orientation, int n_views, int batch,
+                    float* position_c, float* orientation_c, float* inv_scale_c, void* stream);
+
+/*
+ * Adjoint of sdfr_view_poses plus the loss of the view loop: per hypothesis, summed over the views,
+ *   g_position    = sum_v R(cam_orientation[v]) (gr_position[v] + g2_position[v])
+ *   g_orientation = sum_v cam_orientation[v] (x) (gr_orientation[v] + g2_orientation[v])   (w.r.t. the
+ *                   world-frame UNIT quaternion)
+ *   g_scale       = sum_v g2_scale[v] - gr_inv_scale[v] / scale^2
+ *   loss         += sum_v depth_weight * loss_sum[v]/n_overlap[v] (NaN without overlap) + point_sum[v]
+ * gr_* = gradients of the (already weighted and normalised) depth loss of each view w.r.t. its
+ * camera-frame pose (sdfr_compare_backward with upstream = depth_weight), g2_* / point_sum = the weighted
+ * point loss of each view (sdfr_point_loss_fused with SDFR_LOSS_WEIGHTED); all [n_views, batch, ...],
+ * any may be NULL.  The outputs feed sdfr_hypothesis_step as its g2_* inputs (and `loss` as its
+ * loss_extra).  SDFR_STEP_CLEAR_INPUTS zeroes the per-view inputs after reading them.
+ */
+int sdfr_views_pull_back(const float* cam_orientation, const float* scale, int n_views, int batch,
+                         float* gr_position, float* gr_orientation, float* gr_inv_scale,
+                         float* g2_position, float* g2_orientation, float* g2_scale, float* loss_sum,
+                         float* n_overlap, float depth_weight, float* point_sum, float* g_position,
+                         float* g_orientation, float* g_scale, float* loss, unsigned flags,
                          void* stream);
+
+/*
+ * Point constraint of the loop (estimation/simple_setup.py:164-175 -> estimation/losses.py:138-153):
+ *   loss[b] += weight * | q_b (x) (source,0) (x) conj(q_b) - target |,   q_b = orientation[b] as stored,
+ * NOT normalised (quaternion_utils.py:37-54 does not normalise either), and its gradient w.r.t. that
+ * un-normalised quaternion accumulated into g_orientation_raw [batch,4] -- the two optional inputs of
+ * sdfr_hypothesis_step.  source / target: HOST float[3].  Either output may be NULL.
+ */
+int sdfr_point_constraint(const float* orientation, int batch, const float* source, const float* target,
+                          float weight, float* g_orientation_raw, float* loss, void* stream);
 
 /*
  * Result selection of the loop, batched and without the reference's host synchronisation

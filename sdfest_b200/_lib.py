@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -72,7 +72,12 @@ SIGNATURES = {
                 c_uint, _P]),
     "sdfr_hypothesis_step": (
         c_int, [_P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, c_float, _P, c_float, _P, _P, _P, _P,
-                _P, _P, _P, ctypes.POINTER(c_float), c_float, c_float, c_float, _P, _P, _P, c_uint, _P]),
+                _P, _P, _P, _P, _P, ctypes.POINTER(c_float), c_float, c_float, c_float, _P, _P, _P, c_uint, _P]),
+    "sdfr_view_poses": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P]),
+    "sdfr_views_pull_back": (
+        c_int, [_P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_float, _P, _P, _P, _P, _P, c_uint, _P]),
+    "sdfr_point_constraint": (
+        c_int, [_P, c_int, ctypes.POINTER(c_float), ctypes.POINTER(c_float), c_float, _P, _P, _P]),
     "sdfr_inlier_count": (
         c_int, [_P, _P, c_longlong, c_int, c_int, c_int, c_float, _P, _P, c_uint, _P]),
     "sdfr_track_best": (

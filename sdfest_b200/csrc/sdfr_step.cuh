@@ -56,6 +56,9 @@ struct StepParams {
   float* __restrict__ g2_orientation; /* quaternion and w.r.t. scale (not its inverse) */
   float* __restrict__ g2_scale;
   float* __restrict__ g_latent;     /* [B,L] or NULL */
+  float* __restrict__ g_orientation_raw; /* [B,4] or NULL: added AFTER the chain rule, i.e. w.r.t. the
+                                          * un-normalised orientation (point constraint, :164-175) */
+  float* __restrict__ loss_extra;        /* [B] or NULL: added to the loss as is */
   float* __restrict__ exp_avg;      /* [B, 8+L] */
   float* __restrict__ exp_avg_sq;   /* [B, 8+L] */
   int* __restrict__ step;           /* [B] */
@@ -119,6 +122,10 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
   p[7] = P.scale[b];
   gr[7] = P.gr_inv_scale ? P.gr_inv_scale[b] : 0.0f;
   g2[7] = P.g2_scale ? P.g2_scale[b] : 0.0f;
+  float graw[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) graw[i] = P.g_orientation_raw ? P.g_orientation_raw[4 * b + i] : 0.0f;
+  const float lextra = P.loss_extra ? P.loss_extra[b] : 0.0f;
   int t = 0;
   if (!frozen) {
     t = P.step[b] + 1;
@@ -136,6 +143,7 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
    * loss; the GRADIENTS stay 0 here (coef above) instead of poisoning Adam as the reference's do */
   if (P.loss_sum) l = n > 0.0f ? P.depth_weight * (lsum / n) : __int_as_float(0x7fc00000);
   if (P.point_sum) l += P.point_weight * psum;
+  l += lextra;
   float bc1 = 1.0f, bc2_sqrt = 1.0f;
   if (!frozen) {
     float g[8]; /* position 0-2, orientation 3-6, scale 7 */
@@ -149,7 +157,7 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
     for (int i = 0; i < 4; ++i) q[i] = p[3 + i] / nrm;
     const float dot = q[0] * gq[0] + q[1] * gq[1] + q[2] * gq[2] + q[3] * gq[3];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) g[3 + i] = (gq[i] - q[i] * dot) / nrm;
+    for (int i = 0; i < 4; ++i) g[3 + i] = (gq[i] - q[i] * dot) / nrm + graw[i];
     g[7] = -(coef * gr[7]) / (p[7] * p[7]) + g2[7];
     bc1 = (float)(1.0 - step_powi((double)P.beta1, t));
     bc2_sqrt = sqrtf((float)(1.0 - step_powi((double)P.beta2, t)));
@@ -202,6 +210,10 @@ sdfr_hypothesis_step_kernel(const __grid_constant__ StepParams P) {
     }
     if (P.gr_inv_scale) P.gr_inv_scale[b] = 0.0f;
     if (P.g2_scale) P.g2_scale[b] = 0.0f;
+    if (P.loss_extra) P.loss_extra[b] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (P.g_orientation_raw) P.g_orientation_raw[4 * b + i] = 0.0f;
   }
 
   /* ---- latent group: 8 values at a time, loads before stores ---- */
@@ -342,6 +354,194 @@ sdfr_track_best_kernel(const __grid_constant__ TrackParams P) {
   if (P.latent && P.best_latent)
     for (int i = 0; i < P.latent_size; ++i)
       P.best_latent[(size_t)b * P.latent_size + i] = P.latent[(size_t)b * P.latent_size + i];
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Several camera views of one object (estimation/simple_setup.py:420-446).  The object pose lives in the
+ * world frame; view v sees it at
+ *     position_c    = R(q_w2c,v) (position - camera_position_v)
+ *     orientation_c = q_w2c,v (x) unit_orientation                 q_w2c,v = conj(camera_orientation_v)
+ * (quaternion_utils.py:12-66, scalar-last; camera orientations are unit quaternions).  Both maps are
+ * linear in the pose, so the per-view gradients the renderer and the point loss return in the camera
+ * frames are pulled back with the transposes -- R^T = rotation by camera_orientation_v, L(q)^T = L(conj q)
+ * = left-multiplication by camera_orientation_v -- and summed over the views.  The reference does this
+ * with ~20 autograd nodes per view and iteration; here: one thread per (view, hypothesis) forward, one
+ * thread per hypothesis backward.
+ * ---------------------------------------------------------------------------------------- */
+struct ViewParams {
+  const float* __restrict__ position;      /* [B,3] world */
+  const float* __restrict__ unit_orientation; /* [B,4] world, unit */
+  const float* __restrict__ inv_scale;     /* [B] */
+  const float* __restrict__ scale;         /* [B] (pull-back only) */
+  const float* __restrict__ cam_position;  /* [V,3] */
+  const float* __restrict__ cam_orientation; /* [V,4] camera-to-world, unit */
+  int n_views, batch;
+  /* forward outputs, [V,B,...] */
+  float* __restrict__ position_c;
+  float* __restrict__ orientation_c;
+  float* __restrict__ inv_scale_c;
+  /* pull-back inputs, [V,B,...]; any may be NULL */
+  float* __restrict__ gr_position;   /* d (weighted depth loss of view v) / d position_c */
+  float* __restrict__ gr_orientation;
+  float* __restrict__ gr_inv_scale;
+  float* __restrict__ g2_position;   /* d (weighted point loss of view v) / d position_c, orientation_c, scale */
+  float* __restrict__ g2_orientation;
+  float* __restrict__ g2_scale;
+  float* __restrict__ loss_sum;      /* [V,B] masked-L1 sums */
+  float* __restrict__ n_overlap;     /* [V,B] */
+  float* __restrict__ point_sum;     /* [V,B] already weighted */
+  float depth_weight;
+  /* pull-back outputs, [B,...] */
+  float* __restrict__ g_position;
+  float* __restrict__ g_orientation; /* w.r.t. the world-frame UNIT quaternion */
+  float* __restrict__ g_scale;
+  float* __restrict__ loss;          /* [B] += */
+  unsigned flags;
+};
+
+__device__ __forceinline__ void quat_rotate(const float* q, const float* v, float* out) {
+  /* R(q) v for a unit quaternion (x,y,z,w): v + 2 w (u x v) + 2 u x (u x v) */
+  const float ux = q[0], uy = q[1], uz = q[2], w = q[3];
+  const float cx = uy * v[2] - uz * v[1], cy = uz * v[0] - ux * v[2], cz = ux * v[1] - uy * v[0];
+  const float dx = uy * cz - uz * cy, dy = uz * cx - ux * cz, dz = ux * cy - uy * cx;
+  out[0] = v[0] + 2.0f * (w * cx + dx);
+  out[1] = v[1] + 2.0f * (w * cy + dy);
+  out[2] = v[2] + 2.0f * (w * cz + dz);
+}
+
+__device__ __forceinline__ void quat_mul(const float* a, const float* b, float* out) {
+  /* Hamilton product a (x) b, scalar-last (quaternion_utils.py:28-34) */
+  out[0] = a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1];
+  out[1] = a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0];
+  out[2] = a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3];
+  out[3] = a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2];
+}
+
+__global__ void __launch_bounds__(128)
+sdfr_view_poses_kernel(const __grid_constant__ ViewParams P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n_views * P.batch) return;
+  const int v = i / P.batch, b = i - v * P.batch;
+  const float cq[4] = {P.cam_orientation[4 * v], P.cam_orientation[4 * v + 1], P.cam_orientation[4 * v + 2],
+                       P.cam_orientation[4 * v + 3]};
+  const float w2c[4] = {-cq[0], -cq[1], -cq[2], cq[3]};
+  const float d[3] = {P.position[3 * b] - P.cam_position[3 * v], P.position[3 * b + 1] - P.cam_position[3 * v + 1],
+                      P.position[3 * b + 2] - P.cam_position[3 * v + 2]};
+  const float q[4] = {P.unit_orientation[4 * b], P.unit_orientation[4 * b + 1], P.unit_orientation[4 * b + 2],
+                      P.unit_orientation[4 * b + 3]};
+  float pc[3], qc[4];
+  quat_rotate(w2c, d, pc);
+  quat_mul(w2c, q, qc);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) P.position_c[3 * i + k] = pc[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) P.orientation_c[4 * i + k] = qc[k];
+  P.inv_scale_c[i] = P.inv_scale[b];
+}
+
+__global__ void __launch_bounds__(128)
+sdfr_views_pull_back_kernel(const __grid_constant__ ViewParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.batch) return;
+  const bool clear = (P.flags & SDFR_STEP_CLEAR_INPUTS) != 0;
+  float gp[3] = {0.f, 0.f, 0.f}, gq[4] = {0.f, 0.f, 0.f, 0.f}, gis = 0.f, gs = 0.f, l = 0.f;
+  for (int v = 0; v < P.n_views; ++v) {
+    const int i = v * P.batch + b;
+    const float cq[4] = {P.cam_orientation[4 * v], P.cam_orientation[4 * v + 1], P.cam_orientation[4 * v + 2],
+                         P.cam_orientation[4 * v + 3]};
+    float a[3] = {0.f, 0.f, 0.f}, c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      a[k] = (P.gr_position ? P.gr_position[3 * i + k] : 0.f) + (P.g2_position ? P.g2_position[3 * i + k] : 0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      c[k] = (P.gr_orientation ? P.gr_orientation[4 * i + k] : 0.f) + (P.g2_orientation ? P.g2_orientation[4 * i + k] : 0.f);
+    float ra[3], rc[4];
+    quat_rotate(cq, a, ra); /* R(q_w2c)^T = R(camera_orientation) */
+    quat_mul(cq, c, rc);    /* L(q_w2c)^T = L(camera_orientation) */
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gp[k] += ra[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) gq[k] += rc[k];
+    gis += P.gr_inv_scale ? P.gr_inv_scale[i] : 0.f;
+    gs += P.g2_scale ? P.g2_scale[i] : 0.f;
+    if (P.loss_sum && P.n_overlap) {
+      const float n = P.n_overlap[i];
+      /* no overlap in a view: NaN, the reference's mean over an empty selection (:131) */
+      l += n > 0.f ? P.depth_weight * (P.loss_sum[i] / n) : __int_as_float(0x7fc00000);
+    }
+    if (P.point_sum) l += P.point_sum[i];
+    if (clear) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (P.gr_position) P.gr_position[3 * i + k] = 0.f;
+        if (P.g2_position) P.g2_position[3 * i + k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (P.gr_orientation) P.gr_orientation[4 * i + k] = 0.f;
+        if (P.g2_orientation) P.g2_orientation[4 * i + k] = 0.f;
+      }
+      if (P.gr_inv_scale) P.gr_inv_scale[i] = 0.f;
+      if (P.g2_scale) P.g2_scale[i] = 0.f;
+      if (P.loss_sum) P.loss_sum[i] = 0.f;
+      if (P.n_overlap) P.n_overlap[i] = 0.f;
+      if (P.point_sum) P.point_sum[i] = 0.f;
+    }
+  }
+  const float s = P.scale[b];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) P.g_position[3 * b + k] = gp[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) P.g_orientation[4 * b + k] = gq[k];
+  P.g_scale[b] = gs - gis / (s * s); /* d(1/s)/ds */
+  P.loss[b] += l;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Point constraint (estimation/simple_setup.py:164-175, estimation/losses.py:138-153): per hypothesis
+ *     loss = weight * | q (x) (source,0) (x) conj(q) - target |
+ * with q the UN-NORMALISED orientation parameter (quaternion_utils.py:37-54 does not normalise: a
+ * non-unit q also scales by |q|^2, and the gradient below is that function's).  For q = (u, w):
+ *     y   = (w^2 - |u|^2) s + 2 (u.s) u + 2 w (u x s),    d = y - t,   g = d / |d|  (0 at d = 0, torch's
+ *                                                                         subgradient of the norm)
+ *     dL/du = 2 [ (u.s) g + (g.u) s - (g.s) u + w (s x g) ],   dL/dw = 2 [ w (g.s) + g.(u x s) ]
+ * Both outputs are ACCUMULATED (they are sdfr_hypothesis_step's g_orientation_raw / loss_extra).
+ * ---------------------------------------------------------------------------------------- */
+struct ConstraintParams {
+  const float* __restrict__ orientation; /* [B,4] un-normalised */
+  int batch;
+  float source[3], target[3], weight;
+  float* __restrict__ g_orientation_raw; /* [B,4] += or NULL */
+  float* __restrict__ loss;              /* [B]   += or NULL */
+};
+
+__global__ void __launch_bounds__(128)
+sdfr_point_constraint_kernel(const __grid_constant__ ConstraintParams P) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= P.batch) return;
+  const float u[3] = {P.orientation[4 * b], P.orientation[4 * b + 1], P.orientation[4 * b + 2]};
+  const float w = P.orientation[4 * b + 3];
+  const float* s = P.source;
+  const float uu = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+  const float us = u[0] * s[0] + u[1] * s[1] + u[2] * s[2];
+  const float c[3] = {u[1] * s[2] - u[2] * s[1], u[2] * s[0] - u[0] * s[2], u[0] * s[1] - u[1] * s[0]}; /* u x s */
+  float d[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) d[k] = (w * w - uu) * s[k] + 2.0f * us * u[k] + 2.0f * w * c[k] - P.target[k];
+  const float nrm = sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  if (P.loss) P.loss[b] += P.weight * nrm;
+  if (!P.g_orientation_raw) return;
+  const float inv = nrm > 0.0f ? P.weight / nrm : 0.0f;
+  const float g[3] = {d[0] * inv, d[1] * inv, d[2] * inv};
+  const float gs = g[0] * s[0] + g[1] * s[1] + g[2] * s[2];
+  const float gu = g[0] * u[0] + g[1] * u[1] + g[2] * u[2];
+  const float gc = g[0] * c[0] + g[1] * c[1] + g[2] * c[2];
+  const float sg[3] = {s[1] * g[2] - s[2] * g[1], s[2] * g[0] - s[0] * g[2], s[0] * g[1] - s[1] * g[0]}; /* s x g */
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    P.g_orientation_raw[4 * b + k] += 2.0f * (us * g[k] + gu * s[k] - gs * u[k] + w * sg[k]);
+  P.g_orientation_raw[4 * b + 3] += 2.0f * (w * gs + gc);
 }
 
 #endif /* SDFR_STEP_CUH_ */

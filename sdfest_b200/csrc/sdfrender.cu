@@ -1763,8 +1763,8 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
                          float* gr_position, float* gr_orientation, float* gr_inv_scale,
                          float depth_weight, float* point_sum, float point_weight,
                          float* g2_position, float* g2_orientation, float* g2_scale,
-                         float* g_latent, float* exp_avg, float* exp_avg_sq, int* step,
-                         const float* lr, float beta1, float beta2, float eps,
+                         float* g_latent, float* g_orientation_raw, float* loss_extra, float* exp_avg,
+                         float* exp_avg_sq, int* step, const float* lr, float beta1, float beta2, float eps,
                          float* unit_orientation, float* inv_scale, float* loss, unsigned flags,
                          void* stream) {
   if (flags & ~(SDFR_STEP_CLEAR_INPUTS | SDFR_STEP_NO_UPDATE)) return fail(SDFR_E_FLAGS, "unknown flag bits");
@@ -1791,6 +1791,7 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
   P.point_sum = point_sum; P.point_weight = point_weight;
   P.g2_position = g2_position; P.g2_orientation = g2_orientation; P.g2_scale = g2_scale;
   P.g_latent = P.latent_size > 0 ? g_latent : nullptr;
+  P.g_orientation_raw = g_orientation_raw; P.loss_extra = loss_extra;
   P.exp_avg = exp_avg; P.exp_avg_sq = exp_avg_sq; P.step = step;
   if (lr) for (int i = 0; i < 4; ++i) P.lr[i] = lr[i];
   P.beta1 = beta1; P.beta2 = beta2; P.eps = eps;
@@ -1798,6 +1799,68 @@ int sdfr_hypothesis_step(float* position, float* orientation, float* scale, floa
   P.flags = flags;
   sdfr_hypothesis_step_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
   return check_launch("sdfr_hypothesis_step_kernel");
+}
+
+static int view_check(int n_views, int batch) {
+  if (n_views < 0 || batch < 0 || (long long)n_views * batch > (1ll << 30))
+    return fail(SDFR_E_SHAPE, "views: n_views >= 0 and batch >= 0 expected");
+  return 0;
+}
+
+int sdfr_view_poses(const float* position, const float* unit_orientation, const float* inv_scale,
+                    const float* cam_position, const float* cam_orientation, int n_views, int batch,
+                    float* position_c, float* orientation_c, float* inv_scale_c, void* stream) {
+  if (int rc = view_check(n_views, batch)) return rc;
+  if (n_views == 0 || batch == 0) return 0;
+  if (!position || !unit_orientation || !inv_scale || !cam_position || !cam_orientation || !position_c ||
+      !orientation_c || !inv_scale_c)
+    return fail(SDFR_E_NULL, "view poses: NULL pointer");
+  ViewParams P;
+  memset(&P, 0, sizeof(P));
+  P.position = position; P.unit_orientation = unit_orientation; P.inv_scale = inv_scale;
+  P.cam_position = cam_position; P.cam_orientation = cam_orientation;
+  P.n_views = n_views; P.batch = batch;
+  P.position_c = position_c; P.orientation_c = orientation_c; P.inv_scale_c = inv_scale_c;
+  sdfr_view_poses_kernel<<<(n_views * batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("sdfr_view_poses_kernel");
+}
+
+int sdfr_views_pull_back(const float* cam_orientation, const float* scale, int n_views, int batch,
+                         float* gr_position, float* gr_orientation, float* gr_inv_scale, float* g2_position,
+                         float* g2_orientation, float* g2_scale, float* loss_sum, float* n_overlap,
+                         float depth_weight, float* point_sum, float* g_position, float* g_orientation,
+                         float* g_scale, float* loss, unsigned flags, void* stream) {
+  if (int rc = view_check(n_views, batch)) return rc;
+  if (flags & ~SDFR_STEP_CLEAR_INPUTS) return fail(SDFR_E_FLAGS, "unknown flag bits");
+  if (batch == 0) return 0;
+  if (!cam_orientation || !scale || !g_position || !g_orientation || !g_scale || !loss)
+    return fail(SDFR_E_NULL, "views pull back: NULL pointer");
+  if ((loss_sum == nullptr) != (n_overlap == nullptr))
+    return fail(SDFR_E_NULL, "views pull back: loss_sum and n_overlap go together");
+  ViewParams P;
+  memset(&P, 0, sizeof(P));
+  P.cam_orientation = cam_orientation; P.scale = scale; P.n_views = n_views; P.batch = batch;
+  P.gr_position = gr_position; P.gr_orientation = gr_orientation; P.gr_inv_scale = gr_inv_scale;
+  P.g2_position = g2_position; P.g2_orientation = g2_orientation; P.g2_scale = g2_scale;
+  P.loss_sum = loss_sum; P.n_overlap = n_overlap; P.depth_weight = depth_weight; P.point_sum = point_sum;
+  P.g_position = g_position; P.g_orientation = g_orientation; P.g_scale = g_scale; P.loss = loss;
+  P.flags = flags;
+  sdfr_views_pull_back_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("sdfr_views_pull_back_kernel");
+}
+
+int sdfr_point_constraint(const float* orientation, int batch, const float* source, const float* target,
+                          float weight, float* g_orientation_raw, float* loss, void* stream) {
+  if (batch < 0) return fail(SDFR_E_SHAPE, "point constraint: batch >= 0 expected");
+  if (batch == 0) return 0;
+  if (!orientation || !source || !target) return fail(SDFR_E_NULL, "point constraint: NULL pointer");
+  ConstraintParams P;
+  memset(&P, 0, sizeof(P));
+  P.orientation = orientation; P.batch = batch; P.weight = weight;
+  for (int k = 0; k < 3; ++k) { P.source[k] = source[k]; P.target[k] = target[k]; }
+  P.g_orientation_raw = g_orientation_raw; P.loss = loss;
+  sdfr_point_constraint_kernel<<<(batch + 127) / 128, 128, 0, (cudaStream_t)stream>>>(P);
+  return check_launch("sdfr_point_constraint_kernel");
 }
 
 int sdfr_inlier_count(const float* depth, const float* depth_obs, long long obs_stride, int batch,

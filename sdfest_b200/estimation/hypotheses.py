@@ -89,13 +89,15 @@ class HypothesisOptimizer:
     Views: with ``camera_positions`` (V,3) and ``camera_orientations`` (V,4) (camera-to-world, as
     SDFPipeline.__call__ takes them) ``depth_obs`` is (V,H,W), one image per view of the SAME object;
     the pose is optimised in the world frame, moved into every camera frame (``estimation/views.py``,
-    simple_setup.py:423-431) and the per-view losses are summed (:432-446).  This mode composes the
-    package's autograd operators (``optimizer="torch"``); the inlier ratio is evaluated on the last
-    view, as the reference's loop variables leave it (:463).
+    simple_setup.py:423-431) and the per-view losses are summed (:432-446); the inlier ratio is
+    evaluated on the last view, as the reference's loop variables leave it (:463).  On the fused path
+    the rigid maps and their adjoint are two tiny kernels (``sdfr_view_poses``,
+    ``sdfr_views_pull_back``) around V batched render / compare / point-loss launches that accumulate
+    the normalised SDF gradients of all views into ONE gradient grid per hypothesis.
 
     ``point_constraint`` = (source (3,), target (3,), weight) adds ``weight * |R(orientation) source -
-    target|`` on the un-normalised orientation (simple_setup.py:164-175, losses.py:138-153); like the
-    views it runs on the autograd-composed path.
+    target|`` on the un-normalised orientation (simple_setup.py:164-175, losses.py:138-153):
+    ``sdfr_point_constraint`` on the fused path.
 
     Result selection: with ``inlier_threshold`` (the reference's ``relative_inlier_threshold``, 0.03)
     every iteration also evaluates the inlier ratio of simple_setup.py:177-188 -- on the depth rendered
@@ -133,7 +135,6 @@ class HypothesisOptimizer:
             raise ValueError("give camera_positions and camera_orientations together")
         multiview = camera_positions is not None
         can_fuse = position.is_cuda and (decoder is None or isinstance(decoder, FusedTailDecoder)) \
-            and not multiview and point_constraint is None \
             and (latent is None or int(latent.shape[1]) <= 64)  # sdfr_hypothesis_step: kStepMaxLatent
         # (source (3,), target (3,), weight): simple_setup.py:164-175, 224, 299
         self.point_constraint = None
@@ -143,8 +144,8 @@ class HypothesisOptimizer:
                                      torch.as_tensor(target, dtype=torch.float32, device=position.device),
                                      float(weight))
         if optimizer == "fused" and not can_fuse:
-            raise ValueError("optimizer='fused' needs CUDA tensors, fixed grids or a FusedTailDecoder, "
-                             "a single view and no point constraint")
+            raise ValueError("optimizer='fused' needs CUDA tensors and fixed grids or a FusedTailDecoder "
+                             "(latent size <= 64)")
         self.optimizer_impl = "fused" if (optimizer != "torch" and can_fuse) else "torch"
         self.overlap = bool(overlap)
         # corner weights of the SDF gradient: the module default at construction time
@@ -220,7 +221,7 @@ class HypothesisOptimizer:
             self.best_latent = None if self.latent is None else self.latent.detach().clone()
             self._iteration = torch.zeros(B, dtype=torch.int32, device=dev0)  # optimizer="torch" (device-side: survives graph replay)
             # valid pixels depend on the observation alone (simple_setup.py:186): counted once
-            if self.optimizer_impl == "fused" and self.inlier_threshold <= 1.0:  # larger: sdfr_inlier_count recounts both
+            if self.optimizer_impl == "fused" and self.inlier_threshold <= 1.0 and not multiview:  # else: sdfr_inlier_count recounts both
                 n_valid = (self.depth_obs != 0).flatten(-2).sum(-1).to(torch.float32)
                 self._inl[1].copy_(n_valid.expand(B) if n_valid.dim() == 0 else n_valid)
         self._graph = None
@@ -244,21 +245,39 @@ class HypothesisOptimizer:
         L = 0 if self.latent is None else int(self.latent.shape[1])
         self._L = L
         W, H = int(self.camera.width), int(self.camera.height)
-        if tuple(self.depth_obs.shape) == (H, W):
+        V = 0 if self._views is None else int(self.depth_obs.shape[0])
+        self._V = V
+        if V:
+            if tuple(self.depth_obs.shape[1:]) != (H, W):
+                raise RuntimeError(f"depth_obs must have shape (V,{H},{W})")
+            self._obs_stride = 0
+        elif tuple(self.depth_obs.shape) == (H, W):
             self._obs_stride = 0
         elif tuple(self.depth_obs.shape) == (B, H, W):
             self._obs_stride = H * W
         else:
             raise RuntimeError(f"depth_obs must have shape ({H},{W}) or ({B},{H},{W})")
         # every small per-hypothesis buffer in one allocation: consumed AND cleared by the step kernel
-        small = torch.zeros(20 * B, dtype=torch.float32, device=dev)
+        # (with views: [V,B,...] each, consumed and cleared by sdfr_views_pull_back)
+        NB = max(V, 1) * B
+        small = torch.zeros(20 * NB, dtype=torch.float32, device=dev)
         cuts = (("loss_sum", 1), ("n_overlap", 1), ("gr_p", 3), ("gr_q", 4), ("gr_is", 1),
                 ("pl", 1), ("g2_p", 3), ("g2_q", 4), ("g2_s", 1))
         off, self._buf = 0, {}
         for name, k in cuts:
-            self._buf[name] = small[off:off + k * B]
-            off += k * B
+            self._buf[name] = small[off:off + k * NB]
+            off += k * NB
         self._small = small
+        # gradient w.r.t. the un-normalised orientation and a loss term taken as is: the point constraint
+        # and (loss only) the view loop's sum; consumed and cleared by the step kernel
+        self._g_raw = self._loss_extra = None
+        if self.point_constraint is not None or V:
+            extra = torch.zeros(5 * B, dtype=torch.float32, device=dev)
+            self._g_raw, self._loss_extra = extra[:4 * B], extra[4 * B:]
+        if self.point_constraint is not None:
+            src, tgt, _ = self.point_constraint
+            self._pc_src = (ctypes.c_float * 3)(*[float(x) for x in src.tolist()])
+            self._pc_tgt = (ctypes.c_float * 3)(*[float(x) for x in tgt.tolist()])
         self._unit_q = torch.empty((B, 4), dtype=torch.float32, device=dev)
         self._inv_scale = torch.empty((B,), dtype=torch.float32, device=dev)
         self._loss = torch.zeros((B,), dtype=torch.float32, device=dev)
@@ -268,6 +287,19 @@ class HypothesisOptimizer:
         self._lr = (ctypes.c_float * 4)(*self.lrs)
         self._depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
         M = int(self.points.shape[-2]) if self.pc_weight else 0
+        if V:
+            # per view: camera-frame poses, the pulled-back gradients, and each view's own cloud weighted
+            # with pc_weight / (its number of points) in the loss and the gradients
+            M = 0  # the single-view point buffers of the step kernel stay unused
+            self._pose_c = (torch.empty((V, B, 3), dtype=torch.float32, device=dev),
+                            torch.empty((V, B, 4), dtype=torch.float32, device=dev),
+                            torch.empty((V, B), dtype=torch.float32, device=dev))
+            pb = torch.zeros(8 * B, dtype=torch.float32, device=dev)
+            self._pb = (pb[:3 * B], pb[3 * B:7 * B], pb[7 * B:])
+            self._view_M = [int(p.shape[0]) if self.pc_weight else 0 for p in self._view_points]
+            self._view_points = [p.contiguous() for p in self._view_points]
+            self._view_up_p = [torch.full((B,), self.pc_weight / m if m else 0.0, dtype=torch.float32, device=dev)
+                               for m in self._view_M]
         self._M = M
         if self.point_counts is None:
             self._points_stride, self._point_flags = 0, 0
@@ -294,33 +326,143 @@ class HypothesisOptimizer:
             SK = _skewed_elems(R)
             self._grid_op = (torch.empty((B, SK), dtype=torch.float32, device=dev), SK, _lib.LAYOUT_SKEWED)
             # both gradient grids in one allocation: one clear per iteration
+            # (views: the normalised gradients of every view and cloud accumulate into the first one)
             self._g_both = torch.empty((2 if M else 1, B, R ** 3), dtype=torch.float32, device=dev)
             self._g_sdf = self._g_both[0]
             self._g_sdf_pc = self._g_both[1] if M else None
         from ..differentiable_renderer.sdf_renderer import get_empty_space_policy
         n_grids = 1 if self._grid_op[1] == 0 else B
         self._bounds = None if get_empty_space_policy() == "off" else \
-            torch.empty((n_grids, 8), dtype=torch.int32, device=dev)
+            torch.empty((max(V, 1), n_grids, 8), dtype=torch.int32, device=dev)
         # second stream: the point loss runs beside the render (both only read the grids), the
         # gradient-grid clears beside the decoder trunk; forks and joins are captured by capture()
         self._side = torch.cuda.Stream(dev) if self.overlap else None
         self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale for the first render
 
-    def _hyp_step(self, flags: int, g_latent: Optional[torch.Tensor] = None) -> None:
+    def _hyp_step(self, flags: int, g_latent: Optional[torch.Tensor] = None,
+                  g_orientation_raw: Optional[torch.Tensor] = None,
+                  loss_extra: Optional[torch.Tensor] = None) -> None:
         b, B = self._buf, self.position.shape[0]
         M = self._M
+        if self._V:
+            # the per-view sums were folded into (g_position, g_orientation, g_scale, loss_extra) by
+            # sdfr_views_pull_back: they enter as the already weighted second gradient set
+            raw = (None,) * 5
+            g2 = tuple(t.data_ptr() for t in self._pb)
+            pl = None
+        else:
+            raw = (b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), b["gr_p"].data_ptr(),
+                   b["gr_q"].data_ptr(), b["gr_is"].data_ptr())
+            g2 = (b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr()) if M else (None,) * 3
+            pl = b["pl"].data_ptr() if M else None
         _lib.check(_lib.lib().sdfr_hypothesis_step(
             self.position.data_ptr(), self.orientation.data_ptr(), self.scale.data_ptr(),
-            _ptr(self.latent), self._L, B, b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(),
-            b["gr_p"].data_ptr(), b["gr_q"].data_ptr(), b["gr_is"].data_ptr(), float(self.depth_weight),
-            b["pl"].data_ptr() if M else None, self._point_weight,
-            b["g2_p"].data_ptr() if M else None, b["g2_q"].data_ptr() if M else None,
-            b["g2_s"].data_ptr() if M else None, _ptr(g_latent), self._m.data_ptr(),
+            _ptr(self.latent), self._L, B, *raw, float(self.depth_weight),
+            pl, self._point_weight, *g2, _ptr(g_latent), _ptr(g_orientation_raw), _ptr(loss_extra),
+            self._m.data_ptr(),
             self._v.data_ptr(), self._t.data_ptr(), self._lr, self.betas[0], self.betas[1], self.eps,
             self._unit_q.data_ptr(), self._inv_scale.data_ptr(), self._loss.data_ptr(), flags,
             _stream()), "sdfr_hypothesis_step")
 
+    def _constraint_launch(self) -> None:
+        """sdfr_point_constraint on the un-normalised orientation: += into g_raw / loss_extra."""
+        if self.point_constraint is None:
+            return
+        _lib.check(_lib.lib().sdfr_point_constraint(
+            self.orientation.data_ptr(), self.position.shape[0], self._pc_src, self._pc_tgt,
+            self.point_constraint[2], self._g_raw.data_ptr(), self._loss_extra.data_ptr(), _stream()),
+            "sdfr_point_constraint")
+
+    def _fused_views_iteration(self) -> torch.Tensor:
+        """One iteration over V views of the same object (simple_setup.py:408-463) as C-ABI launches:
+        decoder tail -> camera-frame poses -> per view {bounds, render + compare, its backward with the
+        1/n_overlap normalisation, point loss} -> pull-back to the world frame -> tail adjoint -> step."""
+        lib, b = _lib.lib(), self._buf
+        B, R, V = self.position.shape[0], self._R, self._V
+        W, H, cx, cy, fx, fy = _camera_params(self.camera)
+        grids, gstride, layout = self._grid_op
+        dec, x = self.decoder, None
+        flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
+        if dec is not None:
+            self._g_both.zero_()
+            x = dec.trunk(self.latent).contiguous()
+            w, bias = dec.tail_parameters()
+            C, S = int(x.shape[1]), int(x.shape[2])
+            _lib.check(lib.sdfr_decoder_tail_forward(
+                x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
+                gstride, layout, _stream()), "sdfr_decoder_tail_forward")
+            flags |= _lib.GRAD_SDF
+        render_flags = flags | (_lib.SDF_GRAD_EXACT if self.sdf_grad_mode == "exact" else 0)
+        cam_p, cam_q = self._views
+        pos_c, ori_c, isc_c = self._pose_c
+        _lib.check(lib.sdfr_view_poses(
+            self.position.data_ptr(), self._unit_q.data_ptr(), self._inv_scale.data_ptr(), cam_p.data_ptr(),
+            cam_q.data_ptr(), V, B, pos_c.data_ptr(), ori_c.data_ptr(), isc_c.data_ptr(), _stream()),
+            "sdfr_view_poses")
+        g_sdf = _ptr(self._g_sdf)
+
+        def view(t, v, k):  # slice v of a [V, B*k] buffer
+            return t.data_ptr() + 4 * v * B * k
+
+        for v in range(V):
+            p_v, q_v, is_v = pos_c[v].data_ptr(), ori_c[v].data_ptr(), isc_c[v].data_ptr()
+            obs = self.depth_obs[v].data_ptr()
+            bounds = None
+            if self._bounds is not None:
+                bounds = self._bounds[v].data_ptr()
+                _lib.check(lib.sdfr_grid_bounds(grids.data_ptr(), R, gstride, layout, p_v, is_v, B,
+                                                self.threshold, bounds, _stream()), "sdfr_grid_bounds")
+            _lib.check(lib.sdfr_compare_forward(
+                grids.data_ptr(), R, gstride, layout, p_v, q_v, is_v, B, W, H, cx, cy, fx, fy, self.threshold,
+                obs, 0, self._depth.data_ptr(), view(b["loss_sum"], v, 1), view(b["n_overlap"], v, 1), 0,
+                bounds, _stream()), "sdfr_compare_forward")
+            # upstream = depth_weight: the gradients arrive weighted and normalised by this view's overlap
+            _lib.check(lib.sdfr_compare_backward(
+                self._depth.data_ptr(), obs, 0, view(b["n_overlap"], v, 1), self._up_d.data_ptr(),
+                grids.data_ptr(), R, gstride, layout, p_v, q_v, is_v, B, W, H, cx, cy, fx, fy, g_sdf, R ** 3,
+                view(b["gr_p"], v, 3), view(b["gr_q"], v, 4), view(b["gr_is"], v, 1), render_flags, bounds,
+                _stream()), "sdfr_compare_backward")
+            if self._view_M[v]:
+                _lib.check(lib.sdfr_point_loss_fused(
+                    self._view_points[v].data_ptr(), 0, self._view_M[v], grids.data_ptr(), R, gstride, layout,
+                    p_v, q_v, self.scale.data_ptr(), B, self._view_up_p[v].data_ptr(), view(b["pl"], v, 1),
+                    g_sdf, R ** 3, view(b["g2_p"], v, 3), view(b["g2_q"], v, 4), view(b["g2_s"], v, 1),
+                    flags | _lib.LOSS_WEIGHTED, _stream()), "sdfr_point_loss_fused")
+        if self.inlier_threshold is not None:  # on the last view's estimate (:463)
+            _lib.check(lib.sdfr_inlier_count(
+                self._depth.data_ptr(), self.depth_obs[V - 1].data_ptr(), 0, B, W, H, self.inlier_threshold,
+                self._inl[0].data_ptr(), self._inl[1].data_ptr(), 0, _stream()), "sdfr_inlier_count")
+        g_p, g_q, g_s = self._pb
+        _lib.check(lib.sdfr_views_pull_back(
+            cam_q.data_ptr(), self.scale.data_ptr(), V, B, b["gr_p"].data_ptr(), b["gr_q"].data_ptr(),
+            b["gr_is"].data_ptr(), b["g2_p"].data_ptr(), b["g2_q"].data_ptr(), b["g2_s"].data_ptr(),
+            b["loss_sum"].data_ptr(), b["n_overlap"].data_ptr(), float(self.depth_weight), b["pl"].data_ptr(),
+            g_p.data_ptr(), g_q.data_ptr(), g_s.data_ptr(), self._loss_extra.data_ptr(),
+            _lib.STEP_CLEAR_INPUTS, _stream()), "sdfr_views_pull_back")
+        self._constraint_launch()
+        g_latent = None
+        if dec is not None:
+            g_x = torch.empty_like(x)
+            _lib.check(lib.sdfr_decoder_tail_backward(
+                g_sdf, R ** 3, None, None, None, 0, w.data_ptr(), C, S, B, R, g_x.data_ptr(), _stream()),
+                "sdfr_decoder_tail_backward")
+            (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
+            g_latent = g_latent.contiguous()
+        self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent, self._g_raw, self._loss_extra)
+        if self.inlier_threshold is not None:
+            _lib.check(lib.sdfr_track_best(
+                self._inl[0].data_ptr(), self._inl[1].data_ptr(), self.position.data_ptr(),
+                self.orientation.data_ptr(), self.scale.data_ptr(), _ptr(self.latent), self._L, B,
+                self._t.data_ptr(), self.inlier_ratio.data_ptr(), self.best_inlier_ratio.data_ptr(),
+                self.best_iteration.data_ptr(), self.best_position.data_ptr(),
+                self.best_orientation.data_ptr(), self.best_scale.data_ptr(), _ptr(self.best_latent),
+                _lib.STEP_CLEAR_INPUTS, _stream()), "sdfr_track_best")
+        self.last_losses = self._loss
+        return self.last_losses
+
     def _fused_iteration(self) -> torch.Tensor:
+        if self._V:
+            return self._fused_views_iteration()
         lib, b = _lib.lib(), self._buf
         B, R, M = self.position.shape[0], self._R, self._M
         W, H, cx, cy, fx, fy = _camera_params(self.camera)
@@ -357,6 +499,7 @@ class HypothesisOptimizer:
         # empty-space bounds of this iteration's grids and poses (the hit-threshold bound depends on
         # position and scale): rays that cannot hit anything are not marched, all others unchanged
         bounds = None
+        self._constraint_launch()
         if self._bounds is not None:
             _lib.check(lib.sdfr_grid_bounds(
                 grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._inv_scale.data_ptr(), B,
@@ -412,7 +555,7 @@ class HypothesisOptimizer:
                 "sdfr_decoder_tail_backward")
             (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
             g_latent = g_latent.contiguous()
-        self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent)
+        self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent, self._g_raw, self._loss_extra)
         if self.inlier_threshold is not None:
             if side is not None and not inl_fused:
                 main.wait_stream(side)

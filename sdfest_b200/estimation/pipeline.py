@@ -8,12 +8,14 @@ section 8: model files and their download, yoco configs, matplotlib visualisatio
 writers, SO3 priors) is not rebuilt: the networks are handed in as modules, and the arguments that
 drive those subsystems raise ``NotImplementedError`` instead of being silently ignored.
 
-The loop itself is ``HypothesisOptimizer`` with one hypothesis: on CUDA tensors, for one view in the
-camera frame and without a point constraint, that is the fused iteration (decoder trunk + fused tail,
-``sdfr_compare_fused_inliers``, ``sdfr_point_loss_fused``, tail adjoint, ``sdfr_hypothesis_step``,
-``sdfr_track_best``), replayed from a CUDA graph; several views, camera poses or a point constraint run
-on the autograd-composed operators.  ``n_hypotheses`` > 1 (an extension) perturbs the initial pose and
-returns the hypothesis with the lowest final loss.
+The loop itself is ``HypothesisOptimizer`` with one hypothesis: on CUDA tensors that is the fused
+iteration (decoder trunk + fused tail, ``sdfr_compare_fused_inliers``, ``sdfr_point_loss_fused``, tail
+adjoint, ``sdfr_hypothesis_step``, ``sdfr_track_best``; with several views or camera poses
+``sdfr_view_poses`` / per-view render, compare and point loss / ``sdfr_views_pull_back``; with a point
+constraint ``sdfr_point_constraint``), replayed from a CUDA graph.  A decoder that does not end in
+interpolate-to-volume + 1x1x1 convolution runs through ``vae.decode`` and the autograd-composed
+operators.  ``n_hypotheses`` > 1 (an extension) perturbs the initial pose and returns the best
+hypothesis: highest best inlier ratio under ``best_inlier_ratio``, else lowest final loss.
 """
 from __future__ import annotations
 
@@ -111,8 +113,12 @@ class SDFPipeline:
         if on_cuda and self.config.get("fused_decoder", True):
             if self._fused_decoder is None:
                 dec = self.vae.decoder
-                self._fused_decoder = dec if isinstance(dec, FusedTailDecoder) else FusedTailDecoder(dec)
-            return self._fused_decoder
+                try:
+                    self._fused_decoder = dec if isinstance(dec, FusedTailDecoder) else FusedTailDecoder(dec)
+                except ValueError:  # no interpolate + 1x1x1 tail to fuse: the plain decoder
+                    self._fused_decoder = False
+            if self._fused_decoder is not False:
+                return self._fused_decoder
         return self.vae.decode
 
     # ------------------------------------------------------------------------------------------
@@ -165,8 +171,7 @@ class SDFPipeline:
                   max_points=int(self.config.get("max_points", 0)),
                   inlier_threshold=self._relative_inlier_threshold, point_constraint=point_constraint)
         if shape_optimization:
-            kw.update(latent=latent, decoder=self._decoder(position.is_cuda and world_is_camera
-                                                           and point_constraint is None))
+            kw.update(latent=latent, decoder=self._decoder(position.is_cuda))
         else:
             with torch.no_grad():
                 kw.update(sdf=self.vae.decode(latent)[:, 0].contiguous())
@@ -188,7 +193,10 @@ class SDFPipeline:
         if latent_out is None:
             latent_out = latent
         if n_hyp > 1:
-            best = int(torch.argmin(torch.nan_to_num(opt.last_losses, nan=float("inf"))))
+            if self.result_selection_strategy == "best_inlier_ratio":
+                best = int(torch.argmax(torch.nan_to_num(opt.best_inlier_ratio, nan=-1.0)))
+            else:
+                best = int(torch.argmin(torch.nan_to_num(opt.last_losses, nan=float("inf"))))
             position, orientation = position[best:best + 1], orientation[best:best + 1]
             scale, latent_out = scale[best:best + 1], latent_out[best:best + 1]
         return position, orientation, scale, latent_out

@@ -222,6 +222,62 @@ def test_reference_pipeline_on_both_native_modules_and_ours(cuda_device, ref_ext
 
 @pytest.mark.gpu
 @needs_reference
+def test_pipeline_with_views_and_point_constraint_matches_the_reference(cuda_device, ref_ext, tmp_path):
+    """Two views with camera poses and a point constraint (simple_setup.py:164-175, 420-446): the reference's
+    pipeline on ITS OWN extension against this package's SDFPipeline, where all of it runs on the fused
+    path (sdfr_view_poses, per-view render / compare / point loss, sdfr_views_pull_back,
+    sdfr_point_constraint, one sdfr_hypothesis_step) from a CUDA graph."""
+    from sdfest_b200.differentiable_renderer import Camera, render_depth_gpu
+    from sdfest_b200.estimation import SDFPipeline, views
+
+    dev = cuda_device
+    vae_path, vae_yaml = os.path.join(ref_loader.FIXTURES, "mug.pt"), os.path.join(ref_loader.FIXTURES, "mug.yaml")
+    init_path = str(tmp_path / "init.pt")
+    depth0, q_true = _observation(dev, vae_path, vae_yaml)
+    iterations = 20
+    cfg = _pipeline_config(init_path, vae_yaml, vae_path, iterations)
+    cam_p = torch.tensor([[0.0, 0.0, 0.0], [0.10, 0.02, -0.04]], device=dev)
+    cam_q = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 0.0, 1.0], [0.02, 0.14, 0.01, 1.0]], device=dev), dim=1)
+    constraint = (torch.tensor([0.0, 1.0, 0.0], device=dev), torch.tensor([0.05, 0.95, 0.1], device=dev), 0.02)
+
+    ref_loader.load_reference(ref_ext)
+    cudnn = torch.backends.cudnn.enabled
+    try:
+        setup = importlib.import_module("sdfest.estimation.simple_setup")
+        _make_init_weights(setup, cfg, q_true, init_path)
+        pipe = setup.SDFPipeline(cfg)
+        # the second view: the same object (true latent / pose of _observation) seen from camera 1
+        z_true = torch.tensor([[0.4, -0.3, 0.2, 0.0, -0.5, 0.3, 0.1, -0.2]], device=dev)
+        with torch.no_grad():
+            sdf = pipe.vae.decode(z_true)[0, 0].contiguous()
+        p_c, q_c = views.to_camera_frames(torch.tensor([[0.02, -0.01, -0.45]], device=dev),
+                                          torch.as_tensor(q_true, device=dev, dtype=torch.float32)[None], cam_p, cam_q)
+        depth1 = render_depth_gpu(sdf, p_c[1, 0].contiguous(), q_c[1, 0].contiguous(), torch.tensor([1 / 0.15], device=dev),
+                                  threshold=0.005, camera=Camera(**CAMERA))
+        assert int((depth1 > 0).sum()) > 3000
+        depths = torch.stack([depth0, depth1]).contiguous()
+        d = depths.clone()
+        theirs = pipe(d, d > 0, torch.zeros(*d.shape, 3, device=dev), camera_positions=cam_p.clone(),
+                      camera_orientations=cam_q.clone(), point_constraint=constraint)
+        theirs = tuple(t.detach().clone() for t in theirs)
+        vae, init_network = pipe.vae, pipe.init_network
+    finally:
+        torch.backends.cudnn.enabled = cudnn
+        ref_loader.purge()
+
+    mine = SDFPipeline(dict(cfg, relative_inlier_threshold=0.03), vae, init_network)
+    d = depths.clone()
+    got = mine(d, d > 0, None, camera_positions=cam_p, camera_orientations=cam_q, point_constraint=constraint)
+    opt = mine.last_optimizer
+    assert opt.optimizer_impl == "fused" and opt._V == 2 and opt._graph is not None
+    tol = dict(position=2e-3, orientation=1e-2, scale=2e-3, latent=5e-2)  # absolute; chaotic Adam steps
+    for a, b, nm in zip(got, theirs, ("position", "orientation", "scale", "latent")):
+        assert tuple(a.shape) == tuple(b.shape), (nm, a.shape, b.shape)
+        assert float((a - b).abs().max()) <= tol[nm], (nm, a, b)
+
+
+@pytest.mark.gpu
+@needs_reference
 def test_reference_view_dataset_on_the_shim(cuda_device):
     """initialization/datasets/generated_dataset.py:277-284 calls render_depth_gpu with keyword arguments
     and no gradient; one sample through the unmodified class."""

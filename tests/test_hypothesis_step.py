@@ -124,7 +124,7 @@ def test_step_kernel_matches_oracle(cuda_device, B, L, with_points):
         _lib.check(lib.sdfr_hypothesis_step(
             p(d["position"]), p(d["orientation"]), p(d["scale"]), p(d["latent"]), L, B,
             p(d["loss_sum"]), p(d["n_overlap"]), p(d["gr_p"]), p(d["gr_q"]), p(d["gr_is"]), 1.0,
-            p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]),
+            p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]), None, None,
             p(m), p(v), p(t), lr, 0.9, 0.999, 1e-8, p(unit), p(inv), p(loss), 0, None), "step")
     torch.cuda.synchronize()
     st, unit_o, inv_o, loss_o = _oracle_run(case32, steps, 1.0, 0.01, L)
@@ -143,7 +143,7 @@ def test_step_kernel_matches_oracle(cuda_device, B, L, with_points):
     _lib.check(lib.sdfr_hypothesis_step(
         p(d["position"]), p(d["orientation"]), p(d["scale"]), p(d["latent"]), L, B,
         p(d["loss_sum"]), p(d["n_overlap"]), p(d["gr_p"]), p(d["gr_q"]), p(d["gr_is"]), 1.0,
-        p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]),
+        p(d["point_sum"]), 0.01, p(d["g2_p"]), p(d["g2_q"]), p(d["g2_s"]), p(d["g_latent"]), None, None,
         p(m), p(v), p(t), lr, 0.9, 0.999, 1e-8, p(unit), p(inv), p(loss),
         _lib.STEP_NO_UPDATE | _lib.STEP_CLEAR_INPUTS, None), "step")
     torch.cuda.synchronize()
@@ -164,16 +164,16 @@ def test_step_kernel_argument_errors(cuda_device):
     lr = (ctypes.c_float * 4)(*LRS)
     a = x.data_ptr()
     assert lib.sdfr_hypothesis_step(None, a, a, None, 0, 1, None, None, None, None, None, 1.0, None, 0.0,
-                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, None, None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
                                     None, 0, None) == -1
     assert lib.sdfr_hypothesis_step(a, a, a, None, 65, 1, None, None, None, None, None, 1.0, None, 0.0,
-                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, None, None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
                                     None, 0, None) == -2
     assert lib.sdfr_hypothesis_step(a, a, a, None, 0, 1, None, None, None, None, None, 1.0, None, 0.0,
-                                    None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
+                                    None, None, None, None, None, None, a, a, a, lr, 0.9, 0.999, 1e-8, None, None,
                                     None, 0x1, None) == -3
     assert lib.sdfr_hypothesis_step(a, a, a, None, 0, 0, None, None, None, None, None, 1.0, None, 0.0,
-                                    None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8,
+                                    None, None, None, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8,
                                     None, None, None, 0, None) == 0
 
 
