@@ -123,11 +123,26 @@ typedef struct sdfr_cell_bounds {
  * One entry per grid: bounds[b] for grid sdf + b*sdf_stride, a single entry (valid for all `batch`
  * hypotheses) when sdf_stride == 0.  position / inv_scale / threshold are those of the render that
  * will use the bounds (tau depends on them); an entry is ignored by a render whose own tau is larger.
- * Cost: one read of the grids (~8 us for 64 x 64^3 on a B200).
+ * Cost: one streaming read of the grids.
  */
 int sdfr_grid_bounds(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
                      const float* position, const float* inv_scale, int batch, float threshold,
                      sdfr_cell_bounds* bounds, void* stream);
+
+/*
+ * The same bounds for grids that do not change between renders (fixed shapes, pose-only optimisation):
+ * sdfr_grid_slab_minima reads the grids ONCE and keeps, per grid and axis, the smallest voxel value of
+ * every slab -- minima [n_grids, 3, resolution] (x, y, z), pose independent; sdfr_bounds_from_minima
+ * then derives the cell bounds of the current poses from 3 * resolution comparisons per grid (the box of
+ * the cells below tau is the bounding box of the voxels below tau, low side moved down by one cell).
+ * n_grids = batch (bounds[b] for hypothesis b) or 1 (one shared grid, one entry, tau = max over the
+ * batch).  Results are identical to sdfr_grid_bounds.
+ */
+int sdfr_grid_slab_minima(const float* sdf, int resolution, long long sdf_stride, int sdf_layout,
+                          int n_grids, float* minima, void* stream);
+int sdfr_bounds_from_minima(const float* minima, int resolution, int n_grids, const float* position,
+                            const float* inv_scale, int batch, float threshold,
+                            sdfr_cell_bounds* bounds, void* stream);
 
 /*
  * sdfr_skew_grids and sdfr_grid_bounds in ONE read of the dense grids: writes the skewed copies and

@@ -41,6 +41,8 @@ SIGNATURES = {
     "sdfr_max_steps": (c_int, []),
     # the trailing (_P, _P) of the render entry points are (bounds or NULL, stream)
     "sdfr_grid_bounds": (c_int, [_P, c_int, c_longlong, c_int, _P, _P, c_int, c_float, _P, _P]),
+    "sdfr_grid_slab_minima": (c_int, [_P, c_int, c_longlong, c_int, c_int, _P, _P]),
+    "sdfr_bounds_from_minima": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_float, _P, _P]),
     "sdfr_skew_grids_bounds": (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P, _P, c_float, _P, _P]),
     "sdfr_forward": (c_int, [_P, c_int, c_longlong, c_int, *_POSE, c_int, *_CAM, c_float, _P, _P, _P]),
     "sdfr_forward_stats": (

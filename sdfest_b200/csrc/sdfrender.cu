@@ -912,105 +912,214 @@ __global__ void sdfr_bounds_init_kernel(const float* __restrict__ pos, const flo
   }
 }
 
-/* CTA = (x cell layer ix, block of 8 row strips, grid n); a warp owns a strip of kBoundsRows cell rows.
- * Lane l holds, for each of the strip's kBoundsRows + 1 voxel rows, the voxel-layer-pair minimum at
- * z = z0 + 2l, z0 + 2l + 1 (64 values = 63 cells per warp step): ALL loads of the strip are issued
- * before the first use (36 independent loads per thread), then the y-pair minimum is a min of two
- * registers and the z-pair minimum one min in the thread and one shuffle -- ~0.3 instructions per
- * cell, no shared memory.
- * History (ncu r02e, bench r02d/r02f): a shared-memory plane with 4 neighbour reads per cell was
- * issue-bound at 43 us for 64 x 64^3; walking the rows with the loads inside the loop that also votes
- * was latency-bound at 54 us (the votes keep the compiler from hoisting the next rows' loads).
- * WRITE_SKEW: the source is the DENSE grid and the kernel also writes the skewed copy (each voxel by the
- * warp that owns it), so that the layout pass and the bounds pass are one read of the grids. */
-constexpr int kBoundsRows = 4;
+/* The scan.  A cell's smallest corner is below tau exactly when one of its 8 corner VOXELS is, and a
+ * voxel x belongs to the cells x-1 and x of its axis (clamped to [0, R-2]), independently per axis; so
+ * the box of the cells below tau is the bounding box of the voxels below tau with its low side moved
+ * down by one:   lo = max(min_voxel - 1, 0),   hi = min(max_voxel, R - 2).
+ * That makes the pass a streaming read -- every voxel loaded once, coalesced, one compare -- instead of
+ * a stencil over cell corners (history: a shared-memory plane with 4 neighbour reads per cell was
+ * issue-bound at 43 us for 64 x 64^3; a register walk over row strips with shuffles for the z pairs,
+ * 34 M warp instructions, 42 us at 67 % ALU-pipe utilisation, ncu r02e).
+ * CTA = (voxel layer ix, grid n): warp w walks rows y = w, w + 8, ..., lane = z.
+ * WRITE_SKEW: the source is the DENSE grid and the kernel also writes the skewed copy, so that the
+ * layout pass and the bounds pass are one read of the grids. */
+__device__ __forceinline__ void bounds_commit(CellBounds* __restrict__ o, int axis, int vlo, int vhi, int R) {
+  atomicMin(&o->lo[axis], vlo > 0 ? vlo - 1 : 0);
+  atomicMax(&o->hi[axis], vhi < R - 2 ? vhi : R - 2);
+}
+
+constexpr int kScanUnroll = 4;
 
 template <bool WRITE_SKEW>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256)
 sdfr_bounds_scan_kernel(const float* __restrict__ sdf, long long sdf_stride, int R, int py, int px,
                         CellBounds* __restrict__ out, float* __restrict__ skew, long long skew_stride,
                         int spy, int spx) {
   __shared__ int s_lo[2], s_hi[2];
-  const int n = blockIdx.z, ix = blockIdx.x;
+  const int n = blockIdx.y, ix = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* __restrict__ g0 = sdf + (size_t)n * sdf_stride + (size_t)ix * px;
-  const float* __restrict__ g1 = g0 + px;
   float* __restrict__ d0 = WRITE_SKEW ? skew + (size_t)n * skew_stride + (size_t)ix * spx : nullptr;
-  const bool last_layer = ix == R - 2; /* this CTA also owns voxel layer R-1 */
   const float tau = out[n].tau;
   if (threadIdx.x < 2) {
     s_lo[threadIdx.x] = 0x7fffffff;
     s_hi[threadIdx.x] = -1;
   }
   __syncthreads();
-  const int y_begin = ((int)blockIdx.y * kWarps + warp) * kBoundsRows;
   int ylo = 0x7fffffff, yhi = -1, zlo = 0x7fffffff, zhi = -1;
-  if (y_begin < R - 1) {
-    for (int z0 = 0; z0 < R - 1; z0 += 63) { /* values z0 .. z0 + 63 give cells z0 .. z0 + 62 */
-      const int za = z0 + 2 * lane, zb = za + 1;
-      const bool oka = za < R, okb = zb < R;
-      float a0[kBoundsRows + 1], a1[kBoundsRows + 1], b0[kBoundsRows + 1], b1[kBoundsRows + 1];
+  /* dense rows of a multiple of 4 voxels: 16-byte loads, lane = 4 consecutive z */
+  const bool vec = (R & 3) == 0 && py == R && (px & 3) == 0 && (sdf_stride & 3) == 0 &&
+                   (reinterpret_cast<uintptr_t>(sdf) & 15) == 0;
+  if (vec) {
+    const int q4 = R >> 2; /* float4 per row */
+    const int rows_per_pass = 256 / q4; /* R <= 1024: q4 <= 256 */
+    const int sub = threadIdx.x / q4, zq = threadIdx.x - sub * q4;
+    if (sub < rows_per_pass) {
+      /* kScanUnroll independent 16-byte loads in flight per thread (the pass is latency-bound otherwise:
+       * one dependent round trip per row) */
+      for (int y0 = sub; y0 < R; y0 += rows_per_pass * kScanUnroll) {
+        float4 v[kScanUnroll];
 #pragma unroll
-      for (int j = 0; j <= kBoundsRows; ++j) { /* voxel rows y_begin .. y_begin + kBoundsRows */
-        const int y = y_begin + j;
-        const bool row = y < R;
-        const float* __restrict__ r0 = g0 + (size_t)y * py;
-        const float* __restrict__ r1 = g1 + (size_t)y * py;
-        a0[j] = (row && oka) ? __ldg(r0 + za) : 3.0e38f;
-        a1[j] = (row && oka) ? __ldg(r1 + za) : 3.0e38f;
-        b0[j] = (row && okb) ? __ldg(r0 + zb) : 3.0e38f;
-        b1[j] = (row && okb) ? __ldg(r1 + zb) : 3.0e38f;
-      }
-      if (WRITE_SKEW) {
+        for (int j = 0; j < kScanUnroll; ++j) {
+          const int y = y0 + j * rows_per_pass;
+          v[j] = y < R ? __ldg(reinterpret_cast<const float4*>(g0 + (size_t)y * py) + zq)
+                       : make_float4(3.0e38f, 3.0e38f, 3.0e38f, 3.0e38f);
+        }
 #pragma unroll
-        for (int j = 0; j <= kBoundsRows; ++j) {
-          const int y = y_begin + j;
-          /* the strip owns its first kBoundsRows voxel rows; the last voxel row of the grid belongs to
-           * the strip that reads it as its halo */
-          const bool own = y < R && (j < kBoundsRows || y == R - 1);
-          /* value z0 + 63 is re-read by the next z step, which owns it -- unless there is none */
-          const bool own_b = okb && (lane < 31 || z0 + 63 >= R - 1);
-          if (own) {
-            float* __restrict__ w0 = d0 + (size_t)y * spy;
-            if (oka) w0[za] = a0[j];
-            if (own_b) w0[zb] = b0[j];
-            if (last_layer) {
-              if (oka) w0[spx + za] = a1[j];
-              if (own_b) w0[spx + zb] = b1[j];
-            }
+        for (int j = 0; j < kScanUnroll; ++j) {
+          const int y = y0 + j * rows_per_pass;
+          if (y >= R) break;
+          if (WRITE_SKEW) {
+            float* __restrict__ w0 = d0 + (size_t)y * spy + 4 * zq;
+            w0[0] = v[j].x; w0[1] = v[j].y; w0[2] = v[j].z; w0[3] = v[j].w;
+          }
+          const unsigned m = (v[j].x < tau ? 1u : 0u) | (v[j].y < tau ? 2u : 0u) | (v[j].z < tau ? 4u : 0u) |
+                             (v[j].w < tau ? 8u : 0u);
+          if (m) {
+            ylo = min(ylo, y); yhi = max(yhi, y);
+            zlo = min(zlo, 4 * zq + __ffs(m) - 1);
+            zhi = max(zhi, 4 * zq + 31 - __clz(m));
           }
         }
       }
-      float pa = fminf(a0[0], a1[0]), pb = fminf(b0[0], b1[0]);
+    }
+  } else {
+    for (int y0 = warp; y0 < R; y0 += kWarps * kScanUnroll) {
+      for (int z = lane; z < R; z += 32) {
+        float v[kScanUnroll];
 #pragma unroll
-      for (int j = 1; j <= kBoundsRows; ++j) { /* cell row y = y_begin + j - 1 */
-        const int y = y_begin + j - 1;
-        const float ca = fminf(a0[j], a1[j]), cb = fminf(b0[j], b1[j]);
-        const float ma = fminf(pa, ca), mb = fminf(pb, cb);
-        const float nxt = __shfl_down_sync(kFull, ma, 1);
-        const bool cell_row = y < R - 1;
-        const bool below_a = cell_row && zb < R && fminf(ma, mb) < tau;                    /* cell za: voxels za, za + 1 */
-        const bool below_b = cell_row && lane < 31 && zb + 1 < R && fminf(mb, nxt) < tau;  /* cell zb: voxels zb, zb + 1 */
-        const unsigned mka = __ballot_sync(kFull, below_a), mkb = __ballot_sync(kFull, below_b);
-        if (mka | mkb) {
-          ylo = min(ylo, y);
-          yhi = max(yhi, y);
-          if (mka) { zlo = min(zlo, z0 + 2 * (__ffs(mka) - 1)); zhi = max(zhi, z0 + 2 * (31 - __clz(mka))); }
-          if (mkb) { zlo = min(zlo, z0 + 2 * (__ffs(mkb) - 1) + 1); zhi = max(zhi, z0 + 2 * (31 - __clz(mkb)) + 1); }
+        for (int j = 0; j < kScanUnroll; ++j) {
+          const int y = y0 + j * kWarps;
+          v[j] = y < R ? __ldg(g0 + (size_t)y * py + z) : 3.0e38f;
         }
-        pa = ca; pb = cb;
+#pragma unroll
+        for (int j = 0; j < kScanUnroll; ++j) {
+          const int y = y0 + j * kWarps;
+          if (y >= R) break;
+          if (WRITE_SKEW) d0[(size_t)y * spy + z] = v[j];
+          if (v[j] < tau) {
+            ylo = min(ylo, y); yhi = max(yhi, y);
+            zlo = min(zlo, z); zhi = max(zhi, z);
+          }
+        }
       }
     }
   }
+  ylo = __reduce_min_sync(kFull, ylo); yhi = __reduce_max_sync(kFull, yhi);
+  zlo = __reduce_min_sync(kFull, zlo); zhi = __reduce_max_sync(kFull, zhi);
   if (lane == 0 && yhi >= 0) {
     atomicMin(&s_lo[0], ylo); atomicMax(&s_hi[0], yhi);
     atomicMin(&s_lo[1], zlo); atomicMax(&s_hi[1], zhi);
   }
   __syncthreads();
   if (threadIdx.x == 0 && s_hi[0] >= 0) {
-    atomicMin(&out[n].lo[0], ix); atomicMax(&out[n].hi[0], ix);
-    atomicMin(&out[n].lo[1], s_lo[0]); atomicMax(&out[n].hi[1], s_hi[0]);
-    atomicMin(&out[n].lo[2], s_lo[1]); atomicMax(&out[n].hi[2], s_hi[1]);
+    bounds_commit(out + n, 0, ix, ix, R);
+    bounds_commit(out + n, 1, s_lo[0], s_hi[0], R);
+    bounds_commit(out + n, 2, s_lo[1], s_hi[1], R);
+  }
+}
+
+/* Slab minima of a grid: minima[n][a][i] = the smallest voxel value with coordinate i on axis a (x, y,
+ * z).  They do not depend on the pose: for FIXED grids they are computed once, and the cell bounds of any
+ * hit-threshold bound tau follow from 3 R comparisons per grid (sdfr_bounds_from_minima_kernel) -- the
+ * bounding box of the voxels below tau is, per axis, the first / last slab whose minimum is below tau.
+ * Same walk as the scan; minima must be pre-filled with +large (sdfr_fill_kernel). */
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  /* order-preserving for IEEE floats: non-negative values compare as ints, negative ones reversed as
+   * unsigned; mixed sequences stay correct because a negative float is a negative int / a huge unsigned */
+  if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+  else atomicMax(reinterpret_cast<unsigned*>(addr), __float_as_uint(v));
+}
+
+__global__ void sdfr_fill_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+constexpr int kSlabMaxR = 1024;
+
+__global__ void __launch_bounds__(256)
+sdfr_slab_minima_kernel(const float* __restrict__ sdf, long long sdf_stride, int R, int py, int px,
+                        float* __restrict__ minima) {
+  __shared__ float s_z[kSlabMaxR];
+  __shared__ float s_x[kWarps];
+  const int n = blockIdx.y, ix = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* __restrict__ g0 = sdf + (size_t)n * sdf_stride + (size_t)ix * px;
+  float* __restrict__ mx = minima + (size_t)n * 3 * R;
+  float* __restrict__ my = mx + R;
+  float* __restrict__ mz = my + R;
+  for (int z = threadIdx.x; z < R; z += 256) s_z[z] = 3.0e38f;
+  __syncthreads();
+  float xmin = 3.0e38f;
+  for (int z0 = 0; z0 < R; z0 += 32) {
+    const int z = z0 + lane;
+    float zmin = 3.0e38f;
+    for (int y = warp; y < R; y += kWarps) {
+      const float v = z < R ? __ldg(g0 + (size_t)y * py + z) : 3.0e38f;
+      zmin = fminf(zmin, v);
+      float r = v;
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) r = fminf(r, __shfl_xor_sync(kFull, r, o));
+      if (lane == 0) atomic_min_float(my + y, r); /* R / 32 partial minima per row and layer */
+    }
+    if (z < R) atomic_min_float(&s_z[z], zmin);
+    xmin = fminf(xmin, zmin);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) xmin = fminf(xmin, __shfl_xor_sync(kFull, xmin, o));
+  if (lane == 0) s_x[warp] = xmin;
+  __syncthreads();
+  for (int z = threadIdx.x; z < R; z += 256) atomic_min_float(mz + z, s_z[z]);
+  if (threadIdx.x == 0) {
+    float m = s_x[0];
+    for (int w = 1; w < kWarps; ++w) m = fminf(m, s_x[w]);
+    mx[ix] = m; /* this CTA owns the layer */
+  }
+}
+
+/* Cell bounds from slab minima: one CTA per grid; tau as in sdfr_bounds_init_kernel. */
+__global__ void __launch_bounds__(256)
+sdfr_bounds_from_minima_kernel(const float* __restrict__ minima, int R, const float* __restrict__ pos,
+                               const float* __restrict__ inv_scale, int batch, int n_grids, float threshold,
+                               CellBounds* __restrict__ out) {
+  const int n = blockIdx.x;
+  __shared__ float red[8];
+  __shared__ int s_lo[3], s_hi[3];
+  float tau = 0.0f;
+  if (n_grids == 1) {
+    for (int b = threadIdx.x; b < batch; b += blockDim.x) tau = fmaxf(tau, hit_tau(pos + 3 * b, inv_scale[b], threshold));
+  } else if (threadIdx.x == 0) {
+    tau = hit_tau(pos + 3 * n, inv_scale[n], threshold);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) tau = fmaxf(tau, __shfl_xor_sync(kFull, tau, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = tau;
+  if (threadIdx.x < 3) {
+    s_lo[threadIdx.x] = 0x7fffffff;
+    s_hi[threadIdx.x] = -1;
+  }
+  __syncthreads();
+  tau = red[0];
+  for (int w = 1; w < 8; ++w) tau = fmaxf(tau, red[w]);
+  const float* __restrict__ m = minima + (size_t)n * 3 * R;
+  for (int i = threadIdx.x; i < 3 * R; i += blockDim.x) {
+    if (m[i] < tau) {
+      const int a = i / R, v = i - a * R;
+      atomicMin(&s_lo[a], v > 0 ? v - 1 : 0);
+      atomicMax(&s_hi[a], v < R - 2 ? v : R - 2);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CellBounds cb;
+    for (int a = 0; a < 3; ++a) {
+      cb.lo[a] = s_lo[a];
+      cb.hi[a] = s_hi[a];
+    }
+    cb.tau = tau;
+    cb.pad = 0;
+    out[n] = cb;
   }
 }
 
@@ -1603,11 +1712,9 @@ static int launch_bounds_scan(const float* sdf, int R, long long sdf_stride, int
   const Grid GS = make_grid(R, kLayoutSkewed);
   CellBounds* out = reinterpret_cast<CellBounds*>(bounds);
   sdfr_bounds_init_kernel<<<n_grids, n_grids == 1 ? 256 : 32, 0, s>>>(pos, inv_scale, batch, n_grids, threshold, out);
-  /* kBoundsRows cell rows per warp, 8 warps per CTA: one CTA per x layer up to R = 65 */
-  const int y_blocks = (R - 1 + kWarps * kBoundsRows - 1) / (kWarps * kBoundsRows);
   for (int z0 = 0; z0 < n_grids; z0 += 65535) {
     const int nz = n_grids - z0 < 65535 ? n_grids - z0 : 65535;
-    const dim3 grid(R - 1, y_blocks, nz);
+    const dim3 grid(R, nz); /* one CTA per voxel layer and grid */
     if (skewed)
       sdfr_bounds_scan_kernel<true><<<grid, 256, 0, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride, R, G.py, G.px,
                                                          out + z0, skewed + (size_t)z0 * skewed_stride,
@@ -1630,6 +1737,39 @@ int sdfr_grid_bounds(const float* sdf, int R, long long sdf_stride, int layout, 
   if (!sdf || !pos || !inv_scale || !bounds) return fail(SDFR_E_NULL, "grid bounds: NULL pointer");
   return launch_bounds_scan(sdf, R, sdf_stride, layout, pos, inv_scale, batch, threshold, bounds, nullptr, 0,
                             (cudaStream_t)stream);
+}
+
+int sdfr_grid_slab_minima(const float* sdf, int R, long long sdf_stride, int layout, int n_grids,
+                          float* minima, void* stream) {
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED) return fail(SDFR_E_FLAGS, "unknown sdf_layout");
+  if (R < 2 || R > kSlabMaxR) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (n_grids < 0 || sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative n_grids or sdf_stride");
+  if (n_grids == 0) return 0;
+  if (!sdf || !minima) return fail(SDFR_E_NULL, "slab minima: NULL pointer");
+  const Grid G = make_grid(R, layout);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)n_grids * 3 * R;
+  sdfr_fill_kernel<<<(int)((total + 255) / 256 < 1024 ? (total + 255) / 256 : 1024), 256, 0, s>>>(minima, total, 3.0e38f);
+  for (int z0 = 0; z0 < n_grids; z0 += 65535) {
+    const int nz = n_grids - z0 < 65535 ? n_grids - z0 : 65535;
+    sdfr_slab_minima_kernel<<<dim3(R, nz), 256, 0, s>>>(sdf + (size_t)z0 * sdf_stride, sdf_stride, R, G.py, G.px,
+                                                        minima + (size_t)z0 * 3 * R);
+  }
+  return check_launch("sdfr_slab_minima_kernel");
+}
+
+int sdfr_bounds_from_minima(const float* minima, int R, int n_grids, const float* pos, const float* inv_scale,
+                            int batch, float threshold, sdfr_cell_bounds* bounds, void* stream) {
+  if (R < 2 || R > kSlabMaxR) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (batch < 0 || n_grids < 0) return fail(SDFR_E_SHAPE, "negative batch or n_grids");
+  if (!(threshold >= 0.0f)) return fail(SDFR_E_SHAPE, "threshold must be >= 0");
+  if (batch == 0 || n_grids == 0) return 0;
+  if (n_grids != 1 && n_grids != batch)
+    return fail(SDFR_E_SHAPE, "bounds from minima: one grid per hypothesis or one shared grid expected");
+  if (!minima || !pos || !inv_scale || !bounds) return fail(SDFR_E_NULL, "bounds from minima: NULL pointer");
+  sdfr_bounds_from_minima_kernel<<<n_grids, 256, 0, (cudaStream_t)stream>>>(
+      minima, R, pos, inv_scale, batch, n_grids, threshold, reinterpret_cast<CellBounds*>(bounds));
+  return check_launch("sdfr_bounds_from_minima_kernel");
 }
 
 int sdfr_skew_grids_bounds(const float* sdf, int R, long long sdf_stride, int batch, float* skewed,

@@ -334,10 +334,31 @@ class HypothesisOptimizer:
         n_grids = 1 if self._grid_op[1] == 0 else B
         self._bounds = None if get_empty_space_policy() == "off" else \
             torch.empty((max(V, 1), n_grids, 8), dtype=torch.int32, device=dev)
+        # fixed grids: their slab minima are read once; every iteration's bounds (they depend on the
+        # pose through the hit-threshold bound) are then 3 R comparisons per grid instead of a grid scan
+        self._minima = None
+        if self._bounds is not None and self.decoder is None:
+            grids, gstride, layout = self._grid_op
+            self._minima = torch.empty((n_grids, 3, R), dtype=torch.float32, device=dev)
+            _lib.check(_lib.lib().sdfr_grid_slab_minima(grids.data_ptr(), R, gstride, layout, n_grids,
+                                                        self._minima.data_ptr(), _stream()), "sdfr_grid_slab_minima")
         # second stream: the point loss runs beside the render (both only read the grids), the
         # gradient-grid clears beside the decoder trunk; forks and joins are captured by capture()
         self._side = torch.cuda.Stream(dev) if self.overlap else None
         self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale for the first render
+
+    def _grid_bounds(self, position_ptr: int, inv_scale_ptr: int, out: torch.Tensor) -> int:
+        """Empty-space bounds of this iteration's grids for the given poses into ``out``; its pointer."""
+        lib, B = _lib.lib(), self.position.shape[0]
+        grids, gstride, layout = self._grid_op
+        if self._minima is not None:
+            _lib.check(lib.sdfr_bounds_from_minima(
+                self._minima.data_ptr(), self._R, int(self._minima.shape[0]), position_ptr, inv_scale_ptr, B,
+                self.threshold, out.data_ptr(), _stream()), "sdfr_bounds_from_minima")
+        else:
+            _lib.check(lib.sdfr_grid_bounds(grids.data_ptr(), self._R, gstride, layout, position_ptr, inv_scale_ptr,
+                                            B, self.threshold, out.data_ptr(), _stream()), "sdfr_grid_bounds")
+        return out.data_ptr()
 
     def _hyp_step(self, flags: int, g_latent: Optional[torch.Tensor] = None,
                   g_orientation_raw: Optional[torch.Tensor] = None,
@@ -409,9 +430,7 @@ class HypothesisOptimizer:
             obs = self.depth_obs[v].data_ptr()
             bounds = None
             if self._bounds is not None:
-                bounds = self._bounds[v].data_ptr()
-                _lib.check(lib.sdfr_grid_bounds(grids.data_ptr(), R, gstride, layout, p_v, is_v, B,
-                                                self.threshold, bounds, _stream()), "sdfr_grid_bounds")
+                bounds = self._grid_bounds(p_v, is_v, self._bounds[v])
             _lib.check(lib.sdfr_compare_forward(
                 grids.data_ptr(), R, gstride, layout, p_v, q_v, is_v, B, W, H, cx, cy, fx, fy, self.threshold,
                 obs, 0, self._depth.data_ptr(), view(b["loss_sum"], v, 1), view(b["n_overlap"], v, 1), 0,
@@ -501,10 +520,7 @@ class HypothesisOptimizer:
         bounds = None
         self._constraint_launch()
         if self._bounds is not None:
-            _lib.check(lib.sdfr_grid_bounds(
-                grids.data_ptr(), R, gstride, layout, self.position.data_ptr(), self._inv_scale.data_ptr(), B,
-                self.threshold, self._bounds.data_ptr(), _stream()), "sdfr_grid_bounds")
-            bounds = self._bounds.data_ptr()
+            bounds = self._grid_bounds(self.position.data_ptr(), self._inv_scale.data_ptr(), self._bounds)
 
         def point_loss():
             _lib.check(lib.sdfr_point_loss_fused(

@@ -345,6 +345,56 @@ def test_grid_bounds_kernel_matches_oracle(c2, layout):
     assert got[6:7].view(np.float32)[0] == tau and (got[0:3] == lo).all() and (got[3:6] == hi).all()
 
 
+@pytest.mark.parametrize("layout", ["dense", "skewed"])
+def test_bounds_from_slab_minima_equal_the_scan(c2, layout):
+    """Fixed grids: sdfr_grid_slab_minima once + sdfr_bounds_from_minima per pose == sdfr_grid_bounds, for
+    the C2 grids at two thresholds, a shared grid, and an odd resolution with negative and positive
+    minima; the minima themselves against numpy."""
+    lib, B, dev = _lib.lib(), c2["B"], c2["dev"]
+    st = torch.cuda.current_stream().cuda_stream
+    src, stride, lay = (c2["grids"], R ** 3, _lib.LAYOUT_DENSE) if layout == "dense" else \
+        (c2["skewed"], c2["SK"], _lib.LAYOUT_SKEWED)
+    minima = torch.full((B, 3, R), float("nan"), device=dev)
+    _lib.check(lib.sdfr_grid_slab_minima(src.data_ptr(), R, stride, lay, B, minima.data_ptr(), st), "minima")
+    g = c2["grids"].view(B, R, R, R)
+    want = torch.stack([g.amin(dim=(2, 3)), g.amin(dim=(1, 3)), g.amin(dim=(1, 2))], 1)
+    assert torch.equal(minima, want)
+    for thr in (THR, 0.05):
+        a = torch.full((B, 8), -7, dtype=torch.int32, device=dev)
+        b = torch.full((B, 8), -9, dtype=torch.int32, device=dev)
+        _lib.check(lib.sdfr_grid_bounds(src.data_ptr(), R, stride, lay, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(),
+                                        B, thr, a.data_ptr(), st), "scan")
+        _lib.check(lib.sdfr_bounds_from_minima(minima.data_ptr(), R, B, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(),
+                                               B, thr, b.data_ptr(), st), "from minima")
+        assert torch.equal(a[:, :7], b[:, :7])
+    a1 = torch.full((1, 8), -7, dtype=torch.int32, device=dev)
+    b1 = torch.full((1, 8), -9, dtype=torch.int32, device=dev)
+    _lib.check(lib.sdfr_grid_bounds(src.data_ptr(), R, 0, lay, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), B, THR,
+                                    a1.data_ptr(), st), "scan shared")
+    _lib.check(lib.sdfr_bounds_from_minima(minima.data_ptr(), R, 1, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), B,
+                                           THR, b1.data_ptr(), st), "from minima shared")
+    assert torch.equal(a1[:, :7], b1[:, :7])
+    if layout == "dense":
+        R2 = 37
+        g2 = (torch.rand(2, R2, R2, R2, device=dev) - 0.5) * torch.tensor([1.0, 1e-3], device=dev).view(2, 1, 1, 1) + \
+            torch.tensor([0.45, 0.0], device=dev).view(2, 1, 1, 1)
+        g2 = g2.contiguous()
+        m2 = torch.empty((2, 3, R2), device=dev)
+        _lib.check(lib.sdfr_grid_slab_minima(g2.data_ptr(), R2, R2 ** 3, _lib.LAYOUT_DENSE, 2, m2.data_ptr(), st), "minima")
+        assert torch.equal(m2, torch.stack([g2.amin(dim=(2, 3)), g2.amin(dim=(1, 3)), g2.amin(dim=(1, 2))], 1))
+        a2 = torch.empty((2, 8), dtype=torch.int32, device=dev)
+        b2 = torch.empty((2, 8), dtype=torch.int32, device=dev)
+        _lib.check(lib.sdfr_grid_bounds(g2.data_ptr(), R2, R2 ** 3, 0, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), 2,
+                                        THR, a2.data_ptr(), st), "scan")
+        _lib.check(lib.sdfr_bounds_from_minima(m2.data_ptr(), R2, 2, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), 2,
+                                               THR, b2.data_ptr(), st), "from minima")
+        assert torch.equal(a2[:, :7], b2[:, :7])
+    assert lib.sdfr_grid_slab_minima(None, R, 0, 0, 1, None, None) == -1
+    assert lib.sdfr_grid_slab_minima(None, R, 0, 0, 0, None, None) == 0
+    assert lib.sdfr_bounds_from_minima(minima.data_ptr(), R, 3, c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), B, THR,
+                                       b1.data_ptr(), None) == -2
+
+
 def test_skew_and_bounds_in_one_pass(c2):
     """sdfr_skew_grids_bounds == sdfr_skew_grids + sdfr_grid_bounds (what bench.py's step launches)."""
     lib, B, dev = _lib.lib(), c2["B"], c2["dev"]
