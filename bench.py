@@ -43,7 +43,8 @@ def parse_args():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--hypotheses", type=int, default=64, help="hypotheses per GPU (weak scaling)")
     p.add_argument("--cpu-sample", type=int, default=32,
-                   help="hypotheses per step rendered by the CPU reference arm / cpu_baseline")
+                   help="hypotheses per step rendered by the cpu_baseline leg of the GPU arm (the "
+                        "--impl reference arm renders all --hypotheses, the arm's own config)")
     p.add_argument("--e2e-chunk", type=int, default=8, help="hypotheses per pipelined chunk (e2e)")
     p.add_argument("--no-ref-ext", action="store_true",
                    help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
@@ -54,6 +55,74 @@ def parse_args():
 def workload_name(B):
     return (f"C2: {B} pose/shape hypotheses x {W}x{H} depth, one {R}^3 fp32 SDF grid per hypothesis, "
             "fused render + masked-L1 compare forward and backward (all four gradients)")
+
+
+def config_object(B, distributed):
+    """`config` of the JSON line -- identical for both arms (the driver compares them)."""
+    return {"workload": workload_name(B), "hypotheses_per_gpu": B, "width": W, "height": H,
+            "resolution": R, "threshold": THRESHOLD, "sdf": "analytic mug grids, one per hypothesis",
+            "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset, outside the event pair)",
+            "collective": ("all_gather of per-hypothesis losses (async, overlapped with the next step)"
+                           if distributed else "none")}
+
+
+# kernels each C-ABI entry point of the timed step launches (memset nodes are not counted); checked
+# against the ncu launch list of this command (profiles/*_launches.csv)
+KERNELS_PER_CALL = {
+    "sdfr_skew_grids_bounds": 2,  # sdfr_bounds_init_kernel, sdfr_bounds_scan_kernel<true>
+    "sdfr_compare_fused": 2,      # sdfr_zero_small_kernel, sdfr_forward_kernel<64, skewed, 2>
+    "sdfr_scale_grads": 1,        # sdfr_scale_grads_kernel
+}
+
+
+def algorithmic_bytes(S, P, B, RRR, hits, n_over):
+    """32 B per trilinear sample, depth store, observation read at hits, grid read once; fused
+    backward: 32 B corner re-read + 64 B read-modify-write per overlap pixel, gradient grid written once."""
+    fwd = 32 * S + 4 * P * B + 4 * RRR * B + 4 * hits
+    bwd = 4 * P * B + 4 * hits + 32 * n_over + 64 * n_over + 4 * RRR * B
+    fused = fwd + 32 * n_over + 64 * n_over + 4 * RRR * B
+    return fwd, bwd, fused
+
+
+def gather_peaks():
+    """Pure-gather rates of this GPU type for the renderer's access pattern (scripts/micro/gather_peaks.cu,
+    measured on the pool's B200s and committed): the L1 / L2 denominators MEASURED_PEAKS.json lacks."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "gather_peaks.json")) as f:
+            d = json.load(f)
+        return {"l1_skewed_gsamples": d["coherent_l1_skewed_ldg32"]["gsamples_per_s"],
+                "l2_skewed_gsamples": d["coherent_l2only_skewed_ldg32"]["gsamples_per_s"],
+                "source": "profiles/gather_peaks.json (scripts/micro/gather_peaks.cu)"}
+    except Exception:
+        return None
+
+
+def roofline_object(fused_bytes, fused_ms, S, peak, peak_src, traffic, peaks=None):
+    """The contract's `roofline` keys for the dominant kernel, plus the gather-rate view of the same
+    launch: the 32*S term never leaves L1/L2 (ncu: 88 % L1 hit rate, DRAM at 8 %), so the HBM fraction
+    says how the kernel compares with a copy of its algorithmic bytes, and `gather` says how close it is
+    to what the memory pipes can deliver for this access pattern."""
+    achieved = fused_bytes / (fused_ms * 1e-3) / 1e9
+    out = {
+        "bound": "hbm", "kernel": "sdfr_forward_kernel<64, skewed, MODE=2> (fused render+compare+backward, incl. its memsets)",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": fused_bytes, "launch_ms": fused_ms,
+        "note": ("algorithmic bytes = SURVEY 8d formula (32 B per trilinear sample + compulsory image/grid "
+                 "traffic); the 32*S gather term is served by L1/L2 (traffic is the ncu DRAM figure: ~0.15x "
+                 "of the algorithmic bytes), so frac is against the HBM copy peak, not a claim of HBM "
+                 "traffic; `gather` compares the same launch with pure-gather kernels"),
+    }
+    gs = S / (fused_ms * 1e-3) / 1e9
+    g = {"achieved_gsamples_per_s": gs, "achieved_GBps": 32 * gs}
+    if peaks:
+        g.update({"l1_peak_gsamples_per_s": peaks["l1_skewed_gsamples"],
+                  "l2_peak_gsamples_per_s": peaks["l2_skewed_gsamples"],
+                  "frac_of_l1_gather_peak": gs / peaks["l1_skewed_gsamples"],
+                  "frac_of_l2_gather_peak": gs / peaks["l2_skewed_gsamples"], "peak_source": peaks["source"],
+                  "limiter": "dependent-gather latency + issue slots (ncu: issue 58 %, L1 wavefronts 59 %, "
+                             "L2 20 %, DRAM 8 %): neither L2 nor HBM bandwidth"})
+    out["gather"] = g
+    return out
 
 
 def measured_peaks():
@@ -181,17 +250,20 @@ def time_cpu(sample, steps, warmup):
 def run_reference_arm(args, rank):
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 50))
-    warmup = max(1, min(args.warmup, 3))
-    sample = min(args.cpu_sample, args.hypotheses)
+    # the arm's own config: every step renders ALL hypotheses of the workload (64 x 640x480 is ~0.25 s of
+    # CPU work per step on 16 threads); steps / warm-up as given (same floor of 3 warm-up steps as the GPU
+    # arm), bounded only so that an accidental --steps 100000 still ends
+    steps = max(1, min(args.steps, 400))
+    warmup = max(args.warmup, 3)
+    sample = args.hypotheses
     mpix, ms, cores = time_cpu(sample, steps, warmup)
-    desc = (f"{sample} of the {args.hypotheses} hypotheses of one step per timed step "
+    desc = (f"all {sample} hypotheses of one step per timed step "
             f"(forward + masked L1 + backward through oracle/liboracle.so, OpenMP over image rows)")
     line = {
         "impl": "reference", "metric": METRIC, "value": mpix, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.hypotheses), "sample": desc},
+        "config": config_object(args.hypotheses, int(os.environ.get("WORLD_SIZE", "1")) > 1),
         "cpu_baseline": {"value": mpix, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": mpix, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -276,8 +348,8 @@ def main():
     sums = torch.zeros(2, B, device=dev)
     g_sdf = torch.empty_like(grids)
     g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
-    gathered = torch.empty(world * B, device=dev) if distributed else None
-    loss = torch.empty(B, device=dev)
+    gathered2 = torch.empty(2, world * B, device=dev) if distributed else None
+    loss2 = torch.empty(2, B, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     RRR = R * R * R
     flags_b = _lib.GRAD_ALL | _lib.ZERO_GRADS
@@ -339,26 +411,47 @@ def main():
             sums[1].data_ptr(), None, R, B, g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
             g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, stream), "sdfr_scale_grads")
 
+    launches = {"kernels": 0, "steps": 0}
+    pending = []  # async all_gather work handles, at most two in flight (double-buffered losses)
+
     def step():
         # layout pass, then forward render + masked-L1 compare + backward in ONE traversal, then
         # the deferred per-hypothesis normalisation of the gradients
         skew_bound()
         fused()
         scale()
-        if distributed:  # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank)
-            torch.div(sums[0], sums[1], out=loss)
-            dist.all_gather_into_tensor(gathered, loss)
+        launches["kernels"] += (KERNELS_PER_CALL["sdfr_skew_grids_bounds"] + KERNELS_PER_CALL["sdfr_compare_fused"]
+                                + KERNELS_PER_CALL["sdfr_scale_grads"])
+        if distributed:
+            # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank).  Nothing in the next
+            # step depends on it (the loop only ranks hypotheses at the end), so it runs on NCCL's own
+            # stream beside the next step's kernels; the buffers alternate, and a buffer is reused only
+            # after the gather that read it has completed (stream-side wait, no host synchronisation).
+            k = launches["steps"] & 1
+            if len(pending) == 2:
+                pending.pop(0).wait()
+            torch.div(sums[0], sums[1], out=loss2[k])
+            pending.append(dist.all_gather_into_tensor(gathered2[k], loss2[k], async_op=True))
+            launches["kernels"] += 2  # the division and NCCL's all-gather kernel
+        launches["steps"] += 1
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     flush_buf = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
 
     def flush_l2():
         flush_buf.zero_()
 
-    def timed(fn, n, warm):
-        """Sum of per-call CUDA-event times (ms) over n calls, L2 flushed before every call."""
+    def timed(fn, n, warm, finish=None):
+        """Sum of per-call CUDA-event times (ms) over n calls, L2 flushed before every call.  `finish`
+        (the drain of the overlapped all-gathers) runs after the last call and its wait is added."""
         for _ in range(warm):
             flush_l2()
             fn()
+        if finish is not None:
+            finish()
         torch.cuda.synchronize()
         if distributed:
             dist.barrier()
@@ -370,15 +463,25 @@ def main():
             a.record()
             fn()
             b.record()
+        tail = None
+        if finish is not None:
+            finish()  # the current stream waits for the last gathers
+            tail = torch.cuda.Event(enable_timing=True)
+            tail.record()
         torch.cuda.synchronize()
         if distributed:
             dist.barrier()
             torch.cuda.synchronize()
-        return sum(a.elapsed_time(b) for a, b in evs)
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        if tail is not None:
+            total += evs[-1][1].elapsed_time(tail)
+        return total
 
     K, Wm = args.steps, max(args.warmup, 3)
     with ClockSampler(local_rank) as clocks:
-        total_ms = timed(step, K, Wm)
+        launches["kernels"] = launches["steps"] = 0
+        total_ms = timed(step, K, Wm, finish=drain if distributed else None)
+    kernels_timed = launches["kernels"] * K // (K + Wm)  # warm-up steps launch the same kernels
     if distributed:
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -441,6 +544,56 @@ def main():
         e2e_graph_s, e2e_check_g = None, str(e)[:120]
     e2e_s = min(e2e_eager_s, e2e_graph_s) if e2e_graph_s else e2e_eager_s
     e2e_value = world * B * P * Ke / e2e_s / 1e6
+
+    # ---- the same end-to-end step the way the reference's callers actually produce the grids ----
+    # (estimation/simple_setup.py:414: sdf = vae.decode(latent) ON the device): the host hands over 8
+    # latent floats + pose per hypothesis and the observed depth map, the device decodes the grids
+    # (decoder trunk + fused tail), renders, compares, back-propagates to pose AND latent, and the host
+    # reads back loss and gradients.  More device work per step than `e2e` (the decoder and its backward),
+    # ~60x fewer bytes over PCIe.  Reported beside `e2e`, which keeps the contract's definition (every
+    # input of the C-ABI call, the grids included, starts in pinned host memory).
+    e2e_decoded = None
+    try:
+        from sdfest_b200.estimation import decode_render_compare
+
+        dec_e = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
+        w_e, b_e = dec_e.tail_parameters()
+        h_in = torch.cat([torch.zeros(B, 8), pos.cpu(), quat.cpu(), (1.0 / inv_s).cpu()[:, None]], 1).pin_memory()
+        h_out = torch.empty(B, 17).pin_memory()
+
+        def e2e_decoded_step():
+            x = h_in.to(dev, non_blocking=True)
+            o = h_obs.to(dev, non_blocking=True)
+            lat, p, q, sc = (x[:, :8].clone().requires_grad_(True), x[:, 8:11].clone().requires_grad_(True),
+                             x[:, 11:15].clone().requires_grad_(True), x[:, 15].clone().requires_grad_(True))
+            l, _, _, _ = decode_render_compare(dec_e.trunk(lat), w_e, b_e, p, q, sc, o, None, R, THRESHOLD, cam,
+                                               base=dec_e.base, depth_weight=1.0, pc_weight=0.0)
+            l.sum().backward()
+            h_out.copy_(torch.cat([l.detach()[:, None], p.grad, q.grad, sc.grad[:, None], lat.grad], 1),
+                        non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return h_out
+
+        for _ in range(3):
+            e2e_decoded_step()
+        if distributed:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            r_dec = e2e_decoded_step()
+        dt = time.perf_counter() - t0
+        if distributed:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e_decoded = {"value": world * B * P * Ke / dt / 1e6, "unit": UNIT, "ms_per_step": dt / Ke * 1e3,
+                       "h2d_bytes_per_step": h_in.numel() * 4 + h_obs.numel() * 4, "d2h_bytes_per_step": h_out.numel() * 4,
+                       "api": "estimation.decode_render_compare on host latents/poses (eager autograd, one "
+                              "stream): decoder trunk + sdfr_decoder_tail_forward + sdfr_compare_fused + tail "
+                              "adjoint + trunk backward",
+                       "checksum": float(r_dec[:, 0].sum())}
+    except Exception as e:  # a second view of e2e, never a requirement
+        e2e_decoded = {"unavailable": str(e)[:200]}
 
     # ---- the whole loop of BASELINE config 2: 50 Adam steps on pose / scale / latent -------------
     # decoder (reference architecture, trunk + fused tail on this library's kernels) -> fused
@@ -513,48 +666,33 @@ def main():
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     n_over = int(sums[1].sum().item())
-    # 32 B per trilinear sample, depth store, observation read at hits, grid read once;
-    # fused backward: 32 B corner re-read + 64 B RMW per overlap pixel, grad grid written once
-    fwd_bytes = 32 * S + 4 * P * B + 4 * RRR * B + 4 * Hh_all
-    bwd_bytes = 4 * P * B + 4 * Hh_all + 32 * n_over + 64 * n_over + 4 * RRR * B
-    fused_bytes = fwd_bytes + 32 * n_over + 64 * n_over + 4 * RRR * B
+    fwd_bytes, bwd_bytes, fused_bytes = algorithmic_bytes(S, P, B, RRR, Hh_all, n_over)
     peak, peak_src = measured_peaks()
-    dom_bytes, dom_ms = fused_bytes, fused_ms
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {
-        "bound": "hbm", "kernel": "sdfr_forward_kernel<64, skewed, MODE=2> (fused render+compare+backward, incl. its memsets)",
-        "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("fused"), "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
-        "note": ("algorithmic bytes = SURVEY 8d formula (32 B per trilinear sample + compulsory "
-                 "image/grid traffic); the 32*S gather term is served by L1/L2, so frac is against "
-                 "the HBM copy peak, not a claim of HBM traffic"),
-        "kernels": {
-            "fused_incl_memsets": {"ms": fused_ms, "bytes": fused_bytes, "GBps": fused_bytes / fused_ms / 1e6},
-            "fused_dense_layout_incl_memsets": {"ms": fused_dense_ms, "bytes": fused_bytes,
-                                                "GBps": fused_bytes / fused_dense_ms / 1e6},
-            "fused_without_empty_space_bounds": {"ms": fused_nobounds_ms},
-            "grid_bounds": {"ms": bound_ms, "bytes": 4 * SK * B, "GBps": 4 * SK * B / bound_ms / 1e6},
-            "skew_grids_bounds": {"ms": skew_bound_ms, "bytes": 4 * (RRR + SK) * B,
-                                  "GBps": 4 * (RRR + SK) * B / skew_bound_ms / 1e6},
-            "skew_grids": {"ms": skew_ms, "bytes": 4 * (RRR + SK) * B, "GBps": 4 * (RRR + SK) * B / skew_ms / 1e6},
-            "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
-            "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6},
-            "unfused_backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
-        },
-        "work": {"samples_S": S, "hit_pixels": Hh_all, "overlap_pixels_Hh": n_over,
-                 "box_pixels": stats["box_pixels"], "pixels": P * B,
-                 "without_empty_space_bounds": {"samples_S": stats_full["samples"], "box_pixels": stats_full["box_pixels"]}},
+    roofline = roofline_object(fused_bytes, fused_ms, S, peak, peak_src, ncu_traffic("fused"), gather_peaks())
+    roofline["kernels"] = {
+        "fused_incl_memsets": {"ms": fused_ms, "bytes": fused_bytes, "GBps": fused_bytes / fused_ms / 1e6},
+        "fused_dense_layout_incl_memsets": {"ms": fused_dense_ms, "bytes": fused_bytes,
+                                            "GBps": fused_bytes / fused_dense_ms / 1e6},
+        "fused_without_empty_space_bounds": {"ms": fused_nobounds_ms},
+        "grid_bounds": {"ms": bound_ms, "bytes": 4 * SK * B, "GBps": 4 * SK * B / bound_ms / 1e6},
+        "skew_grids_bounds": {"ms": skew_bound_ms, "bytes": 4 * (RRR + SK) * B,
+                              "GBps": 4 * (RRR + SK) * B / skew_bound_ms / 1e6},
+        "skew_grids": {"ms": skew_ms, "bytes": 4 * (RRR + SK) * B, "GBps": 4 * (RRR + SK) * B / skew_ms / 1e6},
+        "scale_grads": {"ms": scale_ms, "bytes": 8 * RRR * B, "GBps": 8 * RRR * B / scale_ms / 1e6},
+        "unfused_forward": {"ms": fwd_ms, "bytes": fwd_bytes, "GBps": fwd_bytes / fwd_ms / 1e6,
+                            "gsamples_per_s": S / fwd_ms / 1e6},
+        "unfused_backward_incl_memsets": {"ms": bwd_ms, "bytes": bwd_bytes, "GBps": bwd_bytes / bwd_ms / 1e6},
     }
+    roofline["work"] = {"samples_S": S, "hit_pixels": Hh_all, "overlap_pixels_Hh": n_over,
+                        "box_pixels": stats["box_pixels"], "pixels": P * B,
+                        "without_empty_space_bounds": {"samples_S": stats_full["samples"],
+                                                       "box_pixels": stats_full["box_pixels"]}}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(B), "hypotheses_per_gpu": B, "width": W, "height": H,
-                   "resolution": R, "threshold": THRESHOLD, "sdf": "analytic mug grids, one per hypothesis",
-                   "l2": f"flushed before every timed step ({L2_FLUSH_BYTES >> 20} MiB memset, outside the event pair)",
-                   "collective": "all_gather of per-hypothesis losses" if distributed else "none"},
+        "config": config_object(B, distributed),
         "render_hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
         "loop": loop,
         "roofline": roofline,
@@ -566,7 +704,9 @@ def main():
                 "ms_per_step_cuda_graph": (e2e_graph_s / Ke * 1e3) if e2e_graph_s else e2e_check_g,
                 "d2h": "loss, n_overlap, 8 pose gradients per hypothesis; SDF gradients stay on the device",
                 "checksum": e2e_check},
-        "gpu_launches": 5 * K,  # bounds init + skew/bounds scan + pose-zero + fused + scale kernels per step
+        # kernels launched inside the timed region, counted per C-ABI call made (KERNELS_PER_CALL)
+        "e2e_decoded": e2e_decoded,
+        "gpu_launches": kernels_timed,
         "clocks": clocks.summary(),
         "lib": lib.sdfr_build_info().decode(),
     }

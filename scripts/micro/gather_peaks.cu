@@ -78,7 +78,72 @@ __global__ void __launch_bounds__(256) gather_kernel(const float* __restrict__ g
   if (acc == 123.456f) out[0] = acc;
 }
 
+// ---- north-star option "fp16 copy staged in shared memory for <= 48^3" (n1): the same coherent walk on a
+// 48^3 grid, (a) fp32 skewed through L1 as the product does it, (b) a __half copy of the whole grid
+// (221 184 B, the only size class that fits 227 KB) staged per CTA into shared memory and gathered with
+// 8 x LDS.U16.  One CTA of 1024 threads per SM (the grid owns the SM's shared memory).  The staging copy
+// is inside the timed region once per CTA, as it would be once per (CTA, hypothesis).
+#include <cuda_fp16.h>
+constexpr int R48 = 48;
+template <int SMEM>
+__global__ void __launch_bounds__(1024) gather48_kernel(const float* __restrict__ grids, const __half* __restrict__ hgrids,
+                                                         long long grid_stride, int py, int px, int iters, float* out) {
+  extern __shared__ __half sh[];
+  const int lane = threadIdx.x & 31, warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int gidx = blockIdx.x % kGrids;
+  if (SMEM) {
+    const uint4* src = reinterpret_cast<const uint4*>(hgrids + (size_t)gidx * R48 * R48 * R48);
+    uint4* dst = reinterpret_cast<uint4*>(sh);
+    for (int i = threadIdx.x; i < R48 * R48 * R48 / 8; i += blockDim.x) dst[i] = src[i];
+    __syncthreads();
+  }
+  const float* g = grids + (size_t)gidx * grid_stride;
+  const int fx = ((lane & 7) + (warp_global & 3)) >> 2, fy = ((lane >> 3) + ((warp_global >> 2) & 3)) >> 2;
+  unsigned s = hash(warp_global * 2654435761u + 12345u);
+  int cx = s % (R48 - 4), cy = (s >> 8) % (R48 - 4), cz = (s >> 16) % (R48 - 4);
+  float acc = 0.f;
+  for (int i = 0; i < iters; ++i) {
+    const int ix = cx + fx, iy = cy + fy, iz = cz + ((lane * 7 + i) & 1);
+    cx = cx + 1 < R48 - 4 ? cx + 1 : 0; cy = (i & 1) ? (cy + 1 < R48 - 4 ? cy + 1 : 0) : cy;
+    cz = (i & 3) == 3 ? (cz + 1 < R48 - 4 ? cz + 1 : 0) : cz;
+    if (SMEM) {
+      const __half* c = sh + ((ix * R48 + iy) * R48 + iz);
+      acc += __half2float(c[0]) + __half2float(c[1]) + __half2float(c[R48]) + __half2float(c[R48 + 1]) +
+             __half2float(c[R48 * R48]) + __half2float(c[R48 * R48 + 1]) + __half2float(c[R48 * R48 + R48]) +
+             __half2float(c[R48 * R48 + R48 + 1]);
+    } else {
+      const float* c = g + (ix * px + iy * py + iz);
+      acc += ld<0>(c) + ld<0>(c + 1) + ld<0>(c + py) + ld<0>(c + py + 1) + ld<0>(c + px) + ld<0>(c + px + 1) +
+             ld<0>(c + px + py) + ld<0>(c + px + py + 1);
+    }
+  }
+  if (acc == 123.456f) out[0] = acc;
+}
+
 struct Result { const char* name; double gsamples, gbytes, ms; };
+
+template <int SMEM>
+Result run48(const char* name, const float* grids, const __half* hgrids, long long stride, int py, int px, int ctas,
+             int iters) {
+  float* out; cudaMalloc(&out, 4);
+  const size_t smem = SMEM ? (size_t)R48 * R48 * R48 * sizeof(__half) : 0;
+  if (SMEM) cudaFuncSetAttribute(gather48_kernel<SMEM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+  for (int w = 0; w < 2; ++w) gather48_kernel<SMEM><<<ctas, 1024, smem>>>(grids, hgrids, stride, py, px, iters, out);
+  cudaError_t err = cudaDeviceSynchronize();
+  if (err != cudaSuccess) { fprintf(stderr, "%s: %s\n", name, cudaGetErrorString(err)); return {name, 0, 0, 0}; }
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(a);
+    gather48_kernel<SMEM><<<ctas, 1024, smem>>>(grids, hgrids, stride, py, px, iters, out);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    if (ms < best) best = ms;
+  }
+  const double samples = (double)ctas * 1024 * iters;
+  cudaFree(out);
+  return {name, samples / (best * 1e-3) / 1e9, samples * 32 / (best * 1e-3) / 1e9, best};
+}
 
 template <int MODE, int PAIR, int RANDOM>
 Result run(const char* name, const float* grids, long long stride, int py, int px, int ctas, int iters) {
@@ -116,6 +181,21 @@ int main() {
   rs.push_back(run<1, 1, 0>("coherent_l2only_zpair_ldg64", d_pair, pair, PY2, PX2, ctas, iters / 4));
   rs.push_back(run<0, 0, 1>("random_l2_skewed_ldg32", d_skew, skew, PY, PX, ctas, iters / 8));
   rs.push_back(run<0, 1, 1>("random_l2_zpair_ldg64", d_pair, pair, PY2, PX2, ctas, iters / 8));
+  {
+    // n1: 48^3, fp32 skewed through L1 (2 CTAs x 1024 threads per SM) against the fp16 shared-memory copy
+    // (1 CTA x 1024 per SM); short walks (256 samples per thread ~ one batch of rays per staged grid) and
+    // long ones (staging amortised away)
+    const int PY48 = 48 + (((3 - 48 % 32) + 32) % 32), PX48 = 48 * PY48 + (((9 - (48 * PY48) % 32) + 32) % 32);
+    const long long skew48 = (long long)R48 * PX48;
+    float* d48; __half* h48;
+    cudaMalloc(&d48, skew48 * kGrids * 4); cudaMemset(d48, 0, skew48 * kGrids * 4);
+    cudaMalloc(&h48, (size_t)R48 * R48 * R48 * kGrids * 2); cudaMemset(h48, 0, (size_t)R48 * R48 * R48 * kGrids * 2);
+    rs.push_back(run48<0>("r48_l1_fp32_skewed_ldg32", d48, h48, skew48, PY48, PX48, sms * 2, 4096));
+    rs.push_back(run48<1>("r48_smem_fp16_lds16_long_walk", d48, h48, skew48, PY48, PX48, sms, 4096));
+    rs.push_back(run48<0>("r48_l1_fp32_skewed_ldg32_256_samples", d48, h48, skew48, PY48, PX48, sms * 2, 256));
+    rs.push_back(run48<1>("r48_smem_fp16_lds16_256_samples_incl_staging", d48, h48, skew48, PY48, PX48, sms, 256));
+    cudaFree(d48); cudaFree(h48);
+  }
   int clk = 0; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("{\n \"sms\": %d, \"sm_clock_khz_attr\": %d, \"ctas\": %d, \"threads\": 256, \"bytes_per_sample\": 32,\n", sms, clk, ctas);
   printf(" \"what\": \"pure 8-corner gather kernels (no march, no ALU): Gsample/s and algorithmic GB/s (32 B per sample)\",\n");

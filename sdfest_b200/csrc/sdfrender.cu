@@ -331,7 +331,13 @@ __device__ __forceinline__ void scatter_sdf_warp(float* __restrict__ gs, const G
     }
     if (merge && !lower) alive = false;
   }
+#ifdef SDFR_AB_DROP_RED
+  /* A/B only (scripts/ab/ab_variants.sh): everything but the RED.ADDs themselves -- the upper bound of
+   * what any privatisation of the scatter could save */
+  if (alive && w[0] == 1.2345e30f) scatter_sdf<RT>(gs, G, base, w);
+#else
   if (alive) scatter_sdf<RT>(gs, G, base, w);
+#endif
 }
 
 /* Pose gradients of a CTA.  Every thread keeps its 13 moment sums (sdfr_core.cuh:
