@@ -1,9 +1,16 @@
-"""BASELINE configs 3 and 5, measured on the GPU box.
+"""BASELINE configs 1, 3 and 5, measured on the GPU box.
 
     python scripts/gpu_configs.py [tag]                                     # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node G --master-addr 127.0.0.1 \\
         --master-port 29544 scripts/gpu_configs.py [tag]                    # G GPUs (C5 shards)
 
+C1  random-init SDFVAE decoder (latent 8 -> 64^3, the reference's architecture) + ONE 640x480 depth render,
+    forward and backward down to the latent, through the public autograd API (render_depth_gpu).  Three
+    arms on the same decoder weights: (a) the plain PyTorch decoder + this library's renderer -- what a user
+    of the reference gets by switching the renderer alone; (b) the fused-tail decoder + renderer
+    (FusedTailDecoder); (c) the plain PyTorch decoder + the reference's own CUDA extension behind a
+    minimal autograd wrapper (sdf_renderer.py:296-357 needs open3d at import), when oracle/_ref exists.
+    The decoder decodes residuals around an analytic mug (a random-init decoder has no surface).  Rank 0.
 C3  multi-instance frame: 16 objects with independent 128^3 grids on a 4x4 lattice rendered into ONE
     1280x720 depth map (per-pixel minimum positive depth), forward + backward with all four gradients.
     Ours: sdfr_forward_composite + sdfr_backward_composite (2 launches).  Beside it, when oracle/_ref is
@@ -65,6 +72,82 @@ def timed(fn, n, warm=3, flush=None):
         torch.cuda.synchronize()
         total += a.elapsed_time(b)
     return total / n
+
+
+# ---------------------------------------------------------------------------------------------
+# C1
+# ---------------------------------------------------------------------------------------------
+def config1():
+    from sdfest_b200.differentiable_renderer import render_depth_gpu
+
+    W, H, R = 640, 480, 64
+    cam = Camera(W, H, 320.0, 320.0, 320.0, 240.0, pixel_center=0.5)
+    fused = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
+    plain, base = fused.decoder, fused.base  # the same weights as a plain torch module (cuDNN)
+    hyp = syn.make_hypotheses(1, seed=0, device=dev)
+    z0 = 0.3 * torch.randn(1, 8, generator=torch.Generator().manual_seed(1)).to(dev)
+    up = torch.randn(H, W, generator=torch.Generator().manual_seed(2)).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def leaves():
+        return [t.detach().clone().requires_grad_(True)
+                for t in (z0, hyp["position"][0], hyp["orientation"][0], hyp["inv_scale"])]
+
+    def run(decode, render):
+        z, p, q, s = leaves()
+        d = render(decode(z), p, q, s)
+        d.backward(up)
+        return d.detach(), z.grad, p.grad, q.grad, s.grad
+
+    dec_plain = lambda z: (plain(z)[0, 0] + base).contiguous()  # noqa: E731
+    dec_fused = lambda z: fused(z)[0, 0]  # noqa: E731
+    ours = lambda g, p, q, s: render_depth_gpu(g, p, q, s, threshold=THR, camera=cam)  # noqa: E731
+    res = {"workload": "C1: random-init SDFVAE decoder (latent 8 -> 64^3) + one 640x480 depth render, forward + "
+                       "backward to latent / pose / scale, L2 flushed before every step"}
+    ref_out = run(dec_plain, ours)
+    res["hit_pixels"] = int((ref_out[0] > 0).sum())
+    ms_a = timed(lambda: run(dec_plain, ours), 30, flush=flush)
+    ms_b = timed(lambda: run(dec_fused, ours), 30, flush=flush)
+    res["torch_decoder_our_renderer"] = {"ms": ms_a, "mpix_per_s": W * H / (ms_a * 1e-3) / 1e6}
+    res["fused_tail_decoder_our_renderer"] = {"ms": ms_b, "mpix_per_s": W * H / (ms_b * 1e-3) / 1e6}
+    ms_dec = timed(lambda: dec_plain(z0.clone().requires_grad_(True)).sum().backward(), 30, flush=flush)
+    res["torch_decoder_alone_fwd_bwd_ms"] = ms_dec
+    try:
+        from oracle import build_ref
+        ext = build_ref.load_module()
+    except Exception as e:  # noqa: BLE001
+        ext, res["reference_cuda_ext"] = None, {"unavailable": str(e)[:200]}
+    if ext is not None:
+        class RefRender(torch.autograd.Function):  # sdf_renderer.py:296-357, minus the open3d import
+            @staticmethod
+            def forward(ctx, sdf, p, q, s):
+                (d,) = ext.forward(sdf, p, q, s, W, H, 320.0, 240.0, 320.0, 320.0, THR)
+                ctx.save_for_backward(d, sdf, p, q, s)
+                return d
+
+            @staticmethod
+            def backward(ctx, g):
+                d, sdf, p, q, s = ctx.saved_tensors
+                return tuple(ext.backward(g.contiguous(), d, sdf, p, q, s, W, H, 320.0, 240.0, 320.0, 320.0))
+
+        theirs = run(dec_plain, RefRender.apply)
+        ms_c = timed(lambda: run(dec_plain, RefRender.apply), 30, flush=flush)
+        both = (theirs[0] > 0) & (ref_out[0] > 0)
+        rel = ((theirs[0] - ref_out[0]).abs() / theirs[0].clamp(min=1e-6))[both]
+
+        def gerr(a, b):
+            return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+        res["reference_cuda_ext"] = {
+            "ms": ms_c, "mpix_per_s": W * H / (ms_c * 1e-3) / 1e6, "speedup_renderer_swapped": ms_c / ms_a,
+            "speedup_fused_decoder_too": ms_c / ms_b,
+            "hit_mask_agreement": float(((theirs[0] > 0) == (ref_out[0] > 0)).float().mean()),
+            "depth_within_1e-5_rel": float((rel <= 1e-5).float().mean()),
+            "latent_grad_max_norm_rel_err": gerr(ref_out[1], theirs[1]),
+            "position_grad_max_norm_rel_err": gerr(ref_out[2], theirs[2]),
+            "orientation_grad_max_norm_rel_err": gerr(ref_out[3], theirs[3]),
+            "inv_scale_grad_max_norm_rel_err": gerr(ref_out[4], theirs[4])}
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -268,6 +351,8 @@ def config5():
                     "latent = 0.1 tanh(net), orientation = the network's unit quaternion"}
 
 
+if rank == 0 and os.environ.get("SKIP_C1", "0") != "1":
+    out["c1"] = config1()
 if rank == 0 and os.environ.get("SKIP_C3", "0") != "1":
     out["c3"] = config3()
 if world > 1:
