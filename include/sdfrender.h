@@ -448,6 +448,18 @@ int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const f
                               float* sdf, long long sdf_stride, int sdf_layout, void* stream);
 
 /*
+ * sdfr_decoder_tail_forward that also produces the empty-space bounds of the grids it writes (one entry per
+ * hypothesis, identical to sdfr_grid_bounds on the written grids for the given poses and threshold): the
+ * values are compared with the hit-threshold bound as they are stored, so the loop needs no separate read of
+ * the grids.
+ */
+int sdfr_decoder_tail_forward_bounds(const float* x, int channels, int in_size, const float* weight,
+                                     const float* bias, const float* base, int batch, int resolution,
+                                     float* sdf, long long sdf_stride, int sdf_layout,
+                                     const float* position, const float* inv_scale, float threshold,
+                                     sdfr_cell_bounds* bounds, void* stream);
+
+/*
  * Adjoint of sdfr_decoder_tail_forward w.r.t. x (the decoder is frozen in the estimation loop,
  * simple_setup.py:65: no weight / bias gradients):  grad_x[b] = (written, not accumulated)
  *   weight[c] * W^T ( coef[b] * grad_sdf[b] + grad_sdf_extra[b] ),

@@ -86,6 +86,8 @@ SIGNATURES = {
         c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, c_uint, _P]),
     "sdfr_decoder_tail_forward": (
         c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_longlong, c_int, _P]),
+    "sdfr_decoder_tail_forward_bounds": (
+        c_int, [_P, c_int, c_int, _P, _P, _P, c_int, c_int, _P, c_longlong, c_int, _P, _P, c_float, _P, _P]),
     "sdfr_decoder_tail_backward": (
         c_int, [_P, c_longlong, _P, _P, _P, c_longlong, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "sdfr_upsample3d_forward": (c_int, [_P, c_int, c_int, c_int, _P, _P]),

@@ -52,6 +52,8 @@ struct TailParams {
   long long g_extra_stride;
   float* __restrict__ g_x; /* [B, C, S, S, S] */
   int z_offset;
+  CellBounds* __restrict__ bounds; /* forward, optional: per-hypothesis empty-space bounds (tau pre-set by
+                                    * sdfr_bounds_init_kernel), updated from the values as they are written */
   int xb; /* forward: output x-planes per CTA */
   int fast4; /* forward: 4-row groups (tail_forward_plan); backward: float4 loads of the gradient planes */
 };
@@ -129,6 +131,10 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
   __syncthreads();
   const float bias = P.bias ? __ldg(P.bias) : 0.0f;
   float* __restrict__ out = P.out + (size_t)b * P.out_stride;
+  /* empty-space bounds while the grid is being written (sdfr_bounds_scan_kernel's rule: bounding box of the
+   * voxels below tau, low side moved down one cell): saves the separate read of the grids */
+  const float tau = P.bounds ? P.bounds[b].tau : -3.0e38f;
+  int vxl = 0x7fffffff, vxh = -1, vyl = 0x7fffffff, vyh = -1, vzl = 0x7fffffff, vzh = -1;
   if (P.fast4) {
     /* A thread keeps ONE output column oz (z-interpolation constants in registers) and produces FOUR
      * consecutive output rows per step: the <= 4 source rows they read are blended in x and z once
@@ -179,11 +185,15 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
           const int oy = 4 * g + i;
           if (base) v += __ldg(base + oy * R);
           o[(size_t)oy * P.py] = v;
+          if (v < tau) {
+            vxl = min(vxl, ox); vxh = max(vxh, ox);
+            vyl = min(vyl, oy); vyh = max(vyh, oy);
+            vzl = oz; vzh = oz;
+          }
         }
       }
     }
-    return;
-  }
+  } else {
   for (int j = threadIdx.x; j < nxo * R * R; j += blockDim.x) {
     const int dx = j / (R * R), r = j - dx * R * R;
     const int oy = r / R, oz = r - oy * R, ox = ox0 + dx;
@@ -199,6 +209,22 @@ sdfr_decoder_tail_forward_kernel(const __grid_constant__ TailParams P) {
     float v = (lx0 * (ly0 * a0 + ly1 * a1) + lx1 * (ly0 * b0 + ly1 * b1)) + bias;
     if (P.base) v += __ldg(P.base + (size_t)ox * R * R + r);
     out[(size_t)ox * P.px + oy * P.py + oz] = v;
+    if (v < tau) {
+      vxl = min(vxl, ox); vxh = max(vxh, ox);
+      vyl = min(vyl, oy); vyh = max(vyh, oy);
+      vzl = min(vzl, oz); vzh = max(vzh, oz);
+    }
+  }
+  }
+  if (P.bounds) { /* uniform over the grid */
+    vxl = __reduce_min_sync(0xffffffffu, vxl); vxh = __reduce_max_sync(0xffffffffu, vxh);
+    vyl = __reduce_min_sync(0xffffffffu, vyl); vyh = __reduce_max_sync(0xffffffffu, vyh);
+    vzl = __reduce_min_sync(0xffffffffu, vzl); vzh = __reduce_max_sync(0xffffffffu, vzh);
+    if ((threadIdx.x & 31) == 0 && vxh >= 0) {
+      bounds_commit(P.bounds + b, 0, vxl, vxh, R);
+      bounds_commit(P.bounds + b, 1, vyl, vyh, R);
+      bounds_commit(P.bounds + b, 2, vzl, vzh, R);
+    }
   }
 }
 

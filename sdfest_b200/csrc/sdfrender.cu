@@ -2084,6 +2084,32 @@ int sdfr_decoder_tail_forward(const float* x, int channels, int in_size, const f
   return launch_tail_forward(P, batch, (cudaStream_t)stream);
 }
 
+int sdfr_decoder_tail_forward_bounds(const float* x, int channels, int in_size, const float* weight,
+                                     const float* bias, const float* base, int batch, int R, float* sdf,
+                                     long long sdf_stride, int layout, const float* position,
+                                     const float* inv_scale, float threshold, sdfr_cell_bounds* bounds,
+                                     void* stream) {
+  if (int rc = tail_check(channels, in_size, R, batch)) return rc;
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED)
+    return fail(SDFR_E_FLAGS, "unknown sdf_layout");
+  if (!(threshold >= 0.0f)) return fail(SDFR_E_SHAPE, "threshold must be >= 0");
+  if (batch == 0) return 0;
+  if (!x || !weight || !sdf || !position || !inv_scale || !bounds)
+    return fail(SDFR_E_NULL, "decoder tail + bounds: NULL pointer");
+  const Grid G = make_grid(R, layout);
+  if (sdf_stride < (long long)R * G.px)
+    return fail(SDFR_E_SHAPE, "decoder tail: sdf_stride smaller than one grid in this layout");
+  CellBounds* out = reinterpret_cast<CellBounds*>(bounds);
+  sdfr_bounds_init_kernel<<<batch, 32, 0, (cudaStream_t)stream>>>(position, inv_scale, batch, batch, threshold, out);
+  TailParams P;
+  memset(&P, 0, sizeof(P));
+  P.x = x; P.weight = weight; P.bias = bias; P.base = base;
+  P.C = channels; P.S = in_size; P.R = R;
+  P.out = sdf; P.out_stride = sdf_stride; P.py = G.py; P.px = G.px;
+  P.bounds = out;
+  return launch_tail_forward(P, batch, (cudaStream_t)stream);
+}
+
 int sdfr_decoder_tail_backward(const float* grad_sdf, long long grad_sdf_stride,
                                const float* n_overlap, const float* upstream,
                                const float* grad_sdf_extra, long long extra_stride,

@@ -486,7 +486,7 @@ class HypothesisOptimizer:
         B, R, M = self.position.shape[0], self._R, self._M
         W, H, cx, cy, fx, fy = _camera_params(self.camera)
         grids, gstride, layout = self._grid_op
-        dec, x = self.decoder, None
+        dec, x, tail_bounds = self.decoder, None, None
         main, side = torch.cuda.current_stream(), self._side
 
         def on_side(fn):
@@ -506,9 +506,18 @@ class HypothesisOptimizer:
             x = dec.trunk(self.latent).contiguous()  # autograd graph: latent -> x only
             w, bias = dec.tail_parameters()
             C, S = int(x.shape[1]), int(x.shape[2])
-            _lib.check(lib.sdfr_decoder_tail_forward(
-                x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
-                gstride, layout, _stream()), "sdfr_decoder_tail_forward")
+            if self._bounds is not None:
+                # the tail compares every value with the hypothesis' hit-threshold bound as it stores it:
+                # the empty-space bounds cost no extra read of the grids
+                _lib.check(lib.sdfr_decoder_tail_forward_bounds(
+                    x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
+                    gstride, layout, self.position.data_ptr(), self._inv_scale.data_ptr(), self.threshold,
+                    self._bounds.data_ptr(), _stream()), "sdfr_decoder_tail_forward_bounds")
+                tail_bounds = self._bounds.data_ptr()
+            else:
+                _lib.check(lib.sdfr_decoder_tail_forward(
+                    x.data_ptr(), C, S, w.data_ptr(), _ptr(bias), _ptr(dec.base), B, R, grids.data_ptr(),
+                    gstride, layout, _stream()), "sdfr_decoder_tail_forward")
             if side is not None:
                 main.wait_stream(side)
         flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
@@ -517,9 +526,9 @@ class HypothesisOptimizer:
         render_flags = flags | (_lib.SDF_GRAD_EXACT if self.sdf_grad_mode == "exact" else 0)
         # empty-space bounds of this iteration's grids and poses (the hit-threshold bound depends on
         # position and scale): rays that cannot hit anything are not marched, all others unchanged
-        bounds = None
+        bounds = tail_bounds
         self._constraint_launch()
-        if self._bounds is not None:
+        if self._bounds is not None and bounds is None:
             bounds = self._grid_bounds(self.position.data_ptr(), self._inv_scale.data_ptr(), self._bounds)
 
         def point_loss():

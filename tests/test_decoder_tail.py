@@ -209,6 +209,51 @@ def test_tail_skewed_output_and_deferred_scaling(cuda_device):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("C,S,R,layout", [(4, 30, 64, "skewed"), (4, 30, 64, "dense"), (3, 7, 18, "dense")])
+def test_tail_forward_with_bounds_equals_tail_then_scan(cuda_device, C, S, R, layout):
+    """sdfr_decoder_tail_forward_bounds writes the same grids as sdfr_decoder_tail_forward and the bounds
+    sdfr_grid_bounds finds on them (both kernel paths: 4-row groups and the generic one)."""
+    import ctypes
+
+    lib, dev = _lib.lib(), cuda_device
+    B = 5
+    rng = np.random.default_rng(11)
+    x = torch.tensor(rng.standard_normal((B, C, S, S, S)), dtype=torch.float32, device=dev)
+    w = torch.tensor(rng.standard_normal(C) * 0.2, dtype=torch.float32, device=dev)
+    b = torch.tensor([0.3], device=dev)
+    # a base with a surface: a ball, so that the bounds are a proper sub-box for some hypotheses
+    ax = torch.linspace(-1, 1, R, device=dev)
+    base = ((ax[:, None, None] ** 2 + ax[None, :, None] ** 2 * 2 + ax[None, None, :] ** 2 * 4).sqrt() - 0.8).contiguous()
+    pos = torch.tensor(rng.standard_normal((B, 3)) * 0.1 + [0, 0, -0.8], dtype=torch.float32, device=dev)
+    inv_s = torch.tensor(1.0 / (0.1 + 0.2 * rng.random(B)), dtype=torch.float32, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    if layout == "skewed":
+        n = ctypes.c_longlong(0)
+        _lib.check(lib.sdfr_skewed_pitches(R, None, None, ctypes.byref(n)), "pitches")
+        stride, lay = int(n.value), _lib.LAYOUT_SKEWED
+    else:
+        stride, lay = R ** 3, _lib.LAYOUT_DENSE
+    for thr in (0.005, 0.2):
+        g0 = torch.full((B, stride), -5.0, device=dev)
+        g1 = torch.full((B, stride), -5.0, device=dev)
+        b0 = torch.full((B, 8), -7, dtype=torch.int32, device=dev)
+        b1 = torch.full((B, 8), -9, dtype=torch.int32, device=dev)
+        _lib.check(lib.sdfr_decoder_tail_forward(x.data_ptr(), C, S, w.data_ptr(), b.data_ptr(), base.data_ptr(), B, R,
+                                                 g0.data_ptr(), stride, lay, st), "tail")
+        _lib.check(lib.sdfr_grid_bounds(g0.data_ptr(), R, stride, lay, pos.data_ptr(), inv_s.data_ptr(), B, thr,
+                                        b0.data_ptr(), st), "scan")
+        _lib.check(lib.sdfr_decoder_tail_forward_bounds(
+            x.data_ptr(), C, S, w.data_ptr(), b.data_ptr(), base.data_ptr(), B, R, g1.data_ptr(), stride, lay,
+            pos.data_ptr(), inv_s.data_ptr(), thr, b1.data_ptr(), st), "tail + bounds")
+        torch.cuda.synchronize()
+        assert torch.equal(g0, g1)
+        assert torch.equal(b0[:, :7], b1[:, :7]), (b0, b1)
+        assert bool((b0[:, 3] >= b0[:, 0]).any())  # not all empty
+    assert lib.sdfr_decoder_tail_forward_bounds(x.data_ptr(), C, S, w.data_ptr(), None, None, B, R, g1.data_ptr(),
+                                                stride, lay, None, inv_s.data_ptr(), 0.005, b1.data_ptr(), st) == -1
+
+
+@pytest.mark.gpu
 def test_fused_tail_decoder_matches_plain_decoder(cuda_device):
     torch.manual_seed(1)
     dec = SDFDecoder(64).to(cuda_device).eval()

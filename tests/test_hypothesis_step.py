@@ -631,3 +631,29 @@ def test_result_selection_with_a_threshold_above_one_uses_the_separate_pass(cuda
     # every valid pixel is an inlier: missed ones have relative error 1 < 1.5
     torch.testing.assert_close(b.inlier_ratio, a.inlier_ratio, rtol=0, atol=1e-2)
     assert float(b.inlier_ratio.min()) > 0.9
+
+
+@pytest.mark.gpu
+def test_fused_optimizer_on_a_device_that_is_not_current(cuda_device):
+    """Tensors on cuda:1 while cuda:0 is the current device: the fused iteration, its second stream, the
+    captured graph and the autograd operators all run on the tensors' device (the library launches on the
+    CURRENT device's stream and never calls cudaSetDevice, so the Python side must make it current) and
+    give the results of the same optimiser built on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    torch.cuda.set_device(0)
+    a = _make_optimizers(torch.device("cuda:0"), 4, True, "fused")
+    b = _make_optimizers(torch.device("cuda:1"), 4, True, "fused")
+    assert torch.cuda.current_device() == 0 and b.position.device.index == 1
+    for _ in range(3):
+        la, lb = a.step().clone(), b.step().clone()
+    torch.testing.assert_close(lb.cpu(), la.cpu(), rtol=2e-3, atol=1e-5)
+    b.capture(warmup=1)
+    a.step(), a.step()
+    lb = b.step().clone()
+    torch.cuda.synchronize(1)
+    torch.testing.assert_close(lb.cpu(), a.last_losses.cpu(), rtol=2e-3, atol=1e-5)
+    assert torch.cuda.current_device() == 0
+    t = _make_optimizers(torch.device("cuda:1"), 4, False, "torch")
+    f = _make_optimizers(torch.device("cuda:1"), 4, False, "fused")
+    torch.testing.assert_close(f.step().cpu(), t.step().cpu(), rtol=2e-3, atol=1e-5)
