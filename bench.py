@@ -49,6 +49,10 @@ def parse_args():
     p.add_argument("--no-ref-ext", action="store_true",
                    help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                   help="c2 (default) is the configuration the metric is quoted on and the only one with the "
+                        "full contract line; c1 / c3 / c4 / c5 run BASELINE.json's other configurations "
+                        "(scripts/gpu_configs.py, scripts/gpu_sweep.py) and print their result as one line")
     return p.parse_args()
 
 
@@ -298,6 +302,38 @@ def divert_stdout():
     os.dup2(2, 1)
 
 
+def run_other_workload(args, rank, world):
+    """BASELINE.json's configurations 1, 3, 4, 5 through their measurement scripts (parity for them lives in
+    tests/test_bench_parity.py and tests/test_dropin_reference.py); one JSON line on rank 0."""
+    import runpy
+
+    tag = f"bench_{args.workload}"
+    if args.workload == "c4":
+        script, out_file, key = "gpu_sweep.py", f"{tag}_sweep_n{world}.json", None
+    else:
+        script, out_file, key = "gpu_configs.py", f"{tag}_configs_n{world}.json", args.workload
+        for k in ("c1", "c3", "c5"):
+            if k != args.workload:
+                os.environ[f"SKIP_{k.upper()}"] = "1"
+    sys.argv = [os.path.join(ROOT, "scripts", script), tag]
+    runpy.run_path(sys.argv[0], run_name="__main__")
+    if rank != 0:
+        return
+    with open(os.path.join(ROOT, "gpurun_out", out_file)) as f:
+        res = json.load(f)
+    res = res[key] if key else res
+    metric = {
+        "c1": ("depth-render fwd+bwd of one frame behind the decoder", res.get("fused_tail_decoder_our_renderer", {}).get("mpix_per_s"), "Mpix/s"),
+        "c3": ("composite frame fwd+bwd", res.get("mpix_per_s"), "Mpix/s"),
+        "c4": ("hypothesis sweep", res.get("hyp_iter_per_s"), "hypothesis-iterations/s"),
+        "c5": ("analysis-by-synthesis loop", res.get("instance_iter_per_s"), "instance-iterations/s"),
+    }[args.workload]
+    metric, value, unit = metric
+    emit({"metric": metric, "value": value, "unit": unit, "n_gpus": world,
+          "higher_is_better": True, "data": "synthetic", "dtype": "f32", "vs_baseline": None,
+          "config": {"workload": res.get("workload", args.workload)}, "result": res})
+
+
 def main():
     args = parse_args()
     divert_stdout()
@@ -307,6 +343,9 @@ def main():
 
     if args.impl == "reference":
         run_reference_arm(args, rank)
+        return
+    if args.workload != "c2":
+        run_other_workload(args, rank, world)
         return
 
     import torch

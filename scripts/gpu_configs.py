@@ -357,7 +357,8 @@ if rank == 0 and os.environ.get("SKIP_C3", "0") != "1":
     out["c3"] = config3()
 if world > 1:
     dist.barrier()
-out["c5"] = config5()
+if os.environ.get("SKIP_C5", "0") != "1":
+    out["c5"] = config5()
 if rank == 0:
     tag = sys.argv[1] if len(sys.argv) > 1 else "cfg"
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
