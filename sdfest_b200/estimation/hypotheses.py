@@ -107,6 +107,12 @@ class HypothesisOptimizer:
     The reference keeps references to the live tensors there (:207-210), so what it returns is always
     the last iterate (``result("last_iteration")``); the copies are what the code evidently intends.
 
+    Serving many observations with ONE captured graph: ``point_capacity`` (fused path, one shared
+    observation) stores the observed points in a buffer of that fixed size (padding outside every volume,
+    where the point loss is exactly 0; the mean is taken over the true count), so that ``reset(...)`` can load
+    the next observation and initial estimate into the same device buffers and ``step()`` keeps replaying
+    the graph captured for the first one (``SDFPipeline`` does this).
+
     ``optimizer``: ``"fused"`` runs the whole iteration as direct C-ABI launches -- decoder tail,
     ``sdfr_compare_fused``, ``sdfr_point_loss_fused``, tail adjoint, and ONE
     ``sdfr_hypothesis_step`` kernel for the gradient chain rule, Adam on all four groups, the
@@ -126,7 +132,7 @@ class HypothesisOptimizer:
                  inlier_threshold: Optional[float] = None,
                  camera_positions: Optional[torch.Tensor] = None,
                  camera_orientations: Optional[torch.Tensor] = None,
-                 point_constraint=None):
+                 point_constraint=None, point_capacity: int = 0):
         if (decoder is None) == (sdf is None):
             raise ValueError("give either fixed `sdf` grids or a `decoder` with `latent`")
         if optimizer not in ("auto", "fused", "torch"):
@@ -174,6 +180,9 @@ class HypothesisOptimizer:
         B = self.position.shape[0]
         self.point_counts = None  # (B,) points hypothesis b owns, when the clouds differ
         self._views = None
+        self.point_capacity, self._n_points, self.max_points = int(point_capacity), None, int(max_points)
+        if point_capacity and (self.optimizer_impl != "fused" or multiview or self.depth_obs.dim() != 2):
+            raise ValueError("point_capacity needs the fused path and one shared observation (H,W)")
         if multiview:
             V = int(camera_positions.shape[0])
             if instance is not None:
@@ -192,6 +201,9 @@ class HypothesisOptimizer:
                 raise ValueError("`instance` needs one observed depth map per object instance (K,H,W)")
             self.points = losses.subsample_points(losses.depth_to_pointcloud(self.depth_obs, camera),
                                                   max_points)
+            if point_capacity:
+                self.depth_obs = self.depth_obs.clone()  # reset() overwrites it: never the caller's tensor
+                self._load_points(self.points, int(point_capacity))
         else:
             # object instances: hypothesis b is compared with the depth map and the points of instance
             # instance[b] (default: one map per hypothesis)
@@ -229,6 +241,61 @@ class HypothesisOptimizer:
         if self.optimizer_impl == "fused":
             with torch.cuda.device(self.position.device):
                 self._init_fused()
+
+    def _load_points(self, points: torch.Tensor, capacity: int) -> None:
+        """Observed points (M,3) into the fixed-size buffer (allocated on first use)."""
+        n = int(points.shape[0])
+        if n > capacity:
+            raise ValueError(f"{n} observed points exceed point_capacity {capacity}")
+        if self.points is None or self.points.shape[0] != capacity:
+            self.points = torch.empty((capacity, 3), dtype=torch.float32, device=points.device)
+        self.points.fill_(losses.PAD_COORDINATE)
+        self.points[:n].copy_(points)
+        self._n_points = n
+
+    def reset(self, position: torch.Tensor, orientation: torch.Tensor, scale: torch.Tensor,
+              latent: Optional[torch.Tensor] = None, depth_obs: Optional[torch.Tensor] = None) -> None:
+        """Start over from a new initial estimate -- and, with ``depth_obs``, a new observation -- in the SAME
+        device buffers: optimiser state, result selection and losses are cleared, and a captured graph stays
+        valid (``step()`` keeps replaying it).  Fused path only; a new observation needs ``point_capacity``
+        (or ``pc_weight`` 0).  Raises ValueError when the new cloud does not fit the capacity."""
+        if self.optimizer_impl != "fused":
+            raise RuntimeError("reset() is for optimizer='fused'")
+        if self._V or self.point_counts is not None:
+            raise RuntimeError("reset() supports one shared observation (no views, no instances)")
+        with torch.no_grad(), torch.cuda.device(self.position.device):
+            if depth_obs is not None:
+                if tuple(depth_obs.shape) != tuple(self.depth_obs.shape):
+                    raise ValueError("depth_obs must keep its shape")
+                if self._M and not self.point_capacity:
+                    raise RuntimeError("a new observation needs point_capacity (the cloud size is baked in)")
+                if self._M:
+                    pts = losses.subsample_points(losses.depth_to_pointcloud(depth_obs, self.camera), self.max_points)
+                    self._load_points(pts, self.point_capacity)  # before any buffer is touched: may raise
+                    self._up_p.fill_((self.pc_weight / self._n_points) if self._n_points else 0.0)
+                self.depth_obs.copy_(depth_obs)
+            self.position.copy_(position.reshape(self.position.shape))
+            self.orientation.copy_(orientation.reshape(self.orientation.shape))
+            self.scale.copy_(scale.reshape(self.scale.shape))
+            if self.latent is not None:
+                if latent is None:
+                    raise ValueError("latent expected")
+                self.latent.copy_(latent.reshape(self.latent.shape))
+            for t in (self._m, self._v, self._t, self._small, self._loss):
+                t.zero_()
+            if self._g_raw is not None:
+                self._g_raw.zero_()
+                self._loss_extra.zero_()
+            if self.inlier_threshold is not None:
+                self._inl.zero_()
+                self.inlier_ratio.zero_()
+                self.best_inlier_ratio.fill_(-1.0)
+                self.best_iteration.fill_(-1)
+                self._iteration.zero_()
+                if self.inlier_threshold <= 1.0:
+                    self._inl[1].fill_(float((self.depth_obs != 0).sum()))
+            self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale of the new estimate
+        self.last_losses = None
 
     # ------------------------------------------------------------------------------------
     # optimizer="fused": one iteration = a handful of C-ABI launches, no autograd outside the trunk
@@ -301,7 +368,14 @@ class HypothesisOptimizer:
             self._view_up_p = [torch.full((B,), self.pc_weight / m if m else 0.0, dtype=torch.float32, device=dev)
                                for m in self._view_M]
         self._M = M
-        if self.point_counts is None:
+        if self.point_capacity:
+            # fixed-size buffer: the weight pc_weight / (true count) lives in device memory (upstream and,
+            # with SDFR_LOSS_WEIGHTED, the loss), so reset() can change it under a captured graph
+            self._points_stride, self._point_flags = 0, _lib.LOSS_WEIGHTED
+            self._point_weight = 1.0
+            n = self._n_points
+            self._up_p = torch.full((B,), (self.pc_weight / n) if n else 0.0, dtype=torch.float32, device=dev)
+        elif self.point_counts is None:
             self._points_stride, self._point_flags = 0, 0
             self._point_weight = (self.pc_weight / M) if M else 0.0
             self._up_p = torch.full((B,), self._point_weight, dtype=torch.float32, device=dev)

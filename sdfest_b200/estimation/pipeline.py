@@ -41,7 +41,12 @@ class SDFPipeline:
     (3.0), ``mean_shape`` (False), ``init_view`` ("first"), ``result_selection_strategy``
     ("last_iteration" | "best_inlier_ratio"), ``relative_inlier_threshold`` (0.03), ``far_field``,
     ``init`` = {``backbone_type``, ``normalize_pose``, ``head``: {``orientation_repr``}}; extensions:
-    ``cuda_graph`` (True), ``fused_decoder`` (True), ``n_hypotheses`` (1), ``max_points`` (0 = all).
+    ``cuda_graph`` (True), ``fused_decoder`` (True), ``n_hypotheses`` (1), ``max_points`` (0 = all),
+    ``reuse_graph`` (True): keep the captured iteration of a call and replay it for later calls of the same
+    shape (one camera-frame view, shape optimisation on, no point constraint) -- the next observation and
+    initial estimate are loaded into the same device buffers (``HypothesisOptimizer.reset``), which removes
+    the three eager warm-up iterations and the capture (~9 ms) from every call after the first;
+    ``profile`` (False): record ``last_timings``.
     ``vae``: a module with ``decode(latent) -> (B,1,R,R,R)`` and a ``decoder`` attribute (the reference's
     ``SDFVAE``); ``init_network``: ``points (1,M,3) | depth (1,H,W) -> (latent, position, scale,
     orientation representation)`` (the reference's ``SDFPoseNet``).
@@ -63,6 +68,11 @@ class SDFPipeline:
             p.requires_grad_(False)  # both networks are frozen in the pipeline (simple_setup.py:65, 81)
         self._fused_decoder = None
         self.last_optimizer = None  # the HypothesisOptimizer of the last call (losses, inlier ratios)
+        # config["profile"]: wall time of the call's phases (with device synchronisation between them: it
+        # costs a few hundred microseconds per call, so it is off by default), the reference's
+        # log_runtime breakdown (estimation/scripts/real_data.py:286-319) for this pipeline
+        self.last_timings = None
+        self._graph_cache = {}  # (hypotheses, latent size, decoder) -> captured HypothesisOptimizer
 
     # ------------------------------------------------------------------------------------------
     def _preprocess_depth(self, depth_images: torch.Tensor, masks: torch.Tensor) -> None:
@@ -148,6 +158,17 @@ class SDFPipeline:
             if camera_orientations is not None:
                 camera_orientations = camera_orientations.unsqueeze(0)
         n_imgs, dev = depth_images.shape[0], depth_images.device
+        marks = []
+
+        def mark(name):
+            if self.config.get("profile", False):
+                import time
+
+                if depth_images.is_cuda:
+                    torch.cuda.synchronize(dev)
+                marks.append((name, time.perf_counter()))
+
+        mark("start")
         world_is_camera = camera_positions is None and camera_orientations is None and n_imgs == 1
         if camera_positions is None:
             camera_positions = torch.zeros(n_imgs, 3, device=dev)
@@ -158,6 +179,7 @@ class SDFPipeline:
             self._preprocess_depth(depth_images, masks)
             latent, position, scale, orientation = self._nn_init(depth_images, camera_positions,
                                                                  camera_orientations)
+        mark("preprocess_and_init_network")
         n_hyp = int(self.config.get("n_hypotheses", 1))
         if n_hyp > 1:  # extension: perturbed copies of the initial estimate, hypothesis 0 unperturbed
             g = torch.Generator(device="cpu").manual_seed(0)
@@ -180,15 +202,37 @@ class SDFPipeline:
         else:
             obs = depth_images.contiguous()
             kw.update(camera_positions=camera_positions, camera_orientations=camera_orientations)
-        opt = HypothesisOptimizer(self.cam, self.config["threshold"], obs, position, orientation, scale, **kw)
-        self.last_optimizer = opt
         n_it = int(self.config.get("max_iterations", 50))
-        done = 0
-        if opt.optimizer_impl == "fused" and self.config.get("cuda_graph", True) and n_it > 8:
+        use_graph = self.config.get("cuda_graph", True) and n_it > 8
+        # one captured iteration serves every call of the same shape (see `reuse_graph` above)
+        reusable = (use_graph and self.config.get("reuse_graph", True) and position.is_cuda and world_is_camera
+                    and shape_optimization and point_constraint is None
+                    and isinstance(kw.get("decoder"), FusedTailDecoder) and latent.shape[1] <= 64)
+        opt, done = None, 0
+        if reusable:
+            key = (n_hyp, int(latent.shape[1]), id(kw["decoder"]), str(dev))
+            n_obs = int((obs != 0).sum()) if kw["pc_weight"] else 0
+            n_pts = min(n_obs, kw["max_points"]) if kw["max_points"] else n_obs
+            cached = self._graph_cache.get(key)
+            if cached is not None and n_pts <= cached.point_capacity <= 2 * n_pts + 8192:
+                cached.reset(position, orientation, scale, latent, obs)
+                opt, done = cached, -1  # every iteration of this call is a replay
+            else:
+                kw["point_capacity"] = max(4096, -(-n_pts // 4096) * 4096 + 4096)  # room for the next clouds
+        if opt is None:
+            opt = HypothesisOptimizer(self.cam, self.config["threshold"], obs, position, orientation, scale, **kw)
+        self.last_optimizer = opt
+        mark("optimizer_setup")
+        if done == 0 and opt.optimizer_impl == "fused" and use_graph:
             opt.capture(warmup=3)  # three eager iterations, then replays of the recorded one
             done = 3
+            if reusable:
+                self._graph_cache[key] = opt
+        done = max(done, 0)
+        mark("warmup_and_capture")
         for _ in range(n_it - done):
             opt.step()
+        mark("iterations")
         position, orientation, scale, latent_out = opt.result(self.result_selection_strategy)
         if latent_out is None:
             latent_out = latent
@@ -199,4 +243,9 @@ class SDFPipeline:
                 best = int(torch.argmin(torch.nan_to_num(opt.last_losses, nan=float("inf"))))
             position, orientation = position[best:best + 1], orientation[best:best + 1]
             scale, latent_out = scale[best:best + 1], latent_out[best:best + 1]
+        # the optimiser's buffers are reused by the next call (`reuse_graph`): hand out copies
+        position, orientation, scale, latent_out = (t.detach().clone() for t in (position, orientation, scale, latent_out))
+        mark("result")
+        if marks:
+            self.last_timings = {b[0] + "_ms": (b[1] - a[1]) * 1e3 for a, b in zip(marks[:-1], marks[1:])}
         return position, orientation, scale, latent_out
