@@ -448,7 +448,7 @@ def main():
     def scale():
         _lib.check(lib.sdfr_scale_grads(
             sums[1].data_ptr(), None, R, B, g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
-            g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, stream), "sdfr_scale_grads")
+            g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, bounds.data_ptr(), 1, stream), "sdfr_scale_grads")
 
     launches = {"kernels": 0, "steps": 0}
     pending = []  # async all_gather work handles, at most two in flight (double-buffered losses)

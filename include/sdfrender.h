@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SDFR_ABI_VERSION 9
+#define SDFR_ABI_VERSION 10
 
 #define SDFR_E_NULL (-1)  /* a required pointer is NULL */
 #define SDFR_E_SHAPE (-2) /* resolution < 2, negative sizes, image too large */
@@ -238,11 +238,14 @@ int sdfr_compare_fused(const float* sdf, int resolution, long long sdf_stride, i
                        void* stream);
 
 /* In place:  grad[b] *= (upstream ? upstream[b] : 1) / n_overlap[b]  (0 where n_overlap == 0)
- * for the buffers selected by `flags`. */
+ * for the buffers selected by `flags`.  bounds (optional): the empty-space bounds that the render which
+ * produced the gradients USED (bounds[b * bounds_stride]; bounds_stride 1 = one entry per hypothesis, 0 = the
+ * single entry of a shared grid): the SDF gradient can only be non-zero at the voxels of cells inside them,
+ * so only those are visited.  Pass NULL when the render ran without bounds. */
 int sdfr_scale_grads(const float* n_overlap, const float* upstream, int resolution, int batch,
                      float* grad_sdf, long long grad_sdf_stride, float* grad_position,
                      float* grad_orientation, float* grad_inv_scale, unsigned flags,
-                     void* stream);
+                     const sdfr_cell_bounds* bounds, long long bounds_stride, void* stream);
 
 /*
  * Multi-object frame: `n_objects` posed grids rendered into ONE depth map, per-pixel minimum

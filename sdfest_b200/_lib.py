@@ -13,7 +13,7 @@ from ctypes import c_float, c_int, c_longlong, c_uint, c_void_p
 LIB_PATH = os.environ.get("SDFR_LIB_PATH") or os.path.join(
     os.path.dirname(os.path.abspath(__file__)), "libsdfrender.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 GRAD_SDF = 0x01
 GRAD_POSITION = 0x02
@@ -63,7 +63,7 @@ SIGNATURES = {
                 c_float, _P, *_GRADS, c_uint, _P, _P]),
     "sdfr_skewed_pitches": (c_int, [c_int, _P, _P, _P]),
     "sdfr_skew_grids": (c_int, [_P, c_int, c_longlong, c_int, _P, c_longlong, _P]),
-    "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P]),
+    "sdfr_scale_grads": (c_int, [_P, _P, c_int, c_int, *_GRADS, c_uint, _P, c_longlong, _P]),
     "sdfr_point_loss_forward": (
         c_int, [_P, c_longlong, c_int, _P, c_int, c_longlong, c_int, *_POSE, c_int, _P, c_uint, _P]),
     "sdfr_point_loss_backward": (

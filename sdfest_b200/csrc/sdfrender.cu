@@ -708,12 +708,16 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
     reduce_pose(acc_s, F, Gc, b, P.grad_position, P.grad_orientation, P.grad_inv_scale, P.flags);
 }
 
-/* grad *= upstream[b] / n_overlap[b]: the normalisation the fused compare kernel defers. */
+/* grad *= upstream[b] / n_overlap[b]: the normalisation the fused compare kernel defers.  With `bounds`
+ * (the empty-space bounds the render used) only the voxels of the cells inside them are visited: a ray can
+ * only end -- and so only scatter a gradient -- in a cell whose smallest corner is below the hit-threshold
+ * bound, every other voxel of the gradient grid is still the zero it was cleared to (C2: the box holds ~21 %
+ * of the grid, 29 -> 7 us for 64 x 64^3). */
 __global__ void __launch_bounds__(256)
 sdfr_scale_grads_kernel(const float* __restrict__ n_overlap, const float* __restrict__ upstream,
                         long long grid_elems, float* __restrict__ grad_sdf, long long gs_stride,
                         float* __restrict__ gp, float* __restrict__ gq, float* __restrict__ gi,
-                        unsigned flags) {
+                        unsigned flags, const CellBounds* __restrict__ bounds, int bounds_stride, int R) {
   const int b = blockIdx.y;
   const float n = __ldg(n_overlap + b);
   const float u = upstream ? __ldg(upstream + b) : 1.0f;
@@ -730,6 +734,35 @@ sdfr_scale_grads_kernel(const float* __restrict__ n_overlap, const float* __rest
   }
   if (flags & SDFR_GRAD_SDF) {
     float* __restrict__ gs = grad_sdf + (size_t)b * gs_stride;
+    if (bounds) {
+      const CellBounds cb = bounds[(size_t)b * bounds_stride];
+      if (cb.lo[0] > cb.hi[0]) return; /* no cell can be hit: the grid is all zeros */
+      /* voxels of cells lo..hi are lo..hi+1; rows (x, y) of the box, a warp per row, lanes along z */
+      const int x0 = cb.lo[0], nx = cb.hi[0] - cb.lo[0] + 2, y0 = cb.lo[1], ny = cb.hi[1] - cb.lo[1] + 2;
+      const int z0 = cb.lo[2], z1 = cb.hi[2] + 1;
+      const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+      const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
+      /* four rows per step: the loads of all four are in flight before the first store (one dependent
+       * HBM round trip per row otherwise: 22.8 us) */
+      for (int r0 = warp; r0 < nx * ny; r0 += 4 * n_warps) {
+        for (int z = z0 + lane; z <= z1; z += 32) {
+          float v[4];
+          float* p[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int r = r0 + j * n_warps;
+            const bool ok = r < nx * ny;
+            const int rr = ok ? r : r0;
+            p[j] = gs + ((size_t)(x0 + rr / ny) * R + (y0 + rr % ny)) * R + z;
+            v[j] = ok ? *p[j] : 0.0f;
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (r0 + j * n_warps < nx * ny) *p[j] = v[j] * coef;
+        }
+      }
+      return;
+    }
     const long long n4 = ((reinterpret_cast<uintptr_t>(gs) & 15) == 0) ? grid_elems / 4 : 0;
     float4* __restrict__ gs4 = reinterpret_cast<float4*>(gs);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
@@ -1635,7 +1668,7 @@ int sdfr_compare_fused_inliers(const float* sdf, int R, long long sdf_stride, in
 #if SDFR_IN_PART(3)
 int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int batch, float* gs,
                      long long gs_stride, float* gp, float* gq, float* gi, unsigned flags,
-                     void* stream) {
+                     const sdfr_cell_bounds* bounds, long long bounds_stride, void* stream) {
   if (batch < 0) return fail(SDFR_E_SHAPE, "negative batch");
   if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
   if (int rc = check_backward_outputs(flags & ~SDFR_ZERO_GRADS, gs, gs_stride, gp, gq, gi)) return rc;
@@ -1643,6 +1676,8 @@ int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int b
   if (!n_overlap) return fail(SDFR_E_NULL, "n_overlap is NULL");
   if ((flags & SDFR_GRAD_SDF) && gs_stride == 0 && batch > 1)
     return fail(SDFR_E_SHAPE, "a shared grad_sdf grid cannot be scaled per hypothesis");
+  if (bounds_stride != 0 && bounds_stride != 1) return fail(SDFR_E_SHAPE, "bounds_stride must be 0 (one shared grid) or 1");
+  const CellBounds* cb = reinterpret_cast<const CellBounds*>(bounds);
   const long long elems = (long long)R * R * R;
   const int gx = (flags & SDFR_GRAD_SDF) ? (int)((elems / 4 + 2047) / 2048 < 1 ? 1 : (elems / 4 + 2047) / 2048) : 1;
   for (int z0 = 0; z0 < batch; z0 += 65535) {
@@ -1650,7 +1685,8 @@ int sdfr_scale_grads(const float* n_overlap, const float* upstream, int R, int b
     sdfr_scale_grads_kernel<<<dim3(gx, nz), 256, 0, (cudaStream_t)stream>>>(
         n_overlap + z0, upstream ? upstream + z0 : nullptr, elems,
         gs ? gs + (size_t)z0 * gs_stride : nullptr, gs_stride, gp ? gp + 3 * (size_t)z0 : nullptr,
-        gq ? gq + 4 * (size_t)z0 : nullptr, gi ? gi + z0 : nullptr, flags);
+        gq ? gq + 4 * (size_t)z0 : nullptr, gi ? gi + z0 : nullptr, flags,
+        cb ? cb + (size_t)z0 * bounds_stride : nullptr, (int)bounds_stride, R);
   }
   return check_launch("sdfr_scale_grads_kernel");
 }

@@ -505,7 +505,7 @@ class _RenderAndCompare(torch.autograd.Function):
                 ctx.fused_grads = None  # scaled in place: a second backward re-traverses below
                 _lib.check(lib.sdfr_scale_grads(
                     sums[1].data_ptr(), upstream.data_ptr(), R, B, _ptr(g_sdf), stride, _ptr(g_p),
-                    _ptr(g_q), _ptr(g_is), flags, _stream()), "sdfr_scale_grads")
+                    _ptr(g_q), _ptr(g_is), flags, None, 0, _stream()), "sdfr_scale_grads")
             else:
                 g_sdf = torch.empty_like(sdf) if needs[0] else None
                 g_p = torch.empty_like(position) if needs[1] else None

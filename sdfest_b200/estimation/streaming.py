@@ -108,7 +108,7 @@ class StreamedRenderCompare:
                     self.sums[0].data_ptr() + b0 * f4, self.sums[1].data_ptr() + b0 * f4, *grads,
                     self.flags, None, st), "sdfr_compare_fused")
                 _lib.check(lib.sdfr_scale_grads(
-                    self.sums[1].data_ptr() + b0 * f4, None, R, n, *grads, _lib.GRAD_ALL, st),
+                    self.sums[1].data_ptr() + b0 * f4, None, R, n, *grads, _lib.GRAD_ALL, None, 0, st),
                     "sdfr_scale_grads")
             if self.sdf_grads_to_host:
                 s_out.wait_stream(s_cmp)

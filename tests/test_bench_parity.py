@@ -108,7 +108,7 @@ def c2(cuda_device):
         g_quat.data_ptr(), g_is.data_ptr(), flags, None, stream), "sdfr_compare_fused_inliers")
     raw = [t.clone() for t in (g_sdf, g_pos, g_quat, g_is)]
     _lib.check(lib.sdfr_scale_grads(sums[1].data_ptr(), None, R, B, g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
-                                    g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, stream), "scale")
+                                    g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, None, 0, stream), "scale")
     torch.cuda.synchronize()
     return dict(B=B, dev=dev, grids=grids, pos=pos, quat=quat, inv_s=inv_s, obs=obs, depth=depth, sums=sums,
                 g_sdf=g_sdf, g_pos=g_pos, g_quat=g_quat, g_is=g_is, raw=raw, skewed=skewed, SK=SK,
@@ -292,7 +292,7 @@ def test_c4_shared_grid_pose_sweep_matches_oracle(cuda_device, category):
         THR, obs.data_ptr(), 0, depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), None, 0,
         g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags | _lib.ZERO_GRADS, None, st), "sdfr_compare_fused")
     _lib.check(lib.sdfr_scale_grads(sums[1].data_ptr(), None, R, B, None, 0, g_pos.data_ptr(), g_quat.data_ptr(),
-                                    g_is.data_ptr(), flags, st), "sdfr_scale_grads")
+                                    g_is.data_ptr(), flags, None, 0, st), "sdfr_scale_grads")
     torch.cuda.synchronize()
     ngrid, nobs = grid[0].cpu().numpy(), obs.cpu().numpy()
     infos = []
@@ -470,6 +470,51 @@ def test_c2_with_empty_space_bounds_is_unchanged(c2):
     assert tight["hit_pixels"] == full["hit_pixels"]
     assert tight["box_pixels"] < 0.5 * full["box_pixels"] and tight["samples"] < 0.8 * full["samples"]
     _record("c2_empty_space", dict(full=full, with_bounds=tight))
+
+
+def test_scale_grads_inside_the_bounds_box_equals_the_full_pass(c2):
+    """bench.py's step: skew + bounds -> fused render with those bounds -> sdfr_scale_grads over the bounds box
+    only.  Same gradients as scaling the whole grid (every voxel outside the box is an exact zero), and the
+    box really is a small part of the grid."""
+    lib, dev, B = _lib.lib(), c2["dev"], c2["B"]
+    st = torch.cuda.current_stream().cuda_stream
+    bounds = torch.empty((B, 8), dtype=torch.int32, device=dev)
+    skewed = torch.empty_like(c2["skewed"])
+    _lib.check(lib.sdfr_skew_grids_bounds(c2["grids"].data_ptr(), R, R ** 3, B, skewed.data_ptr(), c2["SK"],
+                                          c2["pos"].data_ptr(), c2["inv_s"].data_ptr(), THR, bounds.data_ptr(), st), "skew")
+    out = []
+    for use_box in (False, True):
+        depth = torch.empty_like(c2["depth"])
+        sums = torch.empty(2, B, device=dev)
+        g = [torch.full_like(t, float("nan")) for t in c2["raw"]]
+        _lib.check(lib.sdfr_compare_fused(
+            skewed.data_ptr(), R, c2["SK"], _lib.LAYOUT_SKEWED, c2["pos"].data_ptr(), c2["quat"].data_ptr(),
+            c2["inv_s"].data_ptr(), B, W, H, CX, CY, FX, FY, THR, c2["obs"].data_ptr(), 0, depth.data_ptr(),
+            sums[0].data_ptr(), sums[1].data_ptr(), g[0].data_ptr(), R ** 3, g[1].data_ptr(), g[2].data_ptr(),
+            g[3].data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, bounds.data_ptr(), st), "fused")
+        _lib.check(lib.sdfr_scale_grads(sums[1].data_ptr(), None, R, B, g[0].data_ptr(), R ** 3, g[1].data_ptr(),
+                                        g[2].data_ptr(), g[3].data_ptr(), _lib.GRAD_ALL,
+                                        bounds.data_ptr() if use_box else None, 1 if use_box else 0, st), "scale")
+        torch.cuda.synchronize()
+        out.append(g)
+    for a, b, nm in zip(out[0], out[1], ("sdf", "position", "orientation", "inv_scale")):
+        assert bool(torch.isfinite(b).all())
+        grad_close(b.cpu().numpy(), a.cpu().numpy(), 1e-4, "box-scaled " + nm)
+    bb = bounds.cpu().numpy()
+    ext = np.prod(bb[:, 3:6] - bb[:, 0:3] + 2, axis=1) / R ** 3
+    assert 0.02 < float(ext.mean()) < 0.5
+    # nothing outside the box was non-zero to begin with
+    g_sdf = out[1][0].view(B, R, R, R)
+    for b in range(0, B, 9):
+        lo, hi = bb[b, 0:3], bb[b, 3:6]
+        inside = torch.zeros(R, R, R, dtype=torch.bool, device=dev)
+        inside[lo[0]:hi[0] + 2, lo[1]:hi[1] + 2, lo[2]:hi[2] + 2] = True
+        assert float(g_sdf[b][~inside].abs().max()) == 0.0
+    # one shared grid: bounds_stride 0 is accepted, other strides are not
+    assert lib.sdfr_scale_grads(sums[1].data_ptr(), None, R, B, None, 0, out[1][1].data_ptr(), None, None,
+                                _lib.GRAD_POSITION, bounds.data_ptr(), 0, st) == 0
+    assert lib.sdfr_scale_grads(sums[1].data_ptr(), None, R, B, None, 0, out[1][1].data_ptr(), None, None,
+                                _lib.GRAD_POSITION, bounds.data_ptr(), 2, st) == -2
 
 
 def test_c3_composite_with_bounds_is_unchanged(cuda_device):
