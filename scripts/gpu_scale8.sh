@@ -9,7 +9,7 @@ echo "== bench N=$N"; timeout 600 $TR --master-port 29511 bench.py --gpus $N --s
 python - <<PY
 import json
 d=json.load(open("gpurun_out/${TAG}_bench_n${N}.json"))
-print("value",d["value"],"ms",d["ms_per_step"],"e2e",d["e2e"]["value"],d["e2e"]["ms_per_step"],"e2e_decoded",d["e2e_decoded"].get("value"))
+print("value",d["value"],"ms",d["ms_per_step"],"e2e",d["e2e"]["value"],d["e2e"]["ms_per_step"],"e2e_grids",d["e2e_grids"].get("value"))
 print("loop",d["loop"]["ms_per_iteration"],d["loop"]["hyp_iter_per_s"],"pose_only",d["loop"]["pose_only"]["ms_per_iteration"])
 PY
 echo "== sweep (C4) N=$N"; timeout 600 $TR --master-port 29533 scripts/gpu_sweep.py ${TAG} > gpurun_out/${TAG}_sweep_n${N}.log 2>&1; echo "exit $?"; tail -3 gpurun_out/${TAG}_sweep_n${N}.log | cut -c1-600

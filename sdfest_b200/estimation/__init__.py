@@ -2,7 +2,7 @@
 from .hypotheses import HypothesisOptimizer, gather_losses, global_best, shard_range  # noqa: F401
 from .losses import (depth_to_pointcloud, depth_to_pointclouds, point_loss,  # noqa: F401
                      subsample_points)
-from .streaming import StreamedRenderCompare  # noqa: F401
+from .streaming import StreamedDecodeRenderCompare, StreamedRenderCompare  # noqa: F401
 from .decoder import (FusedTailDecoder, SDFDecoder, SurfaceDecoder, decoder_tail,  # noqa: F401
                       trunk_stage)
 from .fused import decode_render_compare  # noqa: F401

@@ -71,10 +71,22 @@ class _DecodeRenderCompare(torch.autograd.Function):
             SK = _skewed_elems(R)
             grids = torch.empty((B, SK), dtype=torch.float32, device=dev)
             st = _stream()
-            _lib.check(lib.sdfr_decoder_tail_forward(
-                x.data_ptr(), C, S, weight.data_ptr(), _ptr(bias), _ptr(base), B, R,
-                grids.data_ptr(), SK, _lib.LAYOUT_SKEWED, st), "sdfr_decoder_tail_forward")
             inv_scale = (1.0 / scale.detach()).contiguous()
+            from ..differentiable_renderer.sdf_renderer import get_empty_space_policy
+            bounds = None
+            if get_empty_space_policy() != "off":
+                # the tail compares every value with the hypothesis' hit-threshold bound as it stores it:
+                # rays that cannot hit anything are not marched (identical images)
+                bounds_t = torch.empty((B, 8), dtype=torch.int32, device=dev)
+                _lib.check(lib.sdfr_decoder_tail_forward_bounds(
+                    x.data_ptr(), C, S, weight.data_ptr(), _ptr(bias), _ptr(base), B, R, grids.data_ptr(), SK,
+                    _lib.LAYOUT_SKEWED, position.data_ptr(), inv_scale.data_ptr(), float(threshold),
+                    bounds_t.data_ptr(), st), "sdfr_decoder_tail_forward_bounds")
+                bounds = bounds_t.data_ptr()
+            else:
+                _lib.check(lib.sdfr_decoder_tail_forward(
+                    x.data_ptr(), C, S, weight.data_ptr(), _ptr(bias), _ptr(base), B, R,
+                    grids.data_ptr(), SK, _lib.LAYOUT_SKEWED, st), "sdfr_decoder_tail_forward")
             depth = torch.empty((B, H, W), dtype=torch.float32, device=dev)
             sums = torch.empty((2, B), dtype=torch.float32, device=dev)
             g_sdf = torch.empty((B, R ** 3), dtype=torch.float32, device=dev) if need_x else None
@@ -88,13 +100,13 @@ class _DecodeRenderCompare(torch.autograd.Function):
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
                     float(threshold), depth_obs.data_ptr(), obs_stride, depth.data_ptr(),
                     sums[0].data_ptr(), sums[1].data_ptr(), _ptr(g_sdf), R ** 3, _ptr(g_p), _ptr(g_q),
-                    _ptr(g_is), rflags | _lib.ZERO_GRADS, None, st), "sdfr_compare_fused")
+                    _ptr(g_is), rflags | _lib.ZERO_GRADS, bounds, st), "sdfr_compare_fused")
             else:
                 _lib.check(lib.sdfr_compare_forward(
                     grids.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, position.data_ptr(),
                     orientation.data_ptr(), inv_scale.data_ptr(), B, W, H, cx, cy, fx, fy,
                     float(threshold), depth_obs.data_ptr(), obs_stride, depth.data_ptr(),
-                    sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, None, st), "sdfr_compare_forward")
+                    sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, bounds, st), "sdfr_compare_forward")
             loss_depth = sums[0] / sums[1]  # NaN where nothing overlaps (torch.mean of an empty set)
             loss = float(depth_weight) * torch.nan_to_num(loss_depth, nan=0.0)
             loss_pc = None

@@ -155,3 +155,89 @@ class StreamedRenderCompare:
         return {"loss": hs[:, 0], "n_overlap": hs[:, 1], "g_position": hs[:, 2:5],
                 "g_orientation": hs[:, 5:9], "g_inv_scale": hs[:, 9], "g_sdf_device": self.g_sdf.view(
                     self.B, self.R, self.R, self.R), "g_sdf_host": self.h_g_sdf, "depth_device": self.depth}
+
+
+class StreamedDecodeRenderCompare:
+    """Render-and-compare for hypotheses whose LATENTS live in host memory: what the reference's callers
+    actually hold (estimation/simple_setup.py:414 decodes the grid on the device from 8 floats).
+
+    Per step the host hands over, from pinned memory, latent (B,L), position (B,3), unit orientation (B,4),
+    scale (B,) and the observed depth map (H,W) -- 1.2 MB for 64 hypotheses at 640x480 instead of the 68 MB of
+    grids ``StreamedRenderCompare`` ships -- and reads back per hypothesis the masked-L1 loss, the overlap
+    count and the gradients of the loss w.r.t. latent, position, orientation and scale.  On the device:
+    decoder trunk + ``sdfr_decoder_tail_forward`` (grids written once, in the skewed layout) ->
+    ``sdfr_compare_fused`` -> tail adjoint -> trunk backward (``decode_render_compare``).  The whole step --
+    copies included -- is captured once per set of host buffers in a CUDA graph and replayed.
+    """
+
+    def __init__(self, decoder, camera: Camera, threshold: float, batch: int, latent_size: int, device,
+                 depth_weight: float = 1.0):
+        from .decoder import FusedTailDecoder
+
+        if not isinstance(decoder, FusedTailDecoder):
+            raise TypeError("decoder must be a FusedTailDecoder")
+        self.device = torch.device(device)
+        self.decoder, self.camera, self.threshold = decoder, camera, float(threshold)
+        self.B, self.L, self.depth_weight = int(batch), int(latent_size), float(depth_weight)
+        self.W, self.H = int(camera.width), int(camera.height)
+        B, L, dev = self.B, self.L, self.device
+        with torch.cuda.device(dev):
+            self.d_latent = torch.empty(B, L, device=dev)
+            self.d_pos = torch.empty(B, 3, device=dev)
+            self.d_quat = torch.empty(B, 4, device=dev)
+            self.d_scale = torch.empty(B, device=dev)
+            self.d_obs = torch.empty(self.H, self.W, device=dev)
+            self.d_out = torch.empty(B, 10 + L, device=dev)
+            self.h_out = torch.empty(B, 10 + L, pin_memory=True)
+        self.depth = None  # the rendered depth maps of the last step (device)
+        self._graph = None
+        self._graph_key = None
+        self.h2d_bytes = 4 * (B * (L + 8) + self.H * self.W)
+        self.d2h_bytes = 4 * B * (10 + L)
+
+    def _enqueue(self, h_latent, h_pos, h_quat, h_scale, h_obs):
+        from .fused import decode_render_compare
+
+        for d, h in ((self.d_latent, h_latent), (self.d_pos, h_pos), (self.d_quat, h_quat),
+                     (self.d_scale, h_scale), (self.d_obs, h_obs)):
+            d.copy_(h.view(d.shape), non_blocking=True)
+        leaves = [t.detach().requires_grad_(True) for t in (self.d_latent, self.d_pos, self.d_quat, self.d_scale)]
+        lat, p, q, s = leaves
+        w, b = self.decoder.tail_parameters()
+        loss, depth, n, _ = decode_render_compare(
+            self.decoder.trunk(lat), w, b, p, q, s, self.d_obs, None, self.decoder.volume_size, self.threshold,
+            self.camera, base=self.decoder.base, depth_weight=self.depth_weight, pc_weight=0.0)
+        g_lat, g_p, g_q, g_s = torch.autograd.grad(loss.sum(), leaves)
+        self.depth = depth
+        torch.cat([loss.detach()[:, None], n[:, None], g_p, g_q, g_s[:, None], g_lat], 1, out=self.d_out)
+        self.h_out.copy_(self.d_out, non_blocking=True)
+
+    def __call__(self, h_latent: torch.Tensor, h_position: torch.Tensor, h_orientation: torch.Tensor,
+                 h_scale: torch.Tensor, h_depth_obs: torch.Tensor, graph: bool = True,
+                 sync: bool = True) -> Dict[str, Optional[torch.Tensor]]:
+        """One step from (pinned) host buffers; returns host views, valid after the call when ``sync``."""
+        args = (h_latent, h_position, h_orientation, h_scale, h_depth_obs)
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            if graph:
+                key = tuple(t.data_ptr() for t in args)
+                if self._graph is None or self._graph_key != key:
+                    side = torch.cuda.Stream(self.device)
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):  # warm-up outside capture (cuBLAS workspaces, autograd)
+                        for _ in range(2):
+                            self._enqueue(*args)
+                    main.wait_stream(side)
+                    torch.cuda.synchronize(self.device)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._enqueue(*args)
+                    self._graph, self._graph_key = g, key
+                self._graph.replay()
+            else:
+                self._enqueue(*args)
+            if sync:
+                main.synchronize()
+        hs, L = self.h_out, self.L
+        return {"loss": hs[:, 0], "n_overlap": hs[:, 1], "g_position": hs[:, 2:5], "g_orientation": hs[:, 5:9],
+                "g_scale": hs[:, 9], "g_latent": hs[:, 10:10 + L], "depth_device": self.depth}

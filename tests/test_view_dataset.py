@@ -132,3 +132,44 @@ def test_runtime_breakdown_reports_every_phase(cuda_device):
         runtime_analysis.phase_breakdown(make("fused"), iterations=1, warmup=0)
     for optimizer in ("torch", "fused"):
         assert runtime_analysis.iteration_ms(make(optimizer), iterations=3, warmup=1, graph=True) > 0
+
+
+@pytest.mark.gpu
+def test_streamed_decode_render_compare_matches_the_operator(cuda_device):
+    """Host latents / poses in, losses and gradients out through one CUDA graph
+    (estimation.StreamedDecodeRenderCompare) == decode_render_compare + autograd on device tensors; a second set
+    of host buffers re-captures; eager mode agrees with the replay."""
+    from sdfest_b200 import synthetic as syn
+    from sdfest_b200.differentiable_renderer import Camera, render_depth_batched
+    from sdfest_b200.estimation import StreamedDecodeRenderCompare, decode_render_compare
+
+    dev = cuda_device
+    B, R, W, H, thr = 5, 64, 160, 120, 0.005
+    cam = Camera(W, H, W / 2, W / 2, W / 2, H / 2, pixel_center=0.5)
+    dec = syn.residual_decoder(R, dev, syn.sdf_mug(R, dev))
+    hyp = syn.make_hypotheses(B, seed=0, device=dev)
+    base = syn.make_hypotheses(1, seed=0, device=dev)
+    obs = render_depth_batched(syn.hypothesis_grids(base["shape_param"], R, dev), base["position"],
+                               base["orientation"], base["inv_scale"], thr, cam)[0].contiguous()
+    s = StreamedDecodeRenderCompare(dec, cam, thr, B, 8, dev)
+    assert s.h2d_bytes == 4 * (B * 16 + W * H) and s.d2h_bytes == 4 * B * 18
+    for seed in (0, 1):
+        lat = 0.2 * torch.randn(B, 8, generator=torch.Generator().manual_seed(seed))
+        host = [t.cpu().pin_memory() for t in (lat, hyp["position"] + 0.002 * seed, hyp["orientation"],
+                                               1.0 / hyp["inv_scale"], obs)]
+        out = {k: (v.clone() if v is not None else None) for k, v in s(*host).items()}
+        again = s(*host)  # replay
+        leaves = [t.to(dev).requires_grad_(True) for t in host[:4]]
+        w, b = dec.tail_parameters()
+        loss, depth, n, _ = decode_render_compare(dec.trunk(leaves[0]), w, b, leaves[1], leaves[2], leaves[3], obs, None,
+                                                  R, thr, cam, base=dec.base, depth_weight=1.0, pc_weight=0.0)
+        g = torch.autograd.grad(loss.sum(), leaves)
+        for res in (out, again, s(*host, graph=False)):
+            torch.testing.assert_close(res["loss"], loss.detach().cpu(), rtol=1e-4, atol=1e-6)
+            assert torch.equal(res["n_overlap"], n.cpu())
+            for key, want in (("g_latent", g[0]), ("g_position", g[1]), ("g_orientation", g[2]), ("g_scale", g[3])):
+                want = want.cpu()
+                assert float((res[key] - want).abs().max()) <= 2e-3 * float(want.abs().max()), key
+        assert torch.equal(s.depth, depth)
+    with pytest.raises(TypeError):
+        StreamedDecodeRenderCompare(dec.decoder, cam, thr, B, 8, dev)
