@@ -1162,6 +1162,22 @@ sdfr_bounds_from_minima_kernel(const float* __restrict__ minima, int R, const fl
   }
 }
 
+/* Dense [R][R][R] -> z-pair copy (sdfr_core.cuh: kLayoutZPair): one float2 per voxel. */
+__global__ void __launch_bounds__(256)
+sdfr_zpair_kernel(const float* __restrict__ src, long long src_stride, float* __restrict__ dst,
+                  long long dst_stride, int R, int py2, int px2) {
+  const int b = blockIdx.y;
+  const float* __restrict__ s = src + (size_t)b * src_stride;
+  float2* __restrict__ d = reinterpret_cast<float2*>(dst + (size_t)b * dst_stride);
+  const int n = R * R * R;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int row = i / R, z = i - row * R;
+    const int ix = row / R, iy = row - ix * R;
+    const float v0 = __ldg(s + i), v1 = z + 1 < R ? __ldg(s + i + 1) : v0;
+    d[(size_t)ix * px2 + iy * py2 + z] = make_float2(v0, v1);
+  }
+}
+
 /* Dense [R][R][R] -> skewed pitched copy (sdfr_core.cuh: kLayoutSkewed).  One warp per (x,y)
  * row: coalesced reads, coalesced (unaligned) writes; the padding is never read. */
 __global__ void __launch_bounds__(256)
@@ -1196,9 +1212,10 @@ sdfr_skew_kernel(const float* __restrict__ src, long long src_stride, float* __r
  * Host side
  * ---------------------------------------------------------------------------------------- */
 int check_common(const float* sdf, int R, long long sdf_stride, int layout, const float* pos,
-                 const float* quat, const float* inv_scale, int batch, int W, int H) {
-  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED)
-    return fail(SDFR_E_FLAGS, "unknown sdf_layout");
+                 const float* quat, const float* inv_scale, int batch, int W, int H, bool allow_zpair = false) {
+  if (layout != SDFR_LAYOUT_DENSE && layout != SDFR_LAYOUT_SKEWED &&
+      !(allow_zpair && layout == SDFR_LAYOUT_ZPAIR && R == 64))
+    return fail(SDFR_E_FLAGS, "unknown sdf_layout (the experimental z-pair layout: resolution 64 only)");
   if (batch < 0 || W < 0 || H < 0) return fail(SDFR_E_SHAPE, "negative batch/width/height");
   if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
   if (sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative sdf_stride");
@@ -1299,10 +1316,18 @@ int launch_forward(FwdParams P, int batch, cudaStream_t s) {
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
   const int G = ctas_per_hypothesis(batch, P.cam.W, P.cam.H);
-  const bool skewed = P.grid.py != P.grid.R;
+  const bool skewed = P.grid.layout == kLayoutSkewed;
   for (int z0 = 0; z0 < batch; z0 += 65535) {
     P.z_offset = z0;
     const dim3 grid(G, batch - z0 < 65535 ? batch - z0 : 65535);
+    if (P.grid.layout == kLayoutZPair) { /* experimental: the compare entry points at 64^3 only */
+      if constexpr (MODE >= 1 && !STATS) {
+        launch_forward_rt<64, kLayoutZPair, MODE, STATS>(P, grid, smem, s);
+        continue;
+      } else {
+        return fail(SDFR_E_FLAGS, "the z-pair layout is only wired into sdfr_compare_forward / sdfr_compare_fused");
+      }
+    }
 #define SDFR_CALL(RT, LT) launch_forward_rt<RT, LT, MODE, STATS>(P, grid, smem, s)
     SDFR_DISPATCH_RT_LT(P.grid.R, skewed, SDFR_CALL);
 #undef SDFR_CALL
@@ -1337,7 +1362,8 @@ int launch_backward(BwdParams P, int batch, bool zero_sdf, cudaStream_t s) {
   if (!want_sdf && !want_pose) return 0;
   const size_t smem = table_bytes(P.cam.W, P.cam.H);
   P.use_tables = smem != 0;
-  const bool skewed = P.grid.py != P.grid.R;
+  const bool skewed = P.grid.layout == kLayoutSkewed;
+  if (P.grid.layout == kLayoutZPair) return fail(SDFR_E_FLAGS, "the z-pair layout is not wired into the backward entry points");
   const size_t grid_bytes = sizeof(float) * (size_t)P.grid.R * P.grid.R * P.grid.R;
   int chunk = batch;
   if (want_sdf && P.grad_sdf_stride != 0) {
@@ -1540,7 +1566,7 @@ int sdfr_compare_forward(const float* sdf, int R, long long sdf_stride, int layo
                          const float* depth_obs, long long obs_stride, float* depth,
                          float* loss_sum, float* n_overlap, unsigned flags,
                          const sdfr_cell_bounds* bounds, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, true)) return rc;
   if (flags & ~SDFR_ZERO_GRADS) return fail(SDFR_E_FLAGS, "unknown flag bits");
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if (batch == 0) return 0;
@@ -1600,7 +1626,7 @@ static int compare_fused_impl(const float* sdf, int R, long long sdf_stride, int
                               float* loss_sum, float* n_overlap, float rel_threshold, float* n_inlier,
                               float* gs, long long gs_stride, float* gp, float* gq, float* gi,
                               unsigned flags, const sdfr_cell_bounds* bounds, void* stream) {
-  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H)) return rc;
+  if (int rc = check_common(sdf, R, sdf_stride, layout, pos, quat, inv_scale, batch, W, H, true)) return rc;
   if (int rc = check_backward_outputs(flags, gs, gs_stride, gp, gq, gi)) return rc;
   if (obs_stride < 0) return fail(SDFR_E_SHAPE, "negative obs_stride");
   if ((flags & SDFR_GRAD_SDF) && gs_stride == 0 && batch > 1)
@@ -1828,6 +1854,30 @@ int sdfr_skew_grids_bounds(const float* sdf, int R, long long sdf_stride, int ba
   if (sdf_stride == 0 && batch > 1) skewed_stride = 0; /* one shared grid: one skewed copy */
   return launch_bounds_scan(sdf, R, sdf_stride, SDFR_LAYOUT_DENSE, pos, inv_scale, batch, threshold, bounds, skewed,
                             skewed_stride, (cudaStream_t)stream);
+}
+
+int sdfr_zpair_elems(int R, long long* elems) {
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (elems) *elems = 2ll * R * zpair_pitch_x(R);
+  return 0;
+}
+
+int sdfr_zpair_grids(const float* sdf, int R, long long sdf_stride, int batch, float* zpair,
+                     long long zpair_stride, void* stream) {
+  if (R < 2 || R > 1024) return fail(SDFR_E_SHAPE, "resolution must be in [2, 1024]");
+  if (batch < 0 || sdf_stride < 0) return fail(SDFR_E_SHAPE, "negative batch or sdf_stride");
+  if (batch == 0) return 0;
+  if (!sdf || !zpair) return fail(SDFR_E_NULL, "NULL grid pointer");
+  if (zpair_stride < 2ll * R * zpair_pitch_x(R)) return fail(SDFR_E_SHAPE, "zpair_stride smaller than sdfr_zpair_elems");
+  const long long work = (long long)R * R * R;
+  const int gx = (int)((work + 255) / 256 < 2048 ? (work + 255) / 256 : 2048);
+  for (int z0 = 0; z0 < batch; z0 += 65535) {
+    const int nz = batch - z0 < 65535 ? batch - z0 : 65535;
+    sdfr_zpair_kernel<<<dim3(gx, nz), 256, 0, (cudaStream_t)stream>>>(
+        sdf + (size_t)z0 * sdf_stride, sdf_stride, zpair + (size_t)z0 * zpair_stride, zpair_stride, R,
+        zpair_pitch_y(R), zpair_pitch_x(R));
+  }
+  return check_launch("sdfr_zpair_kernel");
 }
 
 int sdfr_skewed_pitches(int R, int* pitch_y, int* pitch_x, long long* elems) {
