@@ -102,6 +102,52 @@ def test_skewed_layout_geometry():
     assert lib.sdfr_forward(None, 4, 0, 7, None, None, None, 1, *cam, 0.01, None, None, None) == -3
 
 
+def test_argument_errors_of_the_round_two_entry_points_need_no_gpu():
+    """Views, point constraint, slab minima, scale-with-bounds, tail-with-bounds, z-pair: empty work is a no-op,
+    NULL / bad sizes are reported before anything is launched."""
+    import ctypes
+
+    lib = _lib.lib()
+    f3 = (ctypes.c_float * 3)(0.0, 1.0, 0.0)
+    assert lib.sdfr_view_poses(None, None, None, None, None, 0, 4, None, None, None, None) == 0
+    assert lib.sdfr_view_poses(None, None, None, None, None, 2, 0, None, None, None, None) == 0
+    assert lib.sdfr_view_poses(None, None, None, None, None, 2, 4, None, None, None, None) == -1
+    assert lib.sdfr_view_poses(None, None, None, None, None, -1, 4, None, None, None, None) == -2
+    assert lib.sdfr_views_pull_back(None, None, 2, 0, *[None] * 8, 1.0, None, None, None, None, None, 0, None) == 0
+    assert lib.sdfr_views_pull_back(None, None, 2, 3, *[None] * 8, 1.0, None, None, None, None, None, 0, None) == -1
+    assert lib.sdfr_views_pull_back(None, None, 2, 3, *[None] * 8, 1.0, None, None, None, None, None, 0x1, None) == -3
+    assert lib.sdfr_point_constraint(None, 0, f3, f3, 1.0, None, None, None) == 0
+    assert lib.sdfr_point_constraint(None, 2, f3, f3, 1.0, None, None, None) == -1
+    assert lib.sdfr_point_constraint(None, -2, f3, f3, 1.0, None, None, None) == -2
+    assert lib.sdfr_grid_slab_minima(None, 64, 0, 0, 0, None, None) == 0
+    assert lib.sdfr_grid_slab_minima(None, 64, 0, 0, 2, None, None) == -1
+    assert lib.sdfr_grid_slab_minima(None, 1, 0, 0, 2, None, None) == -2
+    assert lib.sdfr_grid_slab_minima(None, 64, 0, 5, 2, None, None) == -3
+    assert lib.sdfr_bounds_from_minima(None, 64, 0, None, None, 0, 0.005, None, None) == 0
+    assert lib.sdfr_bounds_from_minima(None, 64, 2, None, None, 2, 0.005, None, None) == -1
+    assert lib.sdfr_bounds_from_minima(None, 64, 3, None, None, 2, 0.005, None, None) == -2  # 1 or batch grids
+    assert lib.sdfr_bounds_from_minima(None, 64, 2, None, None, 2, -1.0, None, None) == -2
+    assert lib.sdfr_scale_grads(None, None, 64, 0, None, 0, None, None, None, 0x0F, None, 0, None) == -1  # NULL buffers
+    assert lib.sdfr_scale_grads(None, None, 64, 0, None, 0, None, None, None, 0, None, 0, None) == 0
+    assert lib.sdfr_decoder_tail_forward_bounds(None, 4, 30, None, None, None, 0, 64, None, 0, 0, None, None, 0.005,
+                                                None, None) == 0
+    assert lib.sdfr_decoder_tail_forward_bounds(None, 4, 30, None, None, None, 2, 64, None, 0, 0, None, None, 0.005,
+                                                None, None) == -1
+    assert lib.sdfr_decoder_tail_forward_bounds(None, 40, 30, None, None, None, 2, 64, None, 0, 0, None, None, 0.005,
+                                                None, None) == -2
+    n = ctypes.c_longlong(0)
+    assert lib.sdfr_zpair_elems(64, ctypes.byref(n)) == 0 and n.value == 2 * 64 * (64 * 67 + 9)
+    assert lib.sdfr_zpair_grids(None, 64, 0, 0, None, 0, None) == 0
+    assert lib.sdfr_zpair_grids(None, 64, 0, 1, None, 0, None) == -1
+    cam = (8, 8, 4.0, 4.0, 4.0, 4.0)
+    # the experimental z-pair layout is refused everywhere but the compare entry points at 64^3
+    assert lib.sdfr_forward(None, 64, 0, 2, None, None, None, 1, *cam, 0.01, None, None, None) == -3
+    assert lib.sdfr_compare_forward(None, 32, 0, 2, None, None, None, 1, *cam, 0.01, None, 0, None, None, None, 0,
+                                    None, None) == -3
+    assert lib.sdfr_compare_forward(None, 64, 0, 2, None, None, None, 1, *cam, 0.01, None, 0, None, None, None, 0,
+                                    None, None) == -1  # accepted layout, NULL inputs
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libsdfrender.so"))
