@@ -24,6 +24,7 @@ from typing import List
 import torch
 
 from .. import _lib
+from ..differentiable_renderer.sdf_renderer import _on_device_of, _stream
 
 
 def _check_input(t: torch.Tensor, name: str) -> None:
@@ -42,12 +43,12 @@ def forward(sdf: torch.Tensor, position: torch.Tensor, orientation: torch.Tensor
     """sdf_renderer_forward (sdf_renderer.cpp:42-61): returns ``[depth_image (H,W)]``."""
     for t, n in ((sdf, "sdf"), (position, "position"), (orientation, "orientation"), (inv_scale, "inv_scale")):
         _check_input(t, n)
-    with torch.cuda.device_of(sdf):  # OptionalCUDAGuard, cpp:58
+    with _on_device_of(sdf):  # OptionalCUDAGuard, cpp:58 (free when sdf lives on the current device)
         depth = torch.empty((int(height), int(width)), dtype=torch.float32, device=sdf.device)
         _lib.check(_lib.lib().sdfr_forward(
             sdf.data_ptr(), int(sdf.shape[-1]), 0, _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(),
             inv_scale.data_ptr(), 1, int(width), int(height), float(cx), float(cy), float(fx), float(fy),
-            float(threshold), depth.data_ptr(), None, torch.cuda.current_stream().cuda_stream), "sdfr_forward")
+            float(threshold), depth.data_ptr(), None, _stream()), "sdfr_forward")
     return [depth]
 
 
@@ -60,7 +61,7 @@ def backward(grad_depth_image: torch.Tensor, depth_image: torch.Tensor, sdf: tor
     for t, n in ((grad_depth_image, "grad_depth_image"), (depth_image, "depth_image"), (sdf, "sdf"),
                  (position, "position"), (orientation, "orientation"), (inv_scale, "inv_scale")):
         _check_input(t, n)
-    with torch.cuda.device_of(sdf):  # cpp:82
+    with _on_device_of(sdf):  # cpp:82
         g_sdf = torch.empty_like(sdf)  # cleared by the library (SDFR_ZERO_GRADS)
         exact = position.numel() == 3 and orientation.numel() == 4 and inv_scale.numel() == 1
         alloc = torch.empty_like if exact else torch.zeros_like  # over-long pose tensors: the tail reads 0
@@ -69,6 +70,5 @@ def backward(grad_depth_image: torch.Tensor, depth_image: torch.Tensor, sdf: tor
             grad_depth_image.data_ptr(), depth_image.data_ptr(), sdf.data_ptr(), int(sdf.shape[-1]), 0,
             _lib.LAYOUT_DENSE, position.data_ptr(), orientation.data_ptr(), inv_scale.data_ptr(), 1, int(width),
             int(height), float(cx), float(cy), float(fx), float(fy), g_sdf.data_ptr(), 0, g_p.data_ptr(),
-            g_q.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, None,
-            torch.cuda.current_stream().cuda_stream), "sdfr_backward")
+            g_q.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, None, _stream()), "sdfr_backward")
     return [g_sdf, g_p, g_q, g_is]
