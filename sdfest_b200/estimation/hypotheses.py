@@ -459,6 +459,15 @@ class HypothesisOptimizer:
             self._unit_q.data_ptr(), self._inv_scale.data_ptr(), self._loss.data_ptr(), flags,
             _stream()), "sdfr_hypothesis_step")
 
+    def _latent_leaf(self) -> torch.Tensor:
+        """A FRESH autograd leaf over the latent's storage for this iteration's trunk graph.  Autograd caches a
+        leaf's AccumulateGrad node together with the stream it was created on; a node left over from an eager
+        iteration on the default stream (kept alive by a not-yet-collected graph) makes the engine synchronise
+        the default stream with the capturing one, which is illegal inside a capture
+        (cudaErrorStreamCaptureImplicit; seen under compute-sanitizer, where the garbage collector's timing
+        differs).  A new leaf per iteration has no history."""
+        return self.latent.detach().requires_grad_(True)
+
     def _constraint_launch(self) -> None:
         """sdfr_point_constraint on the un-normalised orientation: += into g_raw / loss_extra."""
         if self.point_constraint is None:
@@ -480,7 +489,8 @@ class HypothesisOptimizer:
         flags = _lib.GRAD_POSITION | _lib.GRAD_ORIENTATION | _lib.GRAD_INV_SCALE
         if dec is not None:
             self._g_both.zero_()
-            x = dec.trunk(self.latent).contiguous()
+            leaf = self._latent_leaf()
+            x = dec.trunk(leaf).contiguous()
             w, bias = dec.tail_parameters()
             C, S = int(x.shape[1]), int(x.shape[2])
             _lib.check(lib.sdfr_decoder_tail_forward(
@@ -539,7 +549,7 @@ class HypothesisOptimizer:
             _lib.check(lib.sdfr_decoder_tail_backward(
                 g_sdf, R ** 3, None, None, None, 0, w.data_ptr(), C, S, B, R, g_x.data_ptr(), _stream()),
                 "sdfr_decoder_tail_backward")
-            (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
+            (g_latent,) = torch.autograd.grad(x, leaf, g_x)
             g_latent = g_latent.contiguous()
         self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent, self._g_raw, self._loss_extra)
         if self.inlier_threshold is not None:
@@ -577,7 +587,8 @@ class HypothesisOptimizer:
 
         if dec is not None:
             on_side(clear_grids)
-            x = dec.trunk(self.latent).contiguous()  # autograd graph: latent -> x only
+            leaf = self._latent_leaf()
+            x = dec.trunk(leaf).contiguous()  # autograd graph: latent -> x only
             w, bias = dec.tail_parameters()
             C, S = int(x.shape[1]), int(x.shape[2])
             if self._bounds is not None:
@@ -652,7 +663,7 @@ class HypothesisOptimizer:
                 self._g_sdf.data_ptr(), R ** 3, b["n_overlap"].data_ptr(), self._up_d.data_ptr(),
                 _ptr(self._g_sdf_pc), R ** 3, w.data_ptr(), C, S, B, R, g_x.data_ptr(), _stream()),
                 "sdfr_decoder_tail_backward")
-            (g_latent,) = torch.autograd.grad(x, self.latent, g_x)
+            (g_latent,) = torch.autograd.grad(x, leaf, g_x)
             g_latent = g_latent.contiguous()
         self._hyp_step(_lib.STEP_CLEAR_INPUTS, g_latent, self._g_raw, self._loss_extra)
         if self.inlier_threshold is not None:
