@@ -78,6 +78,40 @@ def iteration_ms(opt: HypothesisOptimizer, iterations: int = 30, warmup: int = 3
     return a.elapsed_time(b) / iterations
 
 
+# phases of this loop under the names of the reference's timing decorators (real_data.py:228-243):
+#   "init"     pipeline._nn_init                 -> the initialisation network call (caller-measured)
+#   "decode"   pipeline.vae.decode               -> decode
+#   "render"   pipeline.render                   -> render_compare (render + masked L1 are one launch here)
+#   "losses"   pipeline._compute_view_losses     -> point_loss (the depth L1 already happened in "render")
+#   "backward" pipeline._compute_gradients       -> backward
+# plus "optimizer", which the reference does not time separately.
+REFERENCE_KEYS = {"decode": "decode", "render_compare": "render", "point_loss": "losses", "backward": "backward",
+                  "optimizer": "optimizer"}
+
+
+def reference_overview(with_decode: Dict[str, float], without_decode: Dict[str, float], iterations_per_run: int,
+                       runs: int = 1, init_ms: float = None, config: Dict = None) -> Dict:
+    """The YAML document of the reference's ``generate_runtime_overview`` (real_data.py:286-319) from two
+    ``phase_breakdown`` results (shape optimisation on / off): ``results_with_decode`` /
+    ``results_without_decode``, per phase ``total``, ``total_calls``, ``mean``, ``calls_per_run``,
+    ``total_per_run`` -- in SECONDS like the reference, for ``runs`` runs of ``iterations_per_run`` iterations."""
+    def stats(breakdown):
+        out = {}
+        for ours, theirs in REFERENCE_KEYS.items():
+            if ours not in breakdown or (theirs == "decode" and breakdown is without_decode):
+                continue
+            mean = breakdown[ours] * 1e-3
+            calls = iterations_per_run * runs
+            out[theirs] = {"total": mean * calls, "total_calls": calls, "mean": mean,
+                           "calls_per_run": float(iterations_per_run), "total_per_run": mean * iterations_per_run}
+        if init_ms is not None:
+            out["init"] = {"total": init_ms * 1e-3 * runs, "total_calls": runs, "mean": init_ms * 1e-3,
+                           "calls_per_run": 1.0, "total_per_run": init_ms * 1e-3}
+        return out
+
+    return {**(config or {}), "results_with_decode": stats(with_decode), "results_without_decode": stats(without_decode)}
+
+
 def write_yaml(path: str, results: Dict) -> None:
     import yaml
 

@@ -245,3 +245,24 @@ def test_sharded_loop_equals_the_single_process_loop():
     for rank, losses_all, _ in out:
         np.testing.assert_allclose(losses_all, want, rtol=1e-6)
     np.testing.assert_allclose(out[0][2] + out[1][2], want_pos, rtol=1e-6)
+
+
+def test_runtime_overview_has_the_reference_yaml_layout():
+    """runtime_analysis.reference_overview: the document of the reference's generate_runtime_overview
+    (estimation/scripts/real_data.py:286-319): same section and phase names, seconds, per-run statistics."""
+    from sdfest_b200.estimation import runtime_analysis as ra
+
+    w = {"decode": 0.5, "render_compare": 0.2, "point_loss": 0.1, "backward": 0.6, "optimizer": 0.05, "total": 1.45}
+    wo = {"decode": 0.0, "render_compare": 0.2, "point_loss": 0.1, "backward": 0.1, "optimizer": 0.05, "total": 0.45}
+    doc = ra.reference_overview(w, wo, iterations_per_run=50, runs=4, init_ms=6.0, config={"dataset": "synthetic"})
+    assert set(doc) == {"dataset", "results_with_decode", "results_without_decode"}
+    a, b = doc["results_with_decode"], doc["results_without_decode"]
+    assert set(a) == {"init", "decode", "render", "losses", "backward", "optimizer"}
+    assert "decode" not in b and set(b) == set(a) - {"decode"}
+    for sec in (a, b):
+        for st in sec.values():
+            assert set(st) == {"total", "total_calls", "mean", "calls_per_run", "total_per_run"}
+            assert abs(st["total"] - st["mean"] * st["total_calls"]) < 1e-12
+    assert a["render"]["mean"] == 0.2e-3 and a["render"]["total_calls"] == 200 and a["render"]["calls_per_run"] == 50.0
+    assert abs(a["backward"]["total_per_run"] - 0.6e-3 * 50) < 1e-12
+    assert a["init"] == {"total": 0.024, "total_calls": 4, "mean": 0.006, "calls_per_run": 1.0, "total_per_run": 0.006}
