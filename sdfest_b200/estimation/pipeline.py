@@ -24,6 +24,7 @@ from typing import Optional, Tuple
 import torch
 
 from ..differentiable_renderer import Camera
+from ..differentiable_renderer.sdf_renderer import get_empty_space_policy, get_sdf_grad_mode
 from . import losses, views
 from .decoder import FusedTailDecoder
 from .hypotheses import HypothesisOptimizer
@@ -210,7 +211,11 @@ class SDFPipeline:
                     and isinstance(kw.get("decoder"), FusedTailDecoder) and latent.shape[1] <= 64)
         opt, done = None, 0
         if reusable:
-            key = (n_hyp, int(latent.shape[1]), id(kw["decoder"]), str(dev))
+            # everything the captured iteration bakes in: sizes, the decoder object, and the loop's constants
+            key = (n_hyp, int(latent.shape[1]), id(kw["decoder"]), str(dev), float(self.config["threshold"]),
+                   float(kw["depth_weight"]), float(kw["pc_weight"]), int(kw["max_points"]),
+                   float(kw["inlier_threshold"]), self.cam.width, self.cam.height, self.cam.fx, self.cam.fy,
+                   self.cam.cx, self.cam.cy, self.cam.pixel_center, get_sdf_grad_mode(), get_empty_space_policy())
             n_obs = int((obs != 0).sum()) if kw["pc_weight"] else 0
             n_pts = min(n_obs, kw["max_points"]) if kw["max_points"] else n_obs
             cached = self._graph_cache.get(key)
