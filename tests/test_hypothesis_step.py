@@ -657,3 +657,29 @@ def test_fused_optimizer_on_a_device_that_is_not_current(cuda_device):
     t = _make_optimizers(torch.device("cuda:1"), 4, False, "torch")
     f = _make_optimizers(torch.device("cuda:1"), 4, False, "fused")
     torch.testing.assert_close(f.step().cpu(), t.step().cpu(), rtol=2e-3, atol=1e-5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("optimizer", ["fused", "torch"])
+def test_a_hypothesis_without_overlap_never_ranks_best(cuda_device, optimizer):
+    """One hypothesis far off-screen: its rendered depth never overlaps the observation.  The reference's mean
+    over an empty selection is NaN (simple_setup.py:131) and so is the loss reported here -- it must not look
+    like the best one (its depth and point terms are both 0) -- while its parameters and Adam state stay finite
+    and the other hypotheses are unaffected."""
+    from sdfest_b200 import _lib
+    from sdfest_b200.estimation.hypotheses import global_best
+
+    good = _make_optimizers(cuda_device, 4, False, optimizer)
+    bad = _make_optimizers(cuda_device, 4, False, optimizer)
+    with torch.no_grad():
+        bad.position[2] += torch.tensor([5.0, 0.0, 0.0], device=cuda_device)  # out of the frustum
+    if optimizer == "fused":
+        bad._hyp_step(_lib.STEP_NO_UPDATE)
+    for _ in range(3):
+        lg, lb = good.step().clone(), bad.step().clone()
+    assert bool(torch.isnan(lb[2])) and bool(torch.isfinite(lb[[0, 1, 3]]).all())
+    torch.testing.assert_close(lb[[0, 1, 3]], lg[[0, 1, 3]], rtol=1e-5, atol=1e-7)
+    for t in (bad.position, bad.orientation, bad.scale):
+        assert bool(torch.isfinite(t.detach()).all())
+    idx, loss = global_best(lb, 0)
+    assert idx != 2 and loss == float(lb[idx]) and idx == int(torch.argmin(torch.nan_to_num(lg, nan=float("inf"))))
