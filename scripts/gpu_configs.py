@@ -112,6 +112,30 @@ def config1():
     res["fused_tail_decoder_our_renderer"] = {"ms": ms_b, "mpix_per_s": W * H / (ms_b * 1e-3) / 1e6}
     ms_dec = timed(lambda: dec_plain(z0.clone().requires_grad_(True)).sum().backward(), 30, flush=flush)
     res["torch_decoder_alone_fwd_bwd_ms"] = ms_dec
+    # (d) the same step (b) captured ONCE as a CUDA graph and replayed: what the step costs on the GPU when the
+    # host no longer issues ~60 launches per call.  The library's operators launch on the caller's stream and never
+    # allocate or synchronise, so the whole autograd step is capturable; the reference's extension launches on the
+    # legacy default stream (sdf_renderer_cuda.cu:497, 538) and cannot be captured.
+    try:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                run(dec_fused, ours)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            g_out = run(dec_fused, ours)
+        graph.replay()
+        torch.cuda.synchronize()
+        eager = run(dec_fused, ours)
+        ms_d = timed(graph.replay, 30, flush=flush)
+        res["fused_tail_decoder_our_renderer_cuda_graph"] = {
+            "ms": ms_d, "mpix_per_s": W * H / (ms_d * 1e-3) / 1e6,
+            "max_abs_diff_vs_eager": [float((a - b).abs().max()) for a, b in zip(g_out, eager)]}
+    except Exception as e:  # noqa: BLE001
+        res["fused_tail_decoder_our_renderer_cuda_graph"] = {"unavailable": str(e)[:300]}
     try:
         from oracle import build_ref
         ext = build_ref.load_module()
@@ -141,6 +165,8 @@ def config1():
         res["reference_cuda_ext"] = {
             "ms": ms_c, "mpix_per_s": W * H / (ms_c * 1e-3) / 1e6, "speedup_renderer_swapped": ms_c / ms_a,
             "speedup_fused_decoder_too": ms_c / ms_b,
+            "speedup_cuda_graph": (ms_c / res["fused_tail_decoder_our_renderer_cuda_graph"]["ms"]
+                                   if "ms" in res["fused_tail_decoder_our_renderer_cuda_graph"] else None),
             "hit_mask_agreement": float(((theirs[0] > 0) == (ref_out[0] > 0)).float().mean()),
             "depth_within_1e-5_rel": float((rel <= 1e-5).float().mean()),
             "latent_grad_max_norm_rel_err": gerr(ref_out[1], theirs[1]),

@@ -68,6 +68,20 @@ def ours_single_cabi():
 
 
 out["c1_ours_autograd"] = timed(ours_single)
+try:  # the same autograd call captured once and replayed (no host work per call)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            ours_single()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    c1_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(c1_graph):
+        ours_single()
+    out["c1_ours_autograd_cuda_graph"] = timed(c1_graph.replay)
+except Exception as e:  # noqa: BLE001
+    out["c1_ours_autograd_cuda_graph"] = {"unavailable": str(e)[:300]}
 out["c1_ours_cabi"] = timed(ours_single_cabi)
 out["c1_ours_cabi_warm_l2"] = timed(ours_single_cabi, do_flush=False)
 try:

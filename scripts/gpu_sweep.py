@@ -58,12 +58,29 @@ index = torch.cat(index)
 local_losses = torch.empty(hi - lo, device=dev)
 
 
+# The categories are independent optimisers: each iterates on its own stream (forked from / joined to the
+# calling stream), so inside the captured graph they are parallel branches and one category's tail -- the last
+# CTAs of its render launch, its small step kernel -- overlaps the next category's work.  SWEEP_SERIAL=1 keeps
+# them on one stream (the A/B: profiles/*_sweep_branches.json).
+SERIAL = os.environ.get("SWEEP_SERIAL", "0") == "1"
+branches = [torch.cuda.Stream(dev) for _ in opts]
+
+
 def local_iteration():
     off = 0
-    for opt in opts:
-        l = opt.step()
-        local_losses[off:off + l.numel()] = l
-        off += l.numel()
+    main = torch.cuda.current_stream()
+    for opt, br in zip(opts, branches):
+        n = opt.position.shape[0]
+        if SERIAL:
+            local_losses[off:off + n] = opt.step()
+        else:
+            br.wait_stream(main)
+            with torch.cuda.stream(br):
+                local_losses[off:off + n] = opt.step()
+        off += n
+    if not SERIAL:
+        for br in branches:
+            main.wait_stream(br)
 
 
 # the rank's whole iteration (three categories x three launches + the loss concatenation) as ONE graph
@@ -112,7 +129,7 @@ line = {"workload": f"C4 sweep: {N_TOTAL} pose/scale hypotheses on mug/bowl/bott
                     f"{ITER} fused Adam iterations, all_gather of losses every iteration",
         "n_gpus": world, "hypotheses_total": N_TOTAL, "hypotheses_per_gpu": hi - lo, "iterations": ITER,
         "ms_per_iteration": float(ms) / ITER, "hyp_iter_per_s": N_TOTAL * ITER / (float(ms) * 1e-3),
-        "scaling": "strong", "best_hypothesis": int(all_index[best]) if best < all_index.numel() else best,
+        "scaling": "strong", "category_branches": "serial" if SERIAL else "parallel", "best_hypothesis": int(all_index[best]) if best < all_index.numel() else best,
         "best_loss": float(allv[best]), "mean_loss": float(torch.nan_to_num(allv).mean())}
 if rank == 0:
     tag = sys.argv[1] if len(sys.argv) > 1 else "sweep"
