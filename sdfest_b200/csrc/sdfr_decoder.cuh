@@ -486,6 +486,9 @@ struct ConvParams {
 #ifndef SDFR_CONV_CC_ZR4
 #define SDFR_CONV_CC_ZR4 8 /* input channels staged per pass by the 32-deep tiles (tuning knob) */
 #endif
+#ifndef SDFR_CONV_FFMA2
+#define SDFR_CONV_FFMA2 1 /* packed fp32 multiply-adds (FFMA2) in the convolution's inner loop */
+#endif
 #ifndef SDFR_CONV_YR2_MAX_ACC
 #define SDFR_CONV_YR2_MAX_ACC 0 /* CO*ZR up to which a thread computes two output rows (tuning knob, off) */
 #endif
@@ -542,11 +545,21 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
   const size_t in_vol = (size_t)n_in * n_in * n_in;
   constexpr int shift = DGRAD ? K - 1 : 0; /* input coordinate = output coordinate + tap - shift */
 
+  /* Accumulators as float2 pairs over adjacent output channels: the weight vector of a tap arrives as
+   * float4 = two aligned channel pairs, the input value is duplicated into a pair once per row, and every
+   * multiply-add is one FFMA2 (fma.rn.f32x2, sm_100) -- two IEEE fp32 fmas per issue slot and per fma-pipe
+   * cycle, bit-identical to the scalar FFMAs (-DSDFR_CONV_FFMA2=0 builds those for the A/B). */
+#if SDFR_CONV_FFMA2
+  float2 acc2[CO / 2][NZ];
+#define SDFR_ACC(co, i) (((co) & 1) ? acc2[(co) >> 1][i].y : acc2[(co) >> 1][i].x)
+#else
   float acc[CO][NZ];
+#define SDFR_ACC(co, i) acc[co][i]
+#endif
 #pragma unroll
   for (int co = 0; co < CO; ++co)
 #pragma unroll
-    for (int i = 0; i < NZ; ++i) acc[co][i] = 0.0f;
+    for (int i = 0; i < NZ; ++i) SDFR_ACC(co, i) = 0.0f;
 
   const int ci_begin = kr * (CI / KS), ci_end = ci_begin + CI / KS; /* CI % KS == 0 (launcher) */
   for (int ci0 = ci_begin; ci0 < ci_end; ci0 += CC) {
@@ -627,6 +640,11 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
               for (int i = 0; i < ZR + K - 1; ++i) v[i] = row[i];
             }
+#if SDFR_CONV_FFMA2
+            float2 vv[ZR + K - 1];
+#pragma unroll
+            for (int i = 0; i < ZR + K - 1; ++i) vv[i] = make_float2(v[i], v[i]);
+#endif
 #pragma unroll
             for (int dz = 0; dz < K; ++dz) {
               const float4* __restrict__ wp =
@@ -634,6 +652,14 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
               for (int c4 = 0; c4 < CO / 4; ++c4) {
                 const float4 w4 = wp[c4];
+#if SDFR_CONV_FFMA2
+                const float2 wa = make_float2(w4.x, w4.y), wb = make_float2(w4.z, w4.w);
+#pragma unroll
+                for (int i = 0; i < ZR; ++i) {
+                  acc2[2 * c4 + 0][i] = __ffma2_rn(wa, vv[i + dz], acc2[2 * c4 + 0][i]);
+                  acc2[2 * c4 + 1][i] = __ffma2_rn(wb, vv[i + dz], acc2[2 * c4 + 1][i]);
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < ZR; ++i) {
                   acc[4 * c4 + 0][i] = fmaf(w4.x, v[i + dz], acc[4 * c4 + 0][i]);
@@ -641,6 +667,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
                   acc[4 * c4 + 2][i] = fmaf(w4.z, v[i + dz], acc[4 * c4 + 2][i]);
                   acc[4 * c4 + 3][i] = fmaf(w4.w, v[i + dz], acc[4 * c4 + 3][i]);
                 }
+#endif
               }
             }
           }
@@ -681,10 +708,16 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
                   for (int i = 0; i < ZR; ++i) {
                     const float x = v[r + dy][i + dz];
+#if SDFR_CONV_FFMA2
+                    const float2 xx = make_float2(x, x);
+                    acc2[2 * c4 + 0][r * ZR + i] = __ffma2_rn(make_float2(w4.x, w4.y), xx, acc2[2 * c4 + 0][r * ZR + i]);
+                    acc2[2 * c4 + 1][r * ZR + i] = __ffma2_rn(make_float2(w4.z, w4.w), xx, acc2[2 * c4 + 1][r * ZR + i]);
+#else
                     acc[4 * c4 + 0][r * ZR + i] = fmaf(w4.x, x, acc[4 * c4 + 0][r * ZR + i]);
                     acc[4 * c4 + 1][r * ZR + i] = fmaf(w4.y, x, acc[4 * c4 + 1][r * ZR + i]);
                     acc[4 * c4 + 2][r * ZR + i] = fmaf(w4.z, x, acc[4 * c4 + 2][r * ZR + i]);
                     acc[4 * c4 + 3][r * ZR + i] = fmaf(w4.w, x, acc[4 * c4 + 3][r * ZR + i]);
+#endif
                   }
                 }
               }
@@ -705,7 +738,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
       for (int co = 0; co < CO; ++co)
 #pragma unroll
-        for (int i = 0; i < NZ; ++i) red[(co * NZ + i) * 256 + threadIdx.x] = acc[co][i];
+        for (int i = 0; i < NZ; ++i) red[(co * NZ + i) * 256 + threadIdx.x] = SDFR_ACC(co, i);
     }
     cluster.sync();
     if (kr == 0) {
@@ -714,7 +747,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
 #pragma unroll
         for (int co = 0; co < CO; ++co)
 #pragma unroll
-          for (int i = 0; i < NZ; ++i) acc[co][i] += peer[(co * NZ + i) * 256 + threadIdx.x];
+          for (int i = 0; i < NZ; ++i) SDFR_ACC(co, i) += peer[(co * NZ + i) * 256 + threadIdx.x];
       }
     }
     cluster.sync(); /* peers keep their shared memory alive until the leader has read it */
@@ -736,7 +769,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
       for (int i = 0; i < ZR; ++i) {
         const int oz = Z0 + z0 + i;
         if (oz < n_out) {
-          float v = acc[co][r * ZR + i] + bias;
+          float v = SDFR_ACC(co, r * ZR + i) + bias;
           if (!DGRAD && P.relu) v = v > 0.0f ? v : 0.0f;
           o[oz] = v;
         }
@@ -744,6 +777,7 @@ sdfr_conv3_kernel(const __grid_constant__ ConvParams P) {
     }
   }
 }
+#undef SDFR_ACC
 
 template <int CO, int ZR, bool DGRAD, int VEC, int KS = 1, int YR = 1>
 int launch_conv3_v(ConvParams P, int batch, cudaStream_t s) {
