@@ -282,10 +282,14 @@ __device__ __forceinline__ Tiling cta_prologue(Frame& Fs, HullEdge* edges, float
         ncol = nrow = 0;
       }
     }
+    /* the tables span the whole image (table_bytes) and are indexed by the ABSOLUTE column / row; only the
+     * entries of the CTA's tiles are filled.  (Indexing relative to tab_x0 / tab_y0 kept those two integers
+     * live across the march: ptxas spilled them, and the reload in front of every warp tile's table look-up
+     * was 3 % of the fused kernel's stall samples.) */
     for (int i = threadIdx.x; i < ncol; i += kThreads)
-      colx[i] = pixel_dx(T.tab_x0 * kTileW + i, cam.cx, cam.fx);
+      colx[T.tab_x0 * kTileW + i] = pixel_dx(T.tab_x0 * kTileW + i, cam.cx, cam.fx);
     for (int i = threadIdx.x; i < nrow; i += kThreads)
-      rowy[i] = pixel_dy(T.tab_y0 * kTileH + i, cam.cy, cam.fy);
+      rowy[T.tab_y0 * kTileH + i] = pixel_dy(T.tab_y0 * kTileH + i, cam.cy, cam.fy);
     __syncthreads();
   }
   return T;
@@ -516,11 +520,11 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
       float z = 0.0f;
       Ray ray;
       if (inimg && px >= F.x0 && px < F.x1 && py >= F.y0 && py < F.y1) {
-        const float ux = P.use_tables ? colx[px - T.tab_x0 * kTileW] : pixel_dx(px, P.cam.cx, P.cam.fx);
-        const float uy = P.use_tables ? rowy[py - T.tab_y0 * kTileH] : pixel_dy(py, P.cam.cy, P.cam.fy);
+        const float ux = P.use_tables ? colx[px] : pixel_dx(px, P.cam.cx, P.cam.fx);
+        const float uy = P.use_tables ? rowy[py] : pixel_dy(py, P.cam.cy, P.cam.fy);
         ray = make_ray(F, ux, uy);
         float t_min, t_max;
-        if (ray_enters_cull_box(F, ray) && ray_box(F, ray, t_min, t_max)) {
+        if (ray_cull_and_box(F, ray, t_min, t_max)) {
           int steps;
           bool capped;
           z = march<RT, LT>(grid, Gc, F, ray, t_min, t_max, P.threshold, steps, capped);
@@ -651,17 +655,15 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
    * work): the loads of the NEXT tile are issued before the current one is processed */
   const int n_rect = T.rtw * T.rth;
   TileWalk w(g, G, T.rtw);
-  int px = 0, py = 0, tx = 0, ty = 0;
+  int px = 0, py = 0;
   float z = 0.0f, u = 0.0f;
   bool valid = false;
   auto fetch = [&](int r) {
     valid = false;
     z = 0.0f;
     if (r < n_rect) {
-      tx = T.rtx0 + w.tx;
-      ty = T.rty0 + w.ty;
-      px = tx * kTileW + lx;
-      py = ty * kTileH + ly;
+      px = (T.rtx0 + w.tx) * kTileW + lx;
+      py = (T.rty0 + w.ty) * kTileH + ly;
       if (px < W && py < H) {
         valid = true;
         z = __ldg(depth + (size_t)py * W + px);
@@ -672,7 +674,7 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
   fetch(g);
   for (int r = g; r < n_rect; r += G) {
     const float zc = z, uc = u;
-    const int cpx = px, cpy = py, ctx = tx, cty = ty;
+    const int cpx = px, cpy = py;
     const bool cvalid = valid;
     w.next();
     fetch(r + G);
@@ -689,10 +691,8 @@ sdfr_backward_kernel(const __grid_constant__ BwdParams P) {
     int base = 0;
     float w8[8];
     if (has) {
-      const float ux = P.use_tables ? colx[(ctx - T.tab_x0) * kTileW + lx]
-                                    : pixel_dx(cpx, P.cam.cx, P.cam.fx);
-      const float uy = P.use_tables ? rowy[(cty - T.tab_y0) * kTileH + ly]
-                                    : pixel_dy(cpy, P.cam.cy, P.cam.fy);
+      const float ux = P.use_tables ? colx[cpx] : pixel_dx(cpx, P.cam.cx, P.cam.fx);
+      const float uy = P.use_tables ? rowy[cpy] : pixel_dy(cpy, P.cam.cy, P.cam.fy);
       const Ray ray = make_ray(F, ux, uy);
       float m[kMoments];
 #pragma unroll
@@ -825,7 +825,7 @@ sdfr_forward_composite_kernel(const __grid_constant__ FwdParams P, int n_objects
       if (px < F.x0 || px >= F.x1 || py < F.y0 || py >= F.y1) continue;
       const Ray r = make_ray(F, colx[lx], rowy[ly]);
       float t_min, t_max;
-      if (!ray_enters_cull_box(F, r) || !ray_box(F, r, t_min, t_max)) continue;
+      if (!ray_cull_and_box(F, r, t_min, t_max)) continue;
       int steps;
       bool capped;
       const float z = march<RT, LT>(P.sdf + (size_t)(k0 + k) * P.sdf_stride, Gc, F, r, t_min,
