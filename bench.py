@@ -49,6 +49,8 @@ def parse_args():
     p.add_argument("--no-ref-ext", action="store_true",
                    help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-step-graph", action="store_true",
+                   help="issue the step's launches one by one instead of replaying them as one CUDA graph")
     p.add_argument("--min-time", type=float, default=0.0,
                    help="raise --steps so that the timed region lasts at least this many seconds (0 = time "
                         "exactly --steps steps, the driver's contract)")
@@ -61,7 +63,8 @@ def parse_args():
 
 def workload_name(B):
     return (f"C2: {B} pose/shape hypotheses x {W}x{H} depth, one {R}^3 fp32 SDF grid per hypothesis, "
-            "fused render + masked-L1 compare forward and backward (all four gradients)")
+            "fused render + masked-L1 compare forward and backward (all four gradients)")  # unchanged name: the
+    # driver compares `config` between the two arms
 
 
 def config_object(B, distributed):
@@ -77,7 +80,7 @@ def config_object(B, distributed):
 # against the ncu launch list of this command (profiles/*_launches.csv)
 KERNELS_PER_CALL = {
     "sdfr_skew_grids_bounds": 2,  # sdfr_bounds_init_kernel, sdfr_bounds_scan_kernel<true>
-    "sdfr_compare_fused": 2,      # sdfr_zero_small_kernel, sdfr_forward_kernel<64, skewed, 2>
+    "sdfr_compare_fused": 2,      # sdfr_zero_sums_and_small_kernel, sdfr_forward_kernel<64, skewed, 2>
     "sdfr_scale_grads": 1,        # sdfr_scale_grads_kernel
 }
 
@@ -406,10 +409,12 @@ def main():
     SK = int(n_sk.value)
     skewed = torch.empty(B, SK, device=dev)
 
+    cur_stream = [stream]  # the raw stream the step's launches go to (the capture stream while capturing)
+
     def skew():
         # dense decoder-layout grids -> bank-conflict-free pitched copy (one streaming pass); part
         # of every step because the grids change every iteration when the latent is optimised
-        _lib.check(lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, stream),
+        _lib.check(lib.sdfr_skew_grids(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, cur_stream[0]),
                    "sdfr_skew_grids")
 
     bounds = torch.empty((B, 8), dtype=torch.int32, device=dev)
@@ -419,20 +424,20 @@ def main():
         # cannot hit anything are written as 0 without marching; every other ray is marched exactly as
         # the reference marches it.  Part of every step for the same reason as the layout pass.
         _lib.check(lib.sdfr_grid_bounds(skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(),
-                                        inv_s.data_ptr(), B, THRESHOLD, bounds.data_ptr(), stream),
+                                        inv_s.data_ptr(), B, THRESHOLD, bounds.data_ptr(), cur_stream[0]),
                    "sdfr_grid_bounds")
 
     def skew_bound():
         # layout pass and bounds pass as ONE read of the dense grids (sdfr_skew_grids_bounds)
         _lib.check(lib.sdfr_skew_grids_bounds(grids.data_ptr(), R, RRR, B, skewed.data_ptr(), SK, pos.data_ptr(),
-                                              inv_s.data_ptr(), THRESHOLD, bounds.data_ptr(), stream),
+                                              inv_s.data_ptr(), THRESHOLD, bounds.data_ptr(), cur_stream[0]),
                    "sdfr_skew_grids_bounds")
 
     def fwd():
         _lib.check(lib.sdfr_compare_forward(
             skewed.data_ptr(), R, SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
             inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
-            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, bounds.data_ptr(), stream),
+            depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), _lib.ZERO_GRADS, bounds.data_ptr(), cur_stream[0]),
             "sdfr_compare_forward")
 
     def bwd():
@@ -440,7 +445,7 @@ def main():
             depth.data_ptr(), obs.data_ptr(), 0, sums[1].data_ptr(), None, skewed.data_ptr(), R,
             SK, _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(), inv_s.data_ptr(), B, W, H,
             CX, CY, FX, FY, g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
-            g_is.data_ptr(), flags_b, bounds.data_ptr(), stream), "sdfr_compare_backward")
+            g_is.data_ptr(), flags_b, bounds.data_ptr(), cur_stream[0]), "sdfr_compare_backward")
 
     def fused(dense=False, use_bounds=True):
         _lib.check(lib.sdfr_compare_fused(
@@ -449,22 +454,30 @@ def main():
             inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
             depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), RRR,
             g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
-            bounds.data_ptr() if use_bounds else None, stream), "sdfr_compare_fused")
+            bounds.data_ptr() if use_bounds else None, cur_stream[0]), "sdfr_compare_fused")
 
     def scale():
         _lib.check(lib.sdfr_scale_grads(
             sums[1].data_ptr(), None, R, B, g_sdf.data_ptr(), RRR, g_pos.data_ptr(),
-            g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, bounds.data_ptr(), 1, stream), "sdfr_scale_grads")
+            g_quat.data_ptr(), g_is.data_ptr(), _lib.GRAD_ALL, bounds.data_ptr(), 1, cur_stream[0]), "sdfr_scale_grads")
 
     launches = {"kernels": 0, "steps": 0}
     pending = []  # async all_gather work handles, at most two in flight (double-buffered losses)
 
-    def step():
-        # layout pass, then forward render + masked-L1 compare + backward in ONE traversal, then
-        # the deferred per-hypothesis normalisation of the gradients
+    step_graph = [None]
+
+    def step_kernels():
+        # layout + empty-space-bounds pass, forward render + masked-L1 compare + backward in ONE traversal, then
+        # the deferred per-hypothesis normalisation of the gradients inside the bounds box
         skew_bound()
         fused()
         scale()
+
+    def step():
+        if step_graph[0] is not None:
+            step_graph[0].replay()
+        else:
+            step_kernels()
         launches["kernels"] += (KERNELS_PER_CALL["sdfr_skew_grids_bounds"] + KERNELS_PER_CALL["sdfr_compare_fused"]
                                 + KERNELS_PER_CALL["sdfr_scale_grads"])
         if distributed:
@@ -522,6 +535,18 @@ def main():
             total += evs[-1][1].elapsed_time(tail)
         return total
 
+    if not args.no_step_graph:
+        # the step's launches recorded once and replayed: what a caller with fixed buffers does (the product
+        # loop and the e2e leg below do the same); the collective of the multi-GPU run stays outside the graph
+        for _ in range(2):
+            step_kernels()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            cur_stream[0] = torch.cuda.current_stream().cuda_stream
+            step_kernels()
+        cur_stream[0] = stream
+        step_graph[0] = g
     K, Wm = args.steps, max(args.warmup, 3)
     if args.min_time > 0:  # one probe step decides how many steps fill the requested time (same on every rank)
         probe = torch.tensor([timed(step, 3, 2, finish=drain if distributed else None) / 3], device=dev)
@@ -539,6 +564,8 @@ def main():
     value = world * B * P * K / (total_ms * 1e-3) / 1e6
     ms_per_step = total_ms / K
 
+    # the same step issued launch by launch, and with the normalisation as a separate pass
+    step_eager_ms = timed(step_kernels, K, 2) / K
     # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
     skew()
     bound()
@@ -747,6 +774,11 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": config_object(B, distributed),
         "render_hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
+        "step": {"what": "sdfr_skew_grids_bounds (layout + empty-space bounds, one read of the grids) -> "
+                         "sdfr_compare_fused (render + masked L1 + backward in one traversal) -> sdfr_scale_grads "
+                         "(upstream/n_overlap inside the bounds box)"
+                         + ("" if args.no_step_graph else "; the launches replayed as one CUDA graph"),
+                 "ms_issued_launch_by_launch": step_eager_ms},
         "loop": loop,
         "roofline": roofline,
         # the contract's `e2e`: the step from the inputs the reference's callers hold (latents, poses, observation

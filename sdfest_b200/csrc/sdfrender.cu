@@ -400,6 +400,75 @@ __device__ __forceinline__ void reduce_pose(MomentAcc& acc_s, const Frame& F, co
   }
 }
 
+/* grad_sdf *= coef over the voxels of one hypothesis that can hold a gradient: the cells inside the empty-space
+ * bounds the render used (every other voxel is still the zero it was cleared to), or the whole grid without
+ * bounds.  `warp` of `n_warps` warps share the rows; loads bypass L1 (the values were written by RED.ADDs of
+ * other SMs).  Four rows per step: the loads of all four are in flight before the first store (one dependent
+ * round trip per row otherwise: 22.8 us for the stand-alone pass at C2). */
+__device__ __forceinline__ void scale_sdf_grads(float* __restrict__ gs, const CellBounds* __restrict__ cbp, int R,
+                                                long long grid_elems, float coef, int warp, int n_warps, int lane) {
+  if (cbp) {
+    const CellBounds cb = *cbp;
+    if (cb.lo[0] > cb.hi[0]) return; /* no cell can be hit: the grid is all zeros */
+    /* voxels of cells lo..hi are lo..hi+1; rows (x, y) of the box, a warp per row, lanes along z */
+    const int x0 = cb.lo[0], nx = cb.hi[0] - cb.lo[0] + 2, y0 = cb.lo[1], ny = cb.hi[1] - cb.lo[1] + 2;
+    const int z0 = cb.lo[2], z1 = cb.hi[2] + 1;
+    if ((R & 3) == 0 && (reinterpret_cast<uintptr_t>(gs) & 15) == 0) {
+      /* aligned 16-byte accesses over the z-range rounded out to multiples of four (the extra voxels are the
+       * zeros the grid was cleared to), eight independent loads per thread in flight before the first store:
+       * the single CTA that normalises a hypothesis inside the render launch moves its ~200 KB in a handful of
+       * round trips instead of one per row */
+      const int zv0 = z0 >> 2, nv = (z1 >> 2) - zv0 + 1, total = nx * ny * nv;
+      const int tid = warp * 32 + lane, nthr = n_warps * 32;
+      for (int i0 = tid; i0 < total; i0 += 8 * nthr) {
+        float4 v[8];
+        float4* p[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = i0 + j * nthr;
+          const bool ok = i < total;
+          const int ii = ok ? i : i0;
+          const int r = ii / nv, k = ii - r * nv;
+          const int rx = r / ny, ry = r - rx * ny;
+          p[j] = reinterpret_cast<float4*>(gs + ((size_t)(x0 + rx) * R + (y0 + ry)) * R) + zv0 + k;
+          v[j] = ok ? __ldcg(p[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (i0 + j * nthr < total) *p[j] = make_float4(v[j].x * coef, v[j].y * coef, v[j].z * coef, v[j].w * coef);
+      }
+      return;
+    }
+    for (int r0 = warp; r0 < nx * ny; r0 += 4 * n_warps) {
+      for (int z = z0 + lane; z <= z1; z += 32) {
+        float v[4];
+        float* p[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = r0 + j * n_warps;
+          const bool ok = r < nx * ny;
+          const int rr = ok ? r : r0;
+          p[j] = gs + ((size_t)(x0 + rr / ny) * R + (y0 + rr % ny)) * R + z;
+          v[j] = ok ? __ldcg(p[j]) : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (r0 + j * n_warps < nx * ny) *p[j] = v[j] * coef;
+      }
+    }
+    return;
+  }
+  const long long n4 = ((reinterpret_cast<uintptr_t>(gs) & 15) == 0) ? grid_elems / 4 : 0;
+  float4* __restrict__ gs4 = reinterpret_cast<float4*>(gs);
+  for (long long i = (long long)warp * 32 + lane; i < n4; i += (long long)n_warps * 32) {
+    float4 v = __ldcg(gs4 + i);
+    v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
+    gs4[i] = v;
+  }
+  for (long long i = n4 * 4 + (long long)warp * 32 + lane; i < grid_elems; i += (long long)n_warps * 32)
+    gs[i] = __ldcg(gs + i) * coef;
+}
+
 /* ------------------------------------------------------------------------------------------
  * Forward (replaces sdf_renderer_cuda_forward_kernel, cu:241-298).
  * MODE 0: depth only.  MODE 1: + masked-L1 compare sums.  MODE 2: + the backward of that loss
@@ -732,49 +801,10 @@ sdfr_scale_grads_kernel(const float* __restrict__ n_overlap, const float* __rest
       if (flags & SDFR_GRAD_INV_SCALE) gi[b] *= coef;
     }
   }
-  if (flags & SDFR_GRAD_SDF) {
-    float* __restrict__ gs = grad_sdf + (size_t)b * gs_stride;
-    if (bounds) {
-      const CellBounds cb = bounds[(size_t)b * bounds_stride];
-      if (cb.lo[0] > cb.hi[0]) return; /* no cell can be hit: the grid is all zeros */
-      /* voxels of cells lo..hi are lo..hi+1; rows (x, y) of the box, a warp per row, lanes along z */
-      const int x0 = cb.lo[0], nx = cb.hi[0] - cb.lo[0] + 2, y0 = cb.lo[1], ny = cb.hi[1] - cb.lo[1] + 2;
-      const int z0 = cb.lo[2], z1 = cb.hi[2] + 1;
-      const int warp = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
-      const int n_warps = (int)((gridDim.x * blockDim.x) >> 5);
-      /* four rows per step: the loads of all four are in flight before the first store (one dependent
-       * HBM round trip per row otherwise: 22.8 us) */
-      for (int r0 = warp; r0 < nx * ny; r0 += 4 * n_warps) {
-        for (int z = z0 + lane; z <= z1; z += 32) {
-          float v[4];
-          float* p[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int r = r0 + j * n_warps;
-            const bool ok = r < nx * ny;
-            const int rr = ok ? r : r0;
-            p[j] = gs + ((size_t)(x0 + rr / ny) * R + (y0 + rr % ny)) * R + z;
-            v[j] = ok ? *p[j] : 0.0f;
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (r0 + j * n_warps < nx * ny) *p[j] = v[j] * coef;
-        }
-      }
-      return;
-    }
-    const long long n4 = ((reinterpret_cast<uintptr_t>(gs) & 15) == 0) ? grid_elems / 4 : 0;
-    float4* __restrict__ gs4 = reinterpret_cast<float4*>(gs);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4;
-         i += (long long)gridDim.x * blockDim.x) {
-      float4 v = gs4[i];
-      v.x *= coef; v.y *= coef; v.z *= coef; v.w *= coef;
-      gs4[i] = v;
-    }
-    for (long long i = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < grid_elems;
-         i += (long long)gridDim.x * blockDim.x)
-      gs[i] *= coef;
-  }
+  if (flags & SDFR_GRAD_SDF)
+    scale_sdf_grads(grad_sdf + (size_t)b * gs_stride, bounds ? bounds + (size_t)b * bounds_stride : nullptr, R,
+                    grid_elems, coef, (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5),
+                    (int)((gridDim.x * blockDim.x) >> 5), threadIdx.x & 31);
 }
 
 /* zero up to three small buffers in one launch (pose-gradient outputs) */
@@ -783,6 +813,20 @@ __global__ void sdfr_zero_small_kernel(float* a, int na, float* b, int nb, float
     if (i < na) a[i] = 0.0f;
     else if (i < na + nb) b[i - na] = 0.0f;
     else c[i - na - nb] = 0.0f;
+  }
+}
+
+/* the per-hypothesis sums of the compare kernels (loss_sum, n_overlap, optional n_inlier: n each) and the three
+ * pose-gradient outputs in ONE launch instead of three memset nodes plus a launch */
+__global__ void sdfr_zero_sums_and_small_kernel(float* s0, float* s1, float* s2, int n, float* a, int na, float* b,
+                                                int nb, float* c, int nc) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * n + na + nb + nc; i += gridDim.x * blockDim.x) {
+    if (i < n) s0[i] = 0.0f;
+    else if (i < 2 * n) s1[i - n] = 0.0f;
+    else if (i < 3 * n) { if (s2) s2[i - 2 * n] = 0.0f; }
+    else if (i < 3 * n + na) a[i - 3 * n] = 0.0f;
+    else if (i < 3 * n + na + nb) b[i - 3 * n - na] = 0.0f;
+    else c[i - 3 * n - na - nb] = 0.0f;
   }
 }
 
@@ -1637,12 +1681,17 @@ static int compare_fused_impl(const float* sdf, int R, long long sdf_stride, int
   if (!loss_sum || !n_overlap) return fail(SDFR_E_NULL, "loss_sum or n_overlap is NULL");
   cudaStream_t s = (cudaStream_t)stream;
   if (flags & SDFR_ZERO_GRADS) {
-    if (int rc = zero_async(loss_sum, sizeof(float) * batch, s)) return rc;
-    if (int rc = zero_async(n_overlap, sizeof(float) * batch, s)) return rc;
-    if (n_inlier)
-      if (int rc = zero_async(n_inlier, sizeof(float) * batch, s)) return rc;
+    /* the gradient grids by memset, every small buffer (sums and pose gradients) in one launch */
+    if (int rc = zero_grads(flags & ~(SDFR_GRAD_POSITION | SDFR_GRAD_ORIENTATION | SDFR_GRAD_INV_SCALE), R, batch,
+                            gs, gs_stride, gp, gq, gi, s))
+      return rc;
+    const int na = (flags & SDFR_GRAD_POSITION) ? 3 * batch : 0;
+    const int nb = (flags & SDFR_GRAD_ORIENTATION) ? 4 * batch : 0;
+    const int nc = (flags & SDFR_GRAD_INV_SCALE) ? batch : 0;
+    sdfr_zero_sums_and_small_kernel<<<batch > 512 ? 16 : 1, 256, 0, s>>>(loss_sum, n_overlap, n_inlier, batch, gp,
+                                                                       na, gq, nb, gi, nc);
+    if (int rc = check_launch("sdfr_zero_sums_and_small_kernel")) return rc;
   }
-  if (int rc = zero_grads(flags, R, batch, gs, gs_stride, gp, gq, gi, s)) return rc;
   if (W == 0 || H == 0) return 0;
   if (!depth || !depth_obs) return fail(SDFR_E_NULL, "depth or depth_obs is NULL");
   FwdParams P = fwd_params(sdf, R, sdf_stride, layout, pos, quat, inv_scale, W, H, cx, cy, fx, fy,

@@ -36,7 +36,7 @@ def test_pure_pieces_of_the_line():
     assert abs(g["achieved_gsamples_per_s"] - 100.0) < 1e-9
     assert abs(g["frac_of_l2_gather_peak"] - 100.0 / 201.0) < 1e-12 and "limiter" in g
     assert "gather" in bench.roofline_object(10 ** 9, 0.2, 10 ** 6, 6547.5, "m", None, None)
-    assert sum(bench.KERNELS_PER_CALL.values()) == 5
+    assert sum(bench.KERNELS_PER_CALL.values()) == 5  # the step: bounds (2) + fused (2) + scale (1)
     peaks = bench.gather_peaks()  # the committed micro-benchmark result
     assert peaks and peaks["l1_skewed_gsamples"] > peaks["l2_skewed_gsamples"] > 50
 
