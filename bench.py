@@ -80,7 +80,7 @@ def config_object(B, distributed):
 # against the ncu launch list of this command (profiles/*_launches.csv)
 KERNELS_PER_CALL = {
     "sdfr_skew_grids_bounds": 2,  # sdfr_bounds_init_kernel, sdfr_bounds_scan_kernel<true>
-    "sdfr_compare_fused": 2,      # sdfr_zero_sums_and_small_kernel, sdfr_forward_kernel<64, skewed, 2>
+    "sdfr_compare_fused": 1,      # sdfr_forward_kernel<64, skewed, 2> (the step clears the outputs with memset nodes)
     "sdfr_scale_grads": 1,        # sdfr_scale_grads_kernel
 }
 
@@ -393,9 +393,12 @@ def main():
     P = W * H
 
     depth = torch.empty(B, H, W, device=dev)
-    sums = torch.zeros(2, B, device=dev)
+    # the per-hypothesis sums and the three pose-gradient outputs in ONE allocation (one clear per step)
+    small = torch.zeros(10 * B, device=dev)
+    sums = small[:2 * B].view(2, B)
+    g_pos, g_quat, g_is = small[2 * B:5 * B].view(B, 3), small[5 * B:9 * B].view(B, 4), small[9 * B:]
     g_sdf = torch.empty_like(grids)
-    g_pos, g_quat, g_is = torch.empty_like(pos), torch.empty_like(quat), torch.empty_like(inv_s)
+    clear_stream = torch.cuda.Stream(dev)
     gathered2 = torch.empty(2, world * B, device=dev) if distributed else None
     loss2 = torch.empty(2, B, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
@@ -447,13 +450,13 @@ def main():
             CX, CY, FX, FY, g_sdf.data_ptr(), RRR, g_pos.data_ptr(), g_quat.data_ptr(),
             g_is.data_ptr(), flags_b, bounds.data_ptr(), cur_stream[0]), "sdfr_compare_backward")
 
-    def fused(dense=False, use_bounds=True):
+    def fused(dense=False, use_bounds=True, zero=True):
         _lib.check(lib.sdfr_compare_fused(
             (grids if dense else skewed).data_ptr(), R, RRR if dense else SK,
             _lib.LAYOUT_DENSE if dense else _lib.LAYOUT_SKEWED, pos.data_ptr(), quat.data_ptr(),
             inv_s.data_ptr(), B, W, H, CX, CY, FX, FY, THRESHOLD, obs.data_ptr(), 0,
             depth.data_ptr(), sums[0].data_ptr(), sums[1].data_ptr(), g_sdf.data_ptr(), RRR,
-            g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b,
+            g_pos.data_ptr(), g_quat.data_ptr(), g_is.data_ptr(), flags_b if zero else _lib.GRAD_ALL,
             bounds.data_ptr() if use_bounds else None, cur_stream[0]), "sdfr_compare_fused")
 
     def scale():
@@ -468,7 +471,22 @@ def main():
 
     def step_kernels():
         # layout + empty-space-bounds pass, forward render + masked-L1 compare + backward in ONE traversal, then
-        # the deferred per-hypothesis normalisation of the gradients inside the bounds box
+        # the deferred per-hypothesis normalisation of the gradients inside the bounds box.  The outputs are
+        # cleared on a second stream BESIDE the layout pass (the C ABI accumulates when SDFR_ZERO_GRADS is not
+        # set, include/sdfrender.h; the product loop does the same, estimation/hypotheses.py): two memset nodes
+        # parallel to the first kernels of the captured graph instead of a serial 64 MiB clear in front of the render
+        main = torch.cuda.current_stream()
+        clear_stream.wait_stream(main)
+        with torch.cuda.stream(clear_stream):
+            g_sdf.zero_()
+            small.zero_()
+        skew_bound()
+        main.wait_stream(clear_stream)
+        fused(zero=False)
+        scale()
+
+    def step_serial_clears():
+        # the same step with the library clearing its outputs in front of the render (SDFR_ZERO_GRADS)
         skew_bound()
         fused()
         scale()
@@ -566,6 +584,7 @@ def main():
 
     # the same step issued launch by launch, and with the normalisation as a separate pass
     step_eager_ms = timed(step_kernels, K, 2) / K
+    step_serial_clears_ms = timed(step_serial_clears, K, 2) / K
     # per-kernel launch durations for the roofline (rank 0's GPU; same flush discipline)
     skew()
     bound()
@@ -776,9 +795,10 @@ def main():
         "render_hyp_iter_per_s": world * B * K / (total_ms * 1e-3),
         "step": {"what": "sdfr_skew_grids_bounds (layout + empty-space bounds, one read of the grids) -> "
                          "sdfr_compare_fused (render + masked L1 + backward in one traversal) -> sdfr_scale_grads "
-                         "(upstream/n_overlap inside the bounds box)"
+                         "(upstream/n_overlap inside the bounds box); the outputs cleared on a second stream beside the layout pass"
                          + ("" if args.no_step_graph else "; the launches replayed as one CUDA graph"),
-                 "ms_issued_launch_by_launch": step_eager_ms},
+                 "ms_issued_launch_by_launch": step_eager_ms,
+                 "ms_launch_by_launch_library_clears_in_front_of_the_render": step_serial_clears_ms},
         "loop": loop,
         "roofline": roofline,
         # the contract's `e2e`: the step from the inputs the reference's callers hold (latents, poses, observation
