@@ -194,6 +194,16 @@ __device__ __forceinline__ void build_frame(Frame& smemF, HullEdge* edges, const
   }
 }
 
+/* n / d for 0 <= n < 2^24, d > 0 with a reciprocal computed once (rd = 1.0f / d): the tile loops divide by the
+ * same run-time width for every candidate, and an integer division is ~25 instructions */
+__device__ __forceinline__ int div_by(int n, int d, float rd) {
+  int q = __float2int_rz(__int2float_rn(n) * rd);
+  const int rem = n - q * d;
+  q += rem >= d ? 1 : 0;
+  q -= rem < 0 ? 1 : 0;
+  return q;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -555,12 +565,13 @@ sdfr_forward_kernel(const __grid_constant__ FwdParams P) {
     /* 8 lanes per candidate: lane e tests hull edge e, then stores one float4 of the zero fill */
     const unsigned grp_mask = 0xffu << (lane & 24);
     const HullEdge my_edge = edges[lane & 7];
+    const float inv_rtw = 1.0f / (float)(T.rtw > 0 ? T.rtw : 1);
     for (int i0 = 0; i0 < n_here; i0 += kThreads / 8) {
       const int i = i0 + (threadIdx.x >> 3);
       const bool have = i < n_here;
       const int cand = c0 + (have ? i : 0);
       const int r = g + (cand >> 3) * G, sub = cand & 7;
-      const int wty = r / T.rtw;
+      const int wty = div_by(r, T.rtw, inv_rtw);
       const int tx = T.rtx0 + (r - wty * T.rtw), ty = T.rty0 + wty;
       const int wx0 = tx * kTileW + ((sub & 3) << 3), wy0 = ty * kTileH + ((sub >> 2) << 2);
       const bool out_rect = wx0 >= F.x1 || wx0 + 8 <= F.x0 || wy0 >= F.y1 || wy0 + 4 <= F.y0;
