@@ -49,6 +49,9 @@ def parse_args():
     p.add_argument("--no-ref-ext", action="store_true",
                    help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--gather-every", type=int, default=5,
+                   help="multi-GPU: steps per exchange -- every step's per-hypothesis losses are kept in a ring on "
+                        "the device and all-gathered as one [K, hypotheses] block every K steps (1 = every step)")
     p.add_argument("--no-step-graph", action="store_true",
                    help="issue the step's launches one by one instead of replaying them as one CUDA graph")
     p.add_argument("--min-time", type=float, default=0.0,
@@ -399,8 +402,10 @@ def main():
     g_pos, g_quat, g_is = small[2 * B:5 * B].view(B, 3), small[5 * B:9 * B].view(B, 4), small[9 * B:]
     g_sdf = torch.empty_like(grids)
     clear_stream = torch.cuda.Stream(dev)
-    gathered2 = torch.empty(2, world * B, device=dev) if distributed else None
-    loss2 = torch.empty(2, B, device=dev)
+    Kg = max(1, args.gather_every) if distributed else 1
+    ring = torch.zeros(Kg, 2, B, device=dev)  # loss_sum / n_overlap of the last Kg steps
+    gathered2 = torch.empty(2, world * Kg * B, device=dev) if distributed else None
+    loss2 = torch.empty(2, Kg, B, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     RRR = R * R * R
     flags_b = _lib.GRAD_ALL | _lib.ZERO_GRADS
@@ -467,9 +472,9 @@ def main():
     launches = {"kernels": 0, "steps": 0}
     pending = []  # async all_gather work handles, at most two in flight (double-buffered losses)
 
-    step_graph = [None]
+    step_graph = [None] * Kg  # one captured step per ring slot (they differ in the slot the sums are copied to)
 
-    def step_kernels():
+    def step_kernels(slot=None):
         # layout + empty-space-bounds pass, forward render + masked-L1 compare + backward in ONE traversal, then
         # the deferred per-hypothesis normalisation of the gradients inside the bounds box.  The outputs are
         # cleared on a second stream BESIDE the layout pass (the C ABI accumulates when SDFR_ZERO_GRADS is not
@@ -484,6 +489,8 @@ def main():
         main.wait_stream(clear_stream)
         fused(zero=False)
         scale()
+        if slot is not None:
+            ring[slot].copy_(sums)  # 2 x hypotheses floats, device to device
 
     def step_serial_clears():
         # the same step with the library clearing its outputs in front of the render (SDFR_ZERO_GRADS)
@@ -491,27 +498,40 @@ def main():
         fused()
         scale()
 
+    ring_pos = [0]
+    n_exchanges = [0]
+
+    def exchange():
+        # the only exchange of the path: per-hypothesis losses (<= 2 KB per rank and step).  Nothing in the next
+        # steps depends on it (the loop only ranks hypotheses at the end), so the losses of Kg steps are gathered
+        # as one block, on NCCL's own stream beside the next steps' kernels; the buffers alternate, and a buffer
+        # is reused only after the gather that read it has completed (stream-side wait, no host synchronisation).
+        k = n_exchanges[0] & 1
+        n_exchanges[0] += 1
+        if len(pending) == 2:
+            pending.pop(0).wait()
+        torch.div(ring[:, 0], ring[:, 1], out=loss2[k])
+        pending.append(dist.all_gather_into_tensor(gathered2[k], loss2[k].view(-1), async_op=True))
+        launches["kernels"] += 2  # the division and NCCL's all-gather kernel
+
     def step():
-        if step_graph[0] is not None:
-            step_graph[0].replay()
+        slot = ring_pos[0] if distributed else None
+        if step_graph[slot or 0] is not None:
+            step_graph[slot or 0].replay()
         else:
-            step_kernels()
+            step_kernels(slot)
         launches["kernels"] += (KERNELS_PER_CALL["sdfr_skew_grids_bounds"] + KERNELS_PER_CALL["sdfr_compare_fused"]
                                 + KERNELS_PER_CALL["sdfr_scale_grads"])
         if distributed:
-            # the only exchange of the path: per-hypothesis losses (<= 2 KB / rank).  Nothing in the next
-            # step depends on it (the loop only ranks hypotheses at the end), so it runs on NCCL's own
-            # stream beside the next step's kernels; the buffers alternate, and a buffer is reused only
-            # after the gather that read it has completed (stream-side wait, no host synchronisation).
-            k = launches["steps"] & 1
-            if len(pending) == 2:
-                pending.pop(0).wait()
-            torch.div(sums[0], sums[1], out=loss2[k])
-            pending.append(dist.all_gather_into_tensor(gathered2[k], loss2[k], async_op=True))
-            launches["kernels"] += 2  # the division and NCCL's all-gather kernel
+            ring_pos[0] = (ring_pos[0] + 1) % Kg
+            if ring_pos[0] == 0:
+                exchange()
         launches["steps"] += 1
 
     def drain():
+        if distributed and ring_pos[0] != 0:  # the last, partial block
+            ring_pos[0] = 0
+            exchange()
         while pending:
             pending.pop(0).wait()
 
@@ -559,12 +579,13 @@ def main():
         for _ in range(2):
             step_kernels()
         torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            cur_stream[0] = torch.cuda.current_stream().cuda_stream
-            step_kernels()
-        cur_stream[0] = stream
-        step_graph[0] = g
+        for slot in range(Kg):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):  # NCCL's watchdog thread polls events
+                cur_stream[0] = torch.cuda.current_stream().cuda_stream
+                step_kernels(slot if distributed else None)
+            cur_stream[0] = stream
+            step_graph[slot] = g
     K, Wm = args.steps, max(args.warmup, 3)
     if args.min_time > 0:  # one probe step decides how many steps fill the requested time (same on every rank)
         probe = torch.tensor([timed(step, 3, 2, finish=drain if distributed else None) / 3], device=dev)
@@ -799,6 +820,8 @@ def main():
                          + ("" if args.no_step_graph else "; the launches replayed as one CUDA graph"),
                  "ms_issued_launch_by_launch": step_eager_ms,
                  "ms_launch_by_launch_library_clears_in_front_of_the_render": step_serial_clears_ms},
+        "exchange": ({"what": "every step's per-hypothesis losses kept in a device ring, all-gathered as one block",
+                      "steps_per_all_gather": Kg, "bytes_per_rank_and_gather": 4 * Kg * B} if distributed else None),
         "loop": loop,
         "roofline": roofline,
         # the contract's `e2e`: the step from the inputs the reference's callers hold (latents, poses, observation

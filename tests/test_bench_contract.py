@@ -72,7 +72,10 @@ def test_own_arm_line_of_the_last_committed_runs():
             assert c["kind"] in ("reference", "port") and c["cores"] >= 1 and c["value"] > 0 and c["sample"]
         if pattern.startswith("r02"):  # this round's additions
             per_step = 4 if "step" in d else 5  # since the step clears its outputs with memset nodes
-            assert d["gpu_launches"] == per_step * d["steps"] + (2 * d["steps"] if d["n_gpus"] > 1 else 0)
+            gathers = 0
+            if d["n_gpus"] > 1:  # the division + NCCL's kernel, per step or per block of steps
+                gathers = -(-d["steps"] // d["exchange"]["steps_per_all_gather"]) if d.get("exchange") else d["steps"]
+            assert d["gpu_launches"] == per_step * d["steps"] + 2 * gathers
             assert d["config"] == bench.config_object(d["config"]["hypotheses_per_gpu"], d["n_gpus"] > 1)
             assert 0 < d["roofline"]["gather"]["frac_of_l1_gather_peak"] < d["roofline"]["gather"]["frac_of_l2_gather_peak"]
             if "e2e_grids" in d:  # e2e = host latents -> device decode; e2e_grids = the grids cross PCIe
