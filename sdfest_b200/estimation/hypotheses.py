@@ -181,8 +181,8 @@ class HypothesisOptimizer:
         self.point_counts = None  # (B,) points hypothesis b owns, when the clouds differ
         self._views = None
         self.point_capacity, self._n_points, self.max_points = int(point_capacity), None, int(max_points)
-        if point_capacity and (self.optimizer_impl != "fused" or multiview or self.depth_obs.dim() != 2):
-            raise ValueError("point_capacity needs the fused path and one shared observation (H,W)")
+        if point_capacity and (self.optimizer_impl != "fused" or (not multiview and self.depth_obs.dim() != 2)):
+            raise ValueError("point_capacity needs the fused path and one shared observation (H,W) or views (V,H,W)")
         if multiview:
             V = int(camera_positions.shape[0])
             if instance is not None:
@@ -195,6 +195,12 @@ class HypothesisOptimizer:
                            camera_orientations.detach().to(dev_o, torch.float32).contiguous())
             self._view_points = [losses.subsample_points(losses.depth_to_pointcloud(d, camera), max_points)
                                  for d in self.depth_obs]
+            self._view_counts = [int(p.shape[0]) for p in self._view_points]
+            if point_capacity:
+                # fixed-size clouds (padding outside every volume) and private copies of what reset() overwrites
+                self.depth_obs = self.depth_obs.clone()
+                self._views = tuple(t.clone() for t in self._views)
+                self._view_points = [self._padded_cloud(p, int(point_capacity)) for p in self._view_points]
             self.points = self._view_points[0]
         elif self.depth_obs.dim() == 2:
             if instance is not None:
@@ -242,6 +248,18 @@ class HypothesisOptimizer:
             with torch.cuda.device(self.position.device):
                 self._init_fused()
 
+    @staticmethod
+    def _padded_cloud(points: torch.Tensor, capacity: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(M,3) observed points in a (capacity,3) buffer, the rest far outside every SDF volume."""
+        n = int(points.shape[0])
+        if n > capacity:
+            raise ValueError(f"{n} observed points exceed point_capacity {capacity}")
+        if out is None:
+            out = torch.empty((capacity, 3), dtype=torch.float32, device=points.device)
+        out.fill_(losses.PAD_COORDINATE)
+        out[:n].copy_(points)
+        return out
+
     def _load_points(self, points: torch.Tensor, capacity: int) -> None:
         """Observed points (M,3) into the fixed-size buffer (allocated on first use)."""
         n = int(points.shape[0])
@@ -253,18 +271,54 @@ class HypothesisOptimizer:
         self.points[:n].copy_(points)
         self._n_points = n
 
+    def _reset_views(self, depth_obs: torch.Tensor, camera_positions: Optional[torch.Tensor],
+                     camera_orientations: Optional[torch.Tensor]) -> None:
+        """New observations (V,H,W) and camera poses of the view loop into the buffers the captured graph reads."""
+        if tuple(depth_obs.shape) != tuple(self.depth_obs.shape):
+            raise ValueError("depth_obs must keep its shape (V,H,W)")
+        if self.pc_weight and not self.point_capacity:
+            raise RuntimeError("new observations need point_capacity (the cloud sizes are baked in)")
+        clouds = []
+        if self.pc_weight:
+            clouds = [losses.subsample_points(losses.depth_to_pointcloud(d, self.camera), self.max_points)
+                      for d in depth_obs]
+            for c in clouds:  # before any buffer is touched: may raise
+                if int(c.shape[0]) > self.point_capacity:
+                    raise ValueError(f"{int(c.shape[0])} observed points exceed point_capacity {self.point_capacity}")
+        for v, c in enumerate(clouds):
+            self._padded_cloud(c, self.point_capacity, out=self._view_points[v])
+            n = int(c.shape[0])
+            self._view_counts[v] = n
+            self._view_up_p[v].fill_(self.pc_weight / n if n else 0.0)
+        self.depth_obs.copy_(depth_obs)
+        if camera_positions is not None:
+            self._views[0].copy_(camera_positions.reshape(self._views[0].shape))
+        if camera_orientations is not None:
+            self._views[1].copy_(camera_orientations.reshape(self._views[1].shape))
+
     def reset(self, position: torch.Tensor, orientation: torch.Tensor, scale: torch.Tensor,
-              latent: Optional[torch.Tensor] = None, depth_obs: Optional[torch.Tensor] = None) -> None:
+              latent: Optional[torch.Tensor] = None, depth_obs: Optional[torch.Tensor] = None,
+              camera_positions: Optional[torch.Tensor] = None,
+              camera_orientations: Optional[torch.Tensor] = None) -> None:
         """Start over from a new initial estimate -- and, with ``depth_obs``, a new observation -- in the SAME
         device buffers: optimiser state, result selection and losses are cleared, and a captured graph stays
         valid (``step()`` keeps replaying it).  Fused path only; a new observation needs ``point_capacity``
-        (or ``pc_weight`` 0).  Raises ValueError when the new cloud does not fit the capacity."""
+        (or ``pc_weight`` 0).  With views: ``depth_obs`` (V,H,W) and, optionally, new camera poses.  The point
+        constraint, if any, stays the one given at construction.  Raises ValueError when a new cloud does not
+        fit the capacity."""
         if self.optimizer_impl != "fused":
             raise RuntimeError("reset() is for optimizer='fused'")
-        if self._V or self.point_counts is not None:
-            raise RuntimeError("reset() supports one shared observation (no views, no instances)")
+        if self.point_counts is not None:
+            raise RuntimeError("reset() supports one shared observation or views (no object instances)")
+        if not self._V and (camera_positions is not None or camera_orientations is not None):
+            raise ValueError("camera poses can only be reset on an optimiser constructed with views")
         with torch.no_grad(), torch.cuda.device(self.position.device):
-            if depth_obs is not None:
+            if self._V:
+                if depth_obs is not None:
+                    self._reset_views(depth_obs, camera_positions, camera_orientations)
+                elif camera_positions is not None or camera_orientations is not None:
+                    self._reset_views(self.depth_obs.clone(), camera_positions, camera_orientations)
+            elif depth_obs is not None:
                 if tuple(depth_obs.shape) != tuple(self.depth_obs.shape):
                     raise ValueError("depth_obs must keep its shape")
                 if self._M and not self.point_capacity:
@@ -292,7 +346,7 @@ class HypothesisOptimizer:
                 self.best_inlier_ratio.fill_(-1.0)
                 self.best_iteration.fill_(-1)
                 self._iteration.zero_()
-                if self.inlier_threshold <= 1.0:
+                if self.inlier_threshold <= 1.0 and not self._V:  # views recount both every iteration
                     self._inl[1].fill_(float((self.depth_obs != 0).sum()))
             self._hyp_step(_lib.STEP_NO_UPDATE)  # unit quaternions and 1/scale of the new estimate
         self.last_losses = None
@@ -365,8 +419,10 @@ class HypothesisOptimizer:
             self._pb = (pb[:3 * B], pb[3 * B:7 * B], pb[7 * B:])
             self._view_M = [int(p.shape[0]) if self.pc_weight else 0 for p in self._view_points]
             self._view_points = [p.contiguous() for p in self._view_points]
-            self._view_up_p = [torch.full((B,), self.pc_weight / m if m else 0.0, dtype=torch.float32, device=dev)
-                               for m in self._view_M]
+            # the weight pc_weight / (true number of points of the view) lives in device memory: reset() can
+            # change it under a captured graph (with point_capacity the buffers are larger than the clouds)
+            self._view_up_p = [torch.full((B,), self.pc_weight / n if (n and m) else 0.0, dtype=torch.float32,
+                                          device=dev) for n, m in zip(self._view_counts, self._view_M)]
         self._M = M
         if self.point_capacity:
             # fixed-size buffer: the weight pc_weight / (true count) lives in device memory (upstream and,

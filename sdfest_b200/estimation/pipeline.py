@@ -44,9 +44,9 @@ class SDFPipeline:
     ``init`` = {``backbone_type``, ``normalize_pose``, ``head``: {``orientation_repr``}}; extensions:
     ``cuda_graph`` (True), ``fused_decoder`` (True), ``n_hypotheses`` (1), ``max_points`` (0 = all),
     ``reuse_graph`` (True): keep the captured iteration of a call and replay it for later calls of the same
-    shape (one camera-frame view, shape optimisation on, no point constraint) -- the next observation and
-    initial estimate are loaded into the same device buffers (``HypothesisOptimizer.reset``), which removes
-    the three eager warm-up iterations and the capture (~9 ms) from every call after the first;
+    shape (same number of views, shape optimisation on, same point constraint or none) -- the next observations,
+    camera poses and initial estimate are loaded into the same device buffers (``HypothesisOptimizer.reset``),
+    which removes the three eager warm-up iterations and the capture (~9 ms) from every call after the first;
     ``profile`` (False): record ``last_timings``.
     ``vae``: a module with ``decode(latent) -> (B,1,R,R,R)`` and a ``decoder`` attribute (the reference's
     ``SDFVAE``); ``init_network``: ``points (1,M,3) | depth (1,H,W) -> (latent, position, scale,
@@ -206,8 +206,8 @@ class SDFPipeline:
         n_it = int(self.config.get("max_iterations", 50))
         use_graph = self.config.get("cuda_graph", True) and n_it > 8
         # one captured iteration serves every call of the same shape (see `reuse_graph` above)
-        reusable = (use_graph and self.config.get("reuse_graph", True) and position.is_cuda and world_is_camera
-                    and shape_optimization and point_constraint is None
+        reusable = (use_graph and self.config.get("reuse_graph", True) and position.is_cuda
+                    and shape_optimization
                     and isinstance(kw.get("decoder"), FusedTailDecoder) and latent.shape[1] <= 64)
         opt, done = None, 0
         if reusable:
@@ -215,12 +215,22 @@ class SDFPipeline:
             key = (n_hyp, int(latent.shape[1]), id(kw["decoder"]), str(dev), float(self.config["threshold"]),
                    float(kw["depth_weight"]), float(kw["pc_weight"]), int(kw["max_points"]),
                    float(kw["inlier_threshold"]), self.cam.width, self.cam.height, self.cam.fx, self.cam.fy,
-                   self.cam.cx, self.cam.cy, self.cam.pixel_center, get_sdf_grad_mode(), get_empty_space_policy())
-            n_obs = int((obs != 0).sum()) if kw["pc_weight"] else 0
+                   self.cam.cx, self.cam.cy, self.cam.pixel_center, get_sdf_grad_mode(), get_empty_space_policy(),
+                   # the view loop bakes in the number of views; the point constraint's source / target / weight
+                   # are launch arguments (host values) of the captured sdfr_point_constraint
+                   0 if world_is_camera else n_imgs,
+                   None if point_constraint is None else tuple(
+                       (float(v) for v in torch.as_tensor(point_constraint[0]).flatten().tolist()
+                        + torch.as_tensor(point_constraint[1]).flatten().tolist() + [float(point_constraint[2])])))
+            # the largest cloud of the call (one per view) decides whether the cached buffers fit
+            n_obs = int((obs != 0).flatten(-2).sum(-1).max()) if kw["pc_weight"] else 0
             n_pts = min(n_obs, kw["max_points"]) if kw["max_points"] else n_obs
             cached = self._graph_cache.get(key)
             if cached is not None and n_pts <= cached.point_capacity <= 2 * n_pts + 8192:
-                cached.reset(position, orientation, scale, latent, obs)
+                if world_is_camera:
+                    cached.reset(position, orientation, scale, latent, obs)
+                else:
+                    cached.reset(position, orientation, scale, latent, obs, camera_positions, camera_orientations)
                 opt, done = cached, -1  # every iteration of this call is a replay
             else:
                 kw["point_capacity"] = max(4096, -(-n_pts // 4096) * 4096 + 4096)  # room for the next clouds

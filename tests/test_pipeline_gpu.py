@@ -131,3 +131,48 @@ def test_reset_reproduces_a_fresh_optimizer(cuda_device):
     with pytest.raises(RuntimeError):
         make(hyp[0], obs[0]).reset(hyp[1]["position"], hyp[1]["orientation"], 1.0 / hyp[1]["inv_scale"],
                                    torch.zeros(B, 8, device=dev), obs[1])  # no capacity: cloud size is baked in
+
+
+def test_graph_of_the_first_call_serves_later_views(cuda_device):
+    """The view loop (two views with camera poses, with and without a point constraint): the iteration captured
+    by the first call is replayed for later calls with other observations, camera poses and initial estimates,
+    and gives what a pipeline that builds a new optimiser per call gives."""
+    from sdfest_b200.estimation import SDFPipeline
+
+    dev = cuda_device
+    dec, obs = _observations(dev)
+    cfg = {"device": str(dev), "camera": dict(CAMERA), "threshold": THR, "max_iterations": 20,
+           "init": {"backbone_type": "VanillaPointNet", "normalize_pose": True, "head": {"orientation_repr": "quaternion"}},
+           "result_selection_strategy": "best_inlier_ratio"}
+    vae = VAE(dec)
+
+    def cameras(k):  # the second camera a few centimetres / degrees away from the first, differently per call
+        p = torch.tensor([[0.0, 0.0, 0.0], [0.02 + 0.01 * k, -0.01, 0.005 * k]], device=dev)
+        q = torch.nn.functional.normalize(torch.tensor([[0.0, 0.0, 0.0, 1.0], [0.01 * (k + 1), -0.015, 0.005, 1.0]],
+                                                       device=dev), dim=1)
+        return p, q
+
+    for constraint in (None, (torch.tensor([0.0, 0.0, 1.0]), torch.tensor([0.0, 0.0, 1.0]), 0.05)):
+        reuse, fresh = SDFPipeline(cfg, vae, Init(dev)), SDFPipeline(dict(cfg, reuse_graph=False), vae, Init(dev))
+        first_opt = None
+        for k in (0, 1, 2, 1):
+            views = torch.stack([obs[k], obs[(k + 1) % 3]])
+            p, q = cameras(k)
+            a = reuse(views.clone(), views > 0, None, camera_positions=p, camera_orientations=q,
+                      point_constraint=constraint)
+            b = fresh(views.clone(), views > 0, None, camera_positions=p, camera_orientations=q,
+                      point_constraint=constraint)
+            if first_opt is None:
+                first_opt = reuse.last_optimizer
+                assert first_opt._V == 2 and first_opt.point_capacity > 0
+            else:
+                assert reuse.last_optimizer is first_opt  # no new optimiser, no new capture
+                assert fresh.last_optimizer is not first_opt
+            assert first_opt._view_counts == [int((v > 0).sum()) for v in views]
+            for x, y, tol in zip(a, b, (2e-4, 2e-3, 2e-4, 2e-3)):
+                assert tuple(x.shape) == tuple(y.shape)
+                assert float((x - y).abs().max()) <= tol, (k, x, y)
+        if constraint is not None:  # another constraint is another captured launch: a new optimiser
+            other = (constraint[0], torch.tensor([0.0, 1.0, 0.0]), 0.05)
+            reuse(views.clone(), views > 0, None, camera_positions=p, camera_orientations=q, point_constraint=other)
+            assert reuse.last_optimizer is not first_opt
