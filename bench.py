@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--no-ref-ext", action="store_true",
                    help="skip timing the reference CUDA extension (oracle/_ref) beside ours")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--gather-every", type=int, default=5,
+    p.add_argument("--gather-every", type=int, default=10,
                    help="multi-GPU: steps per exchange -- every step's per-hypothesis losses are kept in a ring on "
                         "the device and all-gathered as one [K, hypotheses] block every K steps (1 = every step)")
     p.add_argument("--no-step-graph", action="store_true",
