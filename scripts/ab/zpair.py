@@ -20,6 +20,7 @@ _lib.check(lib.sdfr_zpair_grids(c.grids.data_ptr(), c.R, c.RRR, c.B, zpair.data_
 
 
 def run(fn_name, src, stride, layout, flags=None):
+    flags = (_lib.GRAD_ALL | _lib.ZERO_GRADS) if flags is None else flags
     common = (src.data_ptr(), c.R, stride, layout, c.pos.data_ptr(), c.quat.data_ptr(), c.inv_s.data_ptr(), c.B, c.W,
               c.H, 320.0, 240.0, 320.0, 320.0, c.THR, c.obs.data_ptr(), 0, c.depth.data_ptr(), c.sums[0].data_ptr(),
               c.sums[1].data_ptr())
@@ -27,7 +28,7 @@ def run(fn_name, src, stride, layout, flags=None):
         _lib.check(lib.sdfr_compare_forward(*common, _lib.ZERO_GRADS, c.bounds.data_ptr(), c.st), "fwd")
     else:
         _lib.check(lib.sdfr_compare_fused(*common, c.g_sdf.data_ptr(), c.RRR, c.g_pos.data_ptr(), c.g_quat.data_ptr(),
-                                          c.g_is.data_ptr(), _lib.GRAD_ALL | _lib.ZERO_GRADS, c.bounds.data_ptr(), c.st), "fused")
+                                          c.g_is.data_ptr(), flags, c.bounds.data_ptr(), c.st), "fused")
 
 
 out = {"zpair_floats_per_grid": ZP, "skewed_floats_per_grid": c.SK}
@@ -37,7 +38,9 @@ for name, (src, stride, layout) in (("skewed", (c.skewed, c.SK, 1)), ("zpair", (
     torch.cuda.synchronize()
     res[name] = [t.clone() for t in (c.depth, c.sums, c.g_sdf, c.g_pos, c.g_quat, c.g_is)]
     out[name] = {"fwd_us": c.timed(lambda: run("fwd", src, stride, layout))["median_us"],
-                 "fused_us": c.timed(lambda: run("fused", src, stride, layout))["median_us"]}
+                 "fused_us": c.timed(lambda: run("fused", src, stride, layout))["median_us"],
+                 # what the pose-only loops (fixed grids: C4 sweep, loop.pose_only) launch
+                 "fused_pose_only_us": c.timed(lambda: run("fused", src, stride, layout, 0x0E | _lib.ZERO_GRADS))["median_us"]}
 out["identical_depth"] = bool(torch.equal(res["skewed"][0], res["zpair"][0]))
 out["identical_counts"] = bool(torch.equal(res["skewed"][1][1], res["zpair"][1][1]))
 out["max_rel_grad_diff"] = max(float((a - b).abs().max() / a.abs().max().clamp(min=1e-30))
